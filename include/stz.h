@@ -1,0 +1,122 @@
+/*
+ * stz.h — C ABI of the B200-native StyleTTS-ZS inference hot path
+ * (style-diffusion sampling loop + duration predictor).
+ *
+ * Reference interface this replaces: NONE EXISTS.  ishine/StyleTTS-ZS publishes no inference
+ * code (/root/reference/README.md:15-16, "Inference — Under construction"); the path itself is
+ * described only in the abstract (/root/reference/README.md:5).  The boundary is therefore the
+ * module API that BASELINE.json's north_star dictates —
+ *     sample_style(text_emb, prompt_feats, steps, cfg_scale) / predict_duration(...)
+ * — and every entry point below is what a ctypes/cffi binding of that module API binds
+ * (SURVEY.md §8b).  INTEGRATION.md shows the Python-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary.
+ *   - all functions return 0 on success or a negative stz_status; none throws.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are
+ *     host memory (pinned for best copy throughput).  fp32 unless stated.
+ *   - device entry points enqueue on `cuda_stream` (a cudaStream_t passed as void*) and
+ *     return without synchronising; the caller owns all in/out buffers and keeps them alive
+ *     until the stream is synchronised.  The library owns weights, workspace and CUDA graphs.
+ *   - a handle is bound to one device and is not re-entrant (one host thread at a time).
+ *   - masks are uint8 [B,T] / [B,P], 1 = valid token; text masks must be prefix masks.
+ *   - there is no CPU fallback: stz_create fails with STZ_E_DEVICE on a non-sm_100 device.
+ */
+#ifndef STZ_H_
+#define STZ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STZ_ABI_VERSION 1
+
+typedef enum stz_status {
+  STZ_OK = 0,
+  STZ_E_ARG = -1,      /* null pointer / bad enum / bad size */
+  STZ_E_SHAPE = -2,    /* shape outside what the kernels support */
+  STZ_E_DEVICE = -3,   /* no sm_100 device / driver entry point missing */
+  STZ_E_CUDA = -4,     /* a CUDA call failed; see stz_last_error */
+  STZ_E_NOMEM = -5
+} stz_status;
+
+typedef enum stz_sampler_kind {
+  STZ_SAMPLER_STUDENT = 0, /* distilled few-step student: Euler on Karras(steps) + terminal 0 */
+  STZ_SAMPLER_TEACHER = 1  /* teacher: ADPM2 on Karras(steps+1), 2 denoiser evals per step     */
+} stz_sampler_kind;
+
+/* Field order mirrors styletts-zs_b200/spec.py:StzConfig. */
+typedef struct stz_config {
+  int32_t n_style, d_style, d_model, n_heads, d_ff, n_layers, d_text, d_prompt, d_time;
+  int32_t d_hid, d_sty_tok, n_sp_heads, n_lstm, max_dur;
+  float sigma_data, sigma_max, sigma_min, rho;
+} stz_config;
+
+typedef struct stz_handle stz_handle;
+
+int stz_abi_version(void);
+
+/* Flat fp32 weight blob layout (mirrors spec.py:weight_entries). */
+size_t stz_weights_nfloats(const stz_config* cfg);
+/* Offset (in floats) of a named entry, or -1. */
+int64_t stz_weight_offset(const stz_config* cfg, const char* name);
+
+/* Uploads the blob to `device`, converts the denoiser's GEMM weights to bf16, precomputes the
+ * null-context K/V.  weights_host: fp32 blob of stz_weights_nfloats(cfg) floats. */
+int stz_create(const stz_config* cfg, const float* weights_host, size_t nfloats, int device,
+               stz_handle** out);
+void stz_destroy(stz_handle* h);
+/* Message of the last failure on this handle (h may be NULL: last stz_create failure). */
+const char* stz_last_error(const stz_handle* h);
+
+/* sample_style(text_emb, prompt_feats, steps, cfg_scale): the CFG style-diffusion loop.
+ *   text_emb_dev   [B,T,d_text]     prompt_feats_dev [B,P,d_prompt]
+ *   text_mask_dev  [B,T] u8         prompt_mask_dev  [B,P] u8           (NULL = all valid)
+ *   noise_dev      [n_slices,B,K,Ds], n_slices = 1 (student) or steps+1 (teacher)
+ *   out_style_dev  [B,K,Ds] */
+int stz_sample_style(stz_handle* h, const float* text_emb_dev, const uint8_t* text_mask_dev,
+                     const float* prompt_feats_dev, const uint8_t* prompt_mask_dev,
+                     const float* noise_dev, int B, int T, int P, int steps, float cfg_scale,
+                     int sampler_kind, float* out_style_dev, void* cuda_stream);
+
+/* predict_duration(text_emb, text_mask, style_codes) -> int32 frames per token.
+ *   style_dev [B,K,Ds]; out_dur_dev [B,T] int32; out_presum_dev [B,T] fp32 or NULL (the
+ *   pre-rounding sum of sigmoids, for diagnostics). */
+int stz_predict_duration(stz_handle* h, const float* text_emb_dev, const uint8_t* text_mask_dev,
+                         const float* style_dev, int B, int T, int32_t* out_dur_dev,
+                         float* out_presum_dev, void* cuda_stream);
+
+/* Host-buffer form of the whole path (what a non-CUDA caller binds): copies the inputs H2D,
+ * runs sample_style and (if out_dur_host != NULL) predict_duration on the sampled codes, copies
+ * the results D2H and synchronises.  All pointers are host pointers. */
+int stz_synthesize_host(stz_handle* h, const float* text_emb, const uint8_t* text_mask,
+                        const float* prompt_feats, const uint8_t* prompt_mask, const float* noise,
+                        int B, int T, int P, int steps, float cfg_scale, int sampler_kind,
+                        float* out_style, int32_t* out_dur);
+
+/* ---- introspection / unit-test entry points (not part of the drop-in surface) ---------- */
+
+/* Number of kernels launched by this handle since creation (graph nodes count per replay). */
+int64_t stz_launch_count(const stz_handle* h);
+
+/* Knobs: "use_graph" (0/1, default 1), "gemm_impl" (0 = tcgen05, 1 = SIMT reference kernel),
+ * "lstm_impl" (0 = default).  Returns STZ_E_ARG for unknown keys. */
+int stz_set_option(stz_handle* h, const char* key, int value);
+
+/* Copies the fp32 residual stream h [B*K*2, d_model] (row = (b*K+k)*2 + branch) into
+ * tap_dev after (eval, layer, stage) during eager (use_graph=0) runs; stage 0/1/2 = after the
+ * self-attention / cross-attention / FFN sub-layer, layer == n_layers -> the guided F.
+ * tap_dev = NULL disables. */
+int stz_debug_set_tap(stz_handle* h, int eval, int layer, int stage, float* tap_dev);
+
+/* C[M,N] = A[M,K] · W[N,K]^T + bias, bf16 operands (device), fp32 out.  impl as "gemm_impl". */
+int stz_op_gemm_bf16(const void* A_bf16_dev, const void* W_bf16_dev, const float* bias_dev,
+                     float* C_dev, int M, int N, int K, int impl, int device, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STZ_H_ */

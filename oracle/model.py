@@ -1,0 +1,249 @@
+"""ORACLE (test infrastructure, not product code): fp32 PyTorch CPU restatement of the
+StyleTTS-ZS inference hot path — style denoiser, CFG sampler loop, duration predictor.
+
+PARITY UNPINNED: the reference has no implementation to follow (/root/reference/README.md:15-16);
+this follows SURVEY.md §8(a) rows a-3 .. a-11, which restate /root/reference/README.md:5
+("a diffusion model ... to sample this time-varying style code", "classifier-free guidance",
+"distilled") with the StyleTTS-lineage shapes.  Pinned by analytic KATs (tests/test_oracle_kat.py)
+and frozen fixtures (tests/golden/).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import schedule as S
+
+SAMPLER_STUDENT, SAMPLER_TEACHER = 0, 1
+
+
+def _bf16(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class _Ops:
+    """GEMM operand precision.  emulate_bf16=True rounds tensor-core operands the way the CUDA
+    path does (bf16 operands, fp32 accumulate) — a diagnostic for tests, never the reference."""
+
+    def __init__(self, emulate_bf16: bool):
+        self.emu = emulate_bf16
+
+    def lin(self, x, w, b=None):
+        if self.emu:
+            x, w = _bf16(x), _bf16(w)
+        return F.linear(x, w, b)
+
+    def r(self, x):
+        return _bf16(x) if self.emu else x
+
+
+def layer_norm(x: torch.Tensor) -> torch.Tensor:
+    return F.layer_norm(x, x.shape[-1:], eps=1e-5)
+
+
+def gelu_tanh(x: torch.Tensor) -> torch.Tensor:
+    return F.gelu(x, approximate="tanh")
+
+
+def masked_mean(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    m = mask.to(x.dtype)[..., None]
+    return (x * m).sum(1) / m.sum(1).clamp(min=1.0)
+
+
+def attention(q, k, v, n_heads: int, key_mask: Optional[torch.Tensor], ops: _Ops):
+    """q [N,Lq,d], k/v [N,Lk,d], key_mask [N,Lk] bool (True = attend).  a-5."""
+    N, Lq, d = q.shape
+    dh = d // n_heads
+    qh = ops.r(q).view(N, Lq, n_heads, dh).transpose(1, 2)
+    kh = ops.r(k).view(N, -1, n_heads, dh).transpose(1, 2)
+    vh = ops.r(v).view(N, -1, n_heads, dh).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) / math.sqrt(dh)
+    if key_mask is not None:
+        s = s.masked_fill(~key_mask[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    if ops.emu:
+        # CUDA path: P is rounded to bf16 for the PV MMA, the row sum stays fp32
+        e = torch.exp(s - s.amax(-1, keepdim=True))
+        o = (_bf16(e) @ vh) / e.sum(-1, keepdim=True)
+    else:
+        o = p @ vh
+    return o.transpose(1, 2).reshape(N, Lq, d)
+
+
+class Conditioning:
+    """a-3: everything that does not depend on the sampler state x."""
+
+    def __init__(self, cfg, W: Dict[str, torch.Tensor], text_emb, text_mask, prompt_feats, prompt_mask,
+                 ops: _Ops):
+        B = text_emb.shape[0]
+        self.B = B
+        ct = layer_norm(ops.lin(text_emb, W["ctx_text.w"], W["ctx_text.b"]) + W["type_emb"][0])
+        cp = layer_norm(ops.lin(prompt_feats, W["ctx_prompt.w"], W["ctx_prompt.b"]) + W["type_emb"][1])
+        cn = layer_norm(W["null_tok"] + W["type_emb"][1]).view(1, 1, -1).expand(B, 1, -1)
+        # cond branch: [text ; prompt], uncond branch: [text ; null token]
+        self.ctx = (torch.cat([ct, cp], 1), torch.cat([ct, cn], 1))
+        self.ctx_mask = (torch.cat([text_mask, prompt_mask], 1),
+                         torch.cat([text_mask, torch.ones(B, 1, dtype=torch.bool)], 1))
+        pt = F.linear(masked_mean(text_emb, text_mask), W["ptext.w"], W["ptext.b"])      # fp32 on both sides
+        pp = F.linear(masked_mean(prompt_feats, prompt_mask), W["pprompt.w"], W["pprompt.b"])
+        self.pooled = (pt + pp, pt + W["null_pp"][None, :])
+        # per-layer cross-attention K/V for both branches
+        self.kv = []
+        for l in range(cfg.n_layers):
+            w, b = W[f"l{l}.kv2.w"], W[f"l{l}.kv2.b"]
+            self.kv.append(tuple(ops.lin(c, w, b) for c in self.ctx))
+
+
+def denoiser_F(cfg, W, x_in: torch.Tensor, c_noise: float, cond: Conditioning, branch: int,
+               ops: _Ops) -> torch.Tensor:
+    """a-4: F_theta(x_in, c_noise | text, prompt-or-null).  x_in [B,K,Ds] -> [B,K,Ds]."""
+    d, L, H = cfg.d_model, cfg.n_layers, cfg.n_heads
+    feat = torch.tensor(S.time_features(c_noise, cfg.d_time), dtype=torch.float64).to(torch.float32)
+    t = F.linear(F.silu(F.linear(feat, W["time.w1"], W["time.b1"])), W["time.w2"], W["time.b2"])
+    c = F.silu(t[None, :] + cond.pooled[branch])                       # [B,d]
+    mod = ops.lin(c, W["mod.w"], W["mod.b"])                           # [B,(9L+2)d]
+
+    def m(i):  # modulation chunk i -> [B,1,d]
+        return mod[:, i * d:(i + 1) * d][:, None, :]
+
+    h = ops.lin(x_in, W["in.w"], W["in.b"]) + W["pos"][None]
+    for l in range(L):
+        p, o = f"l{l}.", 9 * l
+        u = layer_norm(h) * (1 + m(o + 1)) + m(o + 0)
+        qkv = ops.lin(u, W[p + "qkv.w"], W[p + "qkv.b"])
+        a = attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], H, None, ops)
+        h = h + m(o + 2) * ops.lin(a, W[p + "o.w"], W[p + "o.b"])
+        u = layer_norm(h) * (1 + m(o + 4)) + m(o + 3)
+        q = ops.lin(u, W[p + "q2.w"], W[p + "q2.b"])
+        kv = cond.kv[l][branch]
+        a = attention(q, kv[..., :d], kv[..., d:], H, cond.ctx_mask[branch], ops)
+        h = h + m(o + 5) * ops.lin(a, W[p + "o2.w"], W[p + "o2.b"])
+        u = layer_norm(h) * (1 + m(o + 7)) + m(o + 6)
+        f = gelu_tanh(ops.lin(u, W[p + "ff1.w"], W[p + "ff1.b"]))
+        h = h + m(o + 8) * ops.lin(f, W[p + "ff2.w"], W[p + "ff2.b"])
+    u = layer_norm(h) * (1 + m(9 * L + 1)) + m(9 * L)
+    return ops.lin(u, W["out.w"], W["out.b"])
+
+
+def guided_denoise(cfg, W, x, sigma: float, cond: Conditioning, cfg_scale: float, ops: _Ops,
+                   F_override=None):
+    """a-2 + CFG (README.md:5 'classifier-free guidance'): D = c_skip x + c_out (F_u + w (F_c - F_u))."""
+    c_skip, c_out, c_in, c_noise = S.edm_precond(sigma, cfg.sigma_data)
+    if F_override is not None:
+        Fg = F_override(c_in * x, sigma)
+    else:
+        Fc = denoiser_F(cfg, W, c_in * x, c_noise, cond, 0, ops)
+        Fu = denoiser_F(cfg, W, c_in * x, c_noise, cond, 1, ops)
+        Fg = Fu + cfg_scale * (Fc - Fu)
+    return c_skip * x + c_out * Fg
+
+
+def sample_loop(cfg, denoise, noise: torch.Tensor, steps: int, sampler: int) -> torch.Tensor:
+    """a-6/a-7: the sampler loop around D(x, sigma) = denoise(x, sigma)."""
+    if sampler == SAMPLER_STUDENT:
+        sig = S.student_sigmas(steps, cfg)
+        x = sig[0] * noise[0]
+        for i in range(steps):
+            D = denoise(x, sig[i])
+            d = (x - D) / sig[i]
+            x = x + d * (sig[i + 1] - sig[i])
+        return x
+    sig = S.teacher_sigmas(steps, cfg)
+    x = sig[0] * noise[0]
+    for i in range(steps):
+        s, sn = sig[i], sig[i + 1]
+        s_up, s_down, s_mid = S.adpm2_sigmas(s, sn)
+        d = (x - denoise(x, s)) / s
+        x_mid = x + d * (s_mid - s)
+        d_mid = (x_mid - denoise(x_mid, s_mid)) / s_mid
+        x = x + d_mid * (s_down - s) + s_up * noise[i + 1]
+    return x
+
+
+class OraclePath:
+    """Same module API as the CUDA path, CPU fp32."""
+
+    def __init__(self, cfg, weights: torch.Tensor, emulate_bf16: bool = False):
+        from styletts_zs_b200.spec import view_weights
+        self.cfg = cfg
+        self.W = view_weights(cfg, weights.detach().to(torch.float32).cpu())
+        self.ops = _Ops(emulate_bf16)
+        self._lstm = None
+
+    # ---- a-7 ------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample_style(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
+                     prompt_mask=None, noise=None, sampler="student") -> torch.Tensor:
+        cfg = self.cfg
+        B, T, _ = text_emb.shape
+        P = prompt_feats.shape[1]
+        kind = SAMPLER_TEACHER if sampler in ("teacher", SAMPLER_TEACHER) else SAMPLER_STUDENT
+        if text_mask is None:
+            text_mask = torch.ones(B, T, dtype=torch.bool)
+        if prompt_mask is None:
+            prompt_mask = torch.ones(B, P, dtype=torch.bool)
+        if noise is None:
+            raise ValueError("noise tensor is an input (identical seeds == identical noise tensors)")
+        cond = Conditioning(cfg, self.W, text_emb.float(), text_mask.bool(), prompt_feats.float(),
+                            prompt_mask.bool(), self.ops)
+        den = lambda x, s: guided_denoise(cfg, self.W, x, s, cond, cfg_scale, self.ops)
+        return sample_loop(cfg, den, noise.float(), steps, kind)
+
+    # ---- a-8 .. a-11 ----------------------------------------------------------------
+    def _lstms(self):
+        if self._lstm is None:
+            cfg, W = self.cfg, self.W
+            mods = []
+            for l in range(cfg.n_lstm):
+                m = torch.nn.LSTM(cfg.d_hid + cfg.d_sty_tok, cfg.h_lstm, batch_first=True, bidirectional=True)
+                with torch.no_grad():
+                    for dr, suf in (("f", ""), ("r", "_reverse")):
+                        p = f"lstm{l}.{dr}."
+                        getattr(m, "weight_ih_l0" + suf).copy_(W[p + "w_ih"])
+                        getattr(m, "weight_hh_l0" + suf).copy_(W[p + "w_hh"])
+                        getattr(m, "bias_ih_l0" + suf).copy_(W[p + "b_ih"])
+                        getattr(m, "bias_hh_l0" + suf).copy_(W[p + "b_hh"])
+                mods.append(m.eval())
+            self._lstm = mods
+        return self._lstm
+
+    @torch.no_grad()
+    def style_per_token(self, text_emb, style_codes):
+        """a-8: s_tok = MHA(q = text, kv = style codes), n_sp_heads heads."""
+        W, cfg = self.W, self.cfg
+        q = F.linear(text_emb, W["sp.q.w"], W["sp.q.b"])
+        k = F.linear(style_codes, W["sp.k.w"], W["sp.k.b"])
+        v = F.linear(style_codes, W["sp.v.w"], W["sp.v.b"])
+        a = attention(q, k, v, cfg.n_sp_heads, None, _Ops(False))
+        return F.linear(a, W["sp.o.w"], W["sp.o.b"])
+
+    @torch.no_grad()
+    def predict_duration(self, text_emb, style_codes, *, text_mask=None, return_presum=False):
+        cfg, W = self.cfg, self.W
+        text_emb, style_codes = text_emb.float(), style_codes.float()
+        B, T, _ = text_emb.shape
+        if text_mask is None:
+            text_mask = torch.ones(B, T, dtype=torch.bool)
+        text_mask = text_mask.bool()
+        lens = text_mask.sum(1)
+        # masks are prefix masks (padding at the end), as produced by a length vector
+        assert bool((text_mask == (torch.arange(T)[None] < lens[:, None])).all()), "text_mask must be a prefix mask"
+        mf = text_mask.to(torch.float32)[..., None]
+        s_tok = self.style_per_token(text_emb, style_codes)
+        x = text_emb
+        for l, lstm in enumerate(self._lstms()):
+            inp = torch.cat([x, s_tok], -1)
+            packed = torch.nn.utils.rnn.pack_padded_sequence(inp, lens.cpu(), batch_first=True, enforce_sorted=False)
+            out, _ = lstm(packed)
+            x, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=T)
+            if l < cfg.n_lstm - 1:
+                gb = F.linear(s_tok, W[f"adaln{l}.w"], W[f"adaln{l}.b"])
+                x = layer_norm(x) * (1 + gb[..., :cfg.d_hid]) + gb[..., cfg.d_hid:]
+                x = x * mf
+        s = torch.sigmoid(F.linear(x, W["dur.w"], W["dur.b"])).sum(-1)           # a-10
+        dur = (torch.round(s).clamp(min=1) * mf[..., 0]).to(torch.int32)        # half-to-even
+        return (dur, s) if return_presum else dur

@@ -1,0 +1,207 @@
+// Fused attention over the fixed-length style-code sequence.
+//
+// One CTA per (utterance b, head): the 2*K query rows of utterance b (both CFG branches, R layout,
+// contiguous) against a "virtual" key sequence assembled from up to three segments:
+//   self-attention : the utterance's own 2*K rows, a key is visible to queries of the same branch;
+//   cross-attention: [text keys (shared by both branches, padding-masked) ; prompt keys (cond branch
+//                    only, masked) ; the null-prompt key (uncond branch only)].
+// Flash-style streaming over 64-key blocks with an fp32 online softmax; QK^T and PV run on the
+// legacy warp-level tensor path (mma.sync m16n8k16 bf16 -> fp32).  This is ~4 % of the
+// denoiser's flops; the tcgen05 budget goes to the GEMMs (gemm.cuh).
+#pragma once
+#include "ptx.cuh"
+
+namespace stz {
+
+enum KeyRule : int { KEY_ALL = 0, KEY_COND = 1, KEY_UNCOND = 2, KEY_SAME_BRANCH = 3 };
+
+struct AttnSeg {
+  const __nv_bfloat16* k;  // first key row of utterance 0 (already offset to this layer / K or V columns: see k_col)
+  const __nv_bfloat16* v;
+  int ld;                  // row stride in elements
+  int n;                   // keys per utterance in this segment
+  int rows_per_utt;        // row advance per utterance (0 = shared by all utterances)
+  const uint8_t* mask;     // [B, n] 1 = valid, or nullptr
+  int rule;
+};
+
+struct AttnParams {
+  const __nv_bfloat16* q;  // R layout, head h at columns h*64
+  int ldq;
+  __nv_bfloat16* out;      // R layout [R, ldo]
+  int ldo;
+  int n_q;                 // 2 * n_style (<= 128)
+  int nseg;
+  AttnSeg seg[3];
+  float scale_log2;        // log2(e) / sqrt(d_head)
+};
+
+constexpr int ATT_DH = 64;
+constexpr int ATT_KB = 64;       // keys per block
+constexpr int ATT_LDS = 72;      // padded smem row (bf16 elements): 144 B, conflict-free for the fragment loads
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+
+__global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[ATT_KB][ATT_LDS];
+  __shared__ __align__(16) __nv_bfloat16 Vs[ATT_KB][ATT_LDS];
+  __shared__ uint8_t kvis[ATT_KB];  // bit0: visible to cond (even) query rows, bit1: to uncond (odd) rows
+
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;  // query rows inside the utterance
+  const size_t qbase = static_cast<size_t>(b) * p.n_q;
+
+  // Q fragments (A operand, 16 x 64 per warp)
+  uint32_t qa[4][4];
+  {
+    const __nv_bfloat16* q0 = p.q + (qbase + row0) * p.ldq + head * ATT_DH;
+    const __nv_bfloat16* q1 = p.q + (qbase + row1) * p.ldq + head * ATT_DH;
+    const bool v0 = row0 < p.n_q, v1 = row1 < p.n_q;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      qa[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + t * 2) : 0u;
+      qa[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + t * 2) : 0u;
+      qa[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8 + t * 2) : 0u;
+      qa[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + t * 2) : 0u;
+    }
+  }
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+
+  int n_total = 0;
+  for (int s = 0; s < p.nseg; ++s) n_total += p.seg[s].n;
+
+  for (int kb0 = 0; kb0 < n_total; kb0 += ATT_KB) {
+    __syncthreads();
+    // cooperative load of 64 virtual keys: 8 x 16-byte chunks per key row for K and for V
+    for (int i = threadIdx.x; i < ATT_KB * 8; i += blockDim.x) {
+      const int kr = i >> 3, ch = i & 7;
+      int vk = kb0 + kr;
+      uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
+      uint8_t vis = 0;
+      if (vk < n_total) {
+        int s = 0;
+        while (vk >= p.seg[s].n) { vk -= p.seg[s].n; ++s; }
+        const AttnSeg& sg = p.seg[s];
+        const bool ok = sg.mask == nullptr || sg.mask[static_cast<size_t>(b) * sg.n + vk] != 0;
+        if (ok) {
+          const size_t r = static_cast<size_t>(b) * sg.rows_per_utt + vk;
+          kq = *reinterpret_cast<const uint4*>(sg.k + r * sg.ld + head * ATT_DH + ch * 8);
+          vq = *reinterpret_cast<const uint4*>(sg.v + r * sg.ld + head * ATT_DH + ch * 8);
+          vis = sg.rule == KEY_ALL ? 3 : sg.rule == KEY_COND ? 1 : sg.rule == KEY_UNCOND ? 2 : ((vk & 1) ? 2 : 1);
+        }
+      }
+      *reinterpret_cast<uint4*>(&Ks[kr][ch * 8]) = kq;
+      *reinterpret_cast<uint4*>(&Vs[kr][ch * 8]) = vq;
+      if (ch == 0) kvis[kr] = vis;
+    }
+    __syncthreads();
+
+    // S = Q K^T  (16 x 64 per warp)
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][kk * 16 + t * 2]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][kk * 16 + 8 + t * 2]);
+        mma_bf16_16816(sc[nt], qa[kk], b0, b1);
+      }
+    }
+    // scale, mask, block row max
+    float bm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint8_t vis = kvis[nt * 8 + t * 2 + j];
+        const bool s0 = (vis >> (row0 & 1)) & 1, s1 = (vis >> (row1 & 1)) & 1;
+        sc[nt][j] = s0 ? sc[nt][j] * p.scale_log2 : -INFINITY;
+        sc[nt][2 + j] = s1 ? sc[nt][2 + j] * p.scale_log2 : -INFINITY;
+        bm[0] = fmaxf(bm[0], sc[nt][j]);
+        bm[1] = fmaxf(bm[1], sc[nt][2 + j]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
+      bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
+    }
+    float alpha[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mnew[r] = fmaxf(mrow[r], bm[r]);
+      const float base = mnew[r] == -INFINITY ? 0.f : mnew[r];
+      alpha[r] = exp2f(mrow[r] - base);  // mrow = -inf -> 0
+      mrow[r] = mnew[r];
+      mnew[r] = base;
+      lrow[r] *= alpha[r];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sc[nt][j] = exp2f(sc[nt][j] - mnew[0]);
+        sc[nt][2 + j] = exp2f(sc[nt][2 + j] - mnew[1]);
+        lrow[0] += sc[nt][j];
+        lrow[1] += sc[nt][2 + j];
+      }
+    }
+    // O += P V  (P rounded to bf16 as the MMA A operand; row sums stay fp32)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[1] = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
+      pa[2] = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+      pa[3] = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp) {  // two 8-wide dim tiles per ldmatrix.x4
+        const int mi = lane >> 3, r = lane & 7;
+        const uint32_t addr = smem_u32(&Vs[kk * 16 + (mi & 1) * 8 + r][ntp * 16 + (mi >> 1) * 8]);
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, addr);
+        mma_bf16_16816(o[2 * ntp], pa, vb[0], vb[1]);
+        mma_bf16_16816(o[2 * ntp + 1], pa, vb[2], vb[3]);
+      }
+    }
+  }
+  // finalize
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+  const float inv0 = lrow[0] > 0.f ? 1.f / lrow[0] : 0.f, inv1 = lrow[1] > 0.f ? 1.f / lrow[1] : 0.f;
+  if (row0 < p.n_q) {
+    __nv_bfloat16* op = p.out + (qbase + row0) * p.ldo + head * ATT_DH + t * 2;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
+  }
+  if (row1 < p.n_q) {
+    __nv_bfloat16* op = p.out + (qbase + row1) * p.ldo + head * ATT_DH + t * 2;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
+  }
+}
+
+}  // namespace stz

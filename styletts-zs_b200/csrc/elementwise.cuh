@@ -1,0 +1,131 @@
+// HBM-bound fp32 kernels of the path: casts + masked pooling, AdaLN (LayerNorm + modulate),
+// conditioning vector, sampler state initialisation.  128-bit loads, one warp per row.
+#pragma once
+#include "ptx.cuh"
+
+namespace stz {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// x [B,T,D] fp32 -> xb [B,T,D] bf16 and pooled [B,D] = masked mean over T (a-3).  grid = B.
+__global__ void __launch_bounds__(256) cast_pool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
+                                                        __nv_bfloat16* __restrict__ xb, float* __restrict__ pooled,
+                                                        int T, int D) {
+  const int b = blockIdx.x;
+  const int nvec = D >> 2;
+  const float* xr = x + static_cast<size_t>(b) * T * D;
+  __nv_bfloat16* br = xb + static_cast<size_t>(b) * T * D;
+  int cnt = 0;
+  for (int t = 0; t < T; ++t) cnt += (mask == nullptr || mask[static_cast<size_t>(b) * T + t]) ? 1 : 0;
+  const float inv = 1.0f / static_cast<float>(cnt > 0 ? cnt : 1);
+  for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xr + static_cast<size_t>(t) * D) + c);
+      uint2 u;
+      u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(br + static_cast<size_t>(t) * D + c * 4) = u;
+      if (mask == nullptr || mask[static_cast<size_t>(b) * T + t]) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    }
+    *reinterpret_cast<float4*>(pooled + static_cast<size_t>(b) * D + c * 4) =
+        make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+}
+
+// AdaLN: out_bf16[r] = LN(h[r]) * (1 + scale[seq(r)]) + shift[seq(r)]; mod == nullptr -> plain LN.
+// seq(r) = (r / rows_per_utt) * 2 + (r & 1)   (R layout).  One warp per row, D = 128 * VPL.
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h, int rows, const float* __restrict__ mod,
+                                                     int n_mod, int shift_off, int scale_off, int rows_per_utt,
+                                                     __nv_bfloat16* __restrict__ out) {
+  constexpr int D = 128 * VPL;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* hr = reinterpret_cast<const float4*>(h + static_cast<size_t>(row) * D);
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = hr[i * 32 + lane];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+  const float* mrow = nullptr;
+  if (mod != nullptr) mrow = mod + static_cast<size_t>((row / rows_per_utt) * 2 + (row & 1)) * n_mod;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float4 y = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);
+    if (mrow != nullptr) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + scale_off) + i * 32 + lane);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + shift_off) + i * 32 + lane);
+      y.x = y.x * (1.f + sc.x) + sh.x; y.y = y.y * (1.f + sc.y) + sh.y;
+      y.z = y.z * (1.f + sc.z) + sh.z; y.w = y.w * (1.f + sc.w) + sh.w;
+    }
+    uint2 u;
+    u.x = pack_bf16(y.x, y.y); u.y = pack_bf16(y.z, y.w);
+    *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D + (i * 32 + lane) * 4) = u;
+  }
+}
+
+// c[e, s, :] = bf16(SiLU(t_emb[e] + ptext[b] + (branch ? null_pp : pprompt[b])))   s = 2b + branch
+__global__ void __launch_bounds__(256) cvec_kernel(const float* __restrict__ temb, const float* __restrict__ pt,
+                                                   const float* __restrict__ pp, const float* __restrict__ null_pp,
+                                                   __nv_bfloat16* __restrict__ cvec, int E, int n_seq, int D) {
+  const size_t total = static_cast<size_t>(E) * n_seq * D;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D);
+    const int s = static_cast<int>((i / D) % n_seq);
+    const int e = static_cast<int>(i / (static_cast<size_t>(D) * n_seq));
+    const int b = s >> 1;
+    const float p2 = (s & 1) ? null_pp[c] : pp[static_cast<size_t>(b) * D + c];
+    cvec[i] = __float2bfloat16(silu(temb[static_cast<size_t>(e) * D + c] + pt[static_cast<size_t>(b) * D + c] + p2));
+  }
+}
+
+// x = sigma0 * noise0 ; xin rows 2j, 2j+1 = bf16(c_in0 * x[j])
+__global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict__ noise0, float* __restrict__ x,
+                                                         __nv_bfloat16* __restrict__ xin, size_t n_rows, int D,
+                                                         float sigma0, float cin0) {
+  const size_t nvec = n_rows * (D >> 2);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t j = i / (D >> 2);
+    const int c = static_cast<int>(i % (D >> 2)) * 4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(noise0) + i);
+    v.x *= sigma0; v.y *= sigma0; v.z *= sigma0; v.w *= sigma0;
+    reinterpret_cast<float4*>(x)[i] = v;
+    uint2 u;
+    u.x = pack_bf16(cin0 * v.x, cin0 * v.y); u.y = pack_bf16(cin0 * v.z, cin0 * v.w);
+    *reinterpret_cast<uint2*>(xin + (2 * j) * D + c) = u;
+    *reinterpret_cast<uint2*>(xin + (2 * j + 1) * D + c) = u;
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+
+// y[i] = a[i] + b[i % nb]   (bias folding at create time)
+__global__ void __launch_bounds__(256) add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                                      size_t n, size_t nb) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    y[i] = a[i] + b[i % nb];
+}
+
+}  // namespace stz

@@ -1,0 +1,842 @@
+// libstz.so — C ABI (include/stz.h) of the B200-native StyleTTS-ZS inference hot path.
+// Host orchestration: weight upload/conversion, workspace arena, conditioning prep, the denoiser
+// evaluation loop captured as one CUDA graph per (B, T, P, evals, sampler), the duration
+// predictor, and the host-buffer end-to-end entry point.  Kernels live in the *.cuh files.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/stz.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "predictor.cuh"
+#include "stz_layout.h"
+
+using namespace stz;
+typedef __nv_bfloat16 bf16;
+
+static std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct Workspace {
+  int B = 0, T = 0, P = 0, E = 0, noise_slices = 0;
+  char* base = nullptr;
+  size_t bytes = 0;
+  // conditioning
+  bf16 *text_bf, *prompt_bf, *ctx_text, *ctx_prompt, *kv_text, *kv_prompt, *cvec;
+  float *pool_text, *pool_prompt, *pt, *pp, *ctx_pre, *tfeat, *t1, *temb, *coef;
+  // denoiser
+  float *mod, *x, *xmid, *h, *noise;
+  bf16 *xin, *u, *qkv, *att, *ffh;
+  // predictor
+  float *sq, *sk, *sv, *sa, *stok, *G, *xa, *xb, *gb;
+  int* lens;
+  // host-call staging (stz_synthesize_host)
+  float *st_text, *st_prompt, *st_noise, *st_style;
+  uint8_t *st_tmask, *st_pmask, *hs_tmask, *hs_pmask;
+  int32_t* st_dur;
+};
+
+struct stz_handle {
+  stz_config cfg;
+  int device = 0;
+  std::string err;
+  std::vector<WeightEntry> layout;
+  std::map<std::string, size_t> off;
+  size_t n_floats = 0;
+  float* w32 = nullptr;   // fp32 blob on device
+  bf16* wbf = nullptr;    // the same blob rounded to bf16 (same offsets): tensor-core operands
+  float *ctx_text_b = nullptr, *ctx_prompt_b = nullptr;  // bias + type embedding
+  bf16* kv_null = nullptr;                               // [1, L*2d] K/V of the null-prompt token
+  float* whhT = nullptr;                                 // [n_lstm][2][h][4h]
+  float* lstm_b = nullptr;                               // [n_lstm][2][4h] = b_ih + b_hh
+  Workspace ws;
+  cudaStream_t stream = nullptr;      // internal stream (create-time work, host entry point, capture)
+  std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
+  int use_graph = 1, gemm_impl = 0;
+  int64_t launches = 0;
+  int cur_launches = 0;  // launches issued since the counter was last sampled (capture bookkeeping)
+  int tap_eval = -1, tap_layer = -1, tap_stage = -1;
+  float* tap_buf = nullptr;
+  bool capturing = false;
+};
+
+static int fail(stz_handle* H, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (H) H->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(H, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(H, STZ_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define KCHECK(H)                                                                                     \
+  do {                                                                                                \
+    ++(H)->cur_launches;                                                                              \
+    cudaError_t e_ = cudaGetLastError();                                                              \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(H, STZ_E_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define RET(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int ew_grid(size_t n, int per_block = 256) {
+  size_t g = (n + per_block - 1) / per_block;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched at run time: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+// bf16 row-major [rows, cols] with row stride ld (elements); box = box_rows x 64 columns, 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * sizeof(bf16)};
+  cuuint32_t box[2] = {GEMM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM launchers
+// ------------------------------------------------------------------------------------------
+constexpr int GEMM_BN = 128;
+constexpr int GEMM_STAGES = 4;
+
+template <int EPI>
+static int launch_gemm_tc(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W,
+                          const GemmParams& p) {
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
+      make_tmap(&tb, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, GEMM_BN))
+    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", p.M, p.N, p.K);
+  constexpr int smem = gemm_smem_bytes<GEMM_BN, GEMM_STAGES>();
+  dim3 grid(p.N / GEMM_BN, cdiv(p.M, GEMM_BM));
+  gemm_tc_kernel<GEMM_BN, EPI, GEMM_STAGES><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
+  if (H) { KCHECK(H); } else if (cudaGetLastError() != cudaSuccess) return STZ_E_CUDA;
+  return 0;
+}
+
+template <int EPI>
+static cudaError_t set_gemm_attr() {
+  return cudaFuncSetAttribute(gemm_tc_kernel<GEMM_BN, EPI, GEMM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              gemm_smem_bytes<GEMM_BN, GEMM_STAGES>());
+}
+// Per-device opt-in to > 48 KB dynamic shared memory; done once per handle, never during graph capture.
+static cudaError_t init_kernel_attrs() {
+  cudaError_t e;
+  if ((e = set_gemm_attr<EPI_F32>()) != cudaSuccess) return e;
+  if ((e = set_gemm_attr<EPI_F32_POS>()) != cudaSuccess) return e;
+  if ((e = set_gemm_attr<EPI_BF16>()) != cudaSuccess) return e;
+  if ((e = set_gemm_attr<EPI_GELU_BF16>()) != cudaSuccess) return e;
+  if ((e = set_gemm_attr<EPI_GATE_RES>()) != cudaSuccess) return e;
+  if ((e = set_gemm_attr<EPI_SAMPLER>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+template <int EPI>
+static int launch_gemm_simt(stz_handle* H, cudaStream_t st, const bf16* A, int lda, const bf16* W, const GemmParams& p) {
+  dim3 grid(p.N / 32, cdiv(p.M, 128));
+  gemm_simt_kernel<EPI><<<grid, 128, 0, st>>>(A, lda, W, p);
+  if (H) { KCHECK(H); } else if (cudaGetLastError() != cudaSuccess) return STZ_E_CUDA;
+  return 0;
+}
+
+template <int EPI>
+static int gemm(stz_handle* H, cudaStream_t st, int impl, const bf16* A, int lda, int a_rows, const bf16* W,
+                const GemmParams& p) {
+  if (p.N % GEMM_BN != 0 || p.K % GEMM_BK != 0 || p.M <= 0)
+    return fail(H, STZ_E_SHAPE, "gemm shape M=%d N=%d K=%d unsupported (N %% 128, K %% 64)", p.M, p.N, p.K);
+  return impl == 0 ? launch_gemm_tc<EPI>(H, st, A, lda, a_rows, W, p) : launch_gemm_simt<EPI>(H, st, A, lda, W, p);
+}
+
+static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, int ld1, int K1, const float* X2, int ld2,
+                      int K2, const float* W, const float* b, float* Y, int ldy, int M, int N) {
+  dim3 grid(cdiv(N, 64), cdiv(M, 64));
+  if (act == ACT_SILU)
+    linear_f32_kernel<ACT_SILU><<<grid, 256, 0, st>>>(X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
+  else
+    linear_f32_kernel<ACT_NONE><<<grid, 256, 0, st>>>(X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
+  KCHECK(H);
+  return 0;
+}
+
+static int ln_mod(stz_handle* H, cudaStream_t st, const float* h, int rows, int D, const float* mod, int n_mod,
+                  int shift_off, int scale_off, int rows_per_utt, bf16* out) {
+  dim3 grid(cdiv(rows, 8));
+  switch (D / 128) {
+    case 1: ln_mod_kernel<1><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
+    case 2: ln_mod_kernel<2><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
+    case 4: ln_mod_kernel<4><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
+    case 8: ln_mod_kernel<8><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
+    default: return fail(H, STZ_E_SHAPE, "d_model %d unsupported by ln_mod", D);
+  }
+  KCHECK(H);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers over the handle
+// ------------------------------------------------------------------------------------------
+static const float* W32(const stz_handle* H, const std::string& name) { return H->w32 + H->off.at(name); }
+static const bf16* WBF(const stz_handle* H, const std::string& name) { return H->wbf + H->off.at(name); }
+
+static int check_config(const stz_config& c) {
+  if (c.n_heads <= 0 || c.d_model != c.n_heads * 64) return -1;            // d_head == 64 (attention.cuh)
+  if (c.d_model % 128 || c.d_ff % 128 || c.d_style % 128) return -1;       // N tiles of 128
+  if (c.d_text % 64 || c.d_prompt % 64 || c.d_model % 64 || c.d_ff % 64 || c.d_style % 64) return -1;  // K tiles of 64
+  if (c.d_model > 1024 || c.d_hid > 1024 || c.d_hid % 128) return -1;      // warp-per-row kernels
+  if (c.n_style < 1 || c.n_style > 64) return -1;                          // 2K query rows <= 128
+  if (c.d_hid != c.d_text) return -1;                                      // x0 = text_emb
+  if (c.n_sp_heads <= 0 || c.d_sty_tok != c.n_sp_heads * 32) return -1;    // lane = channel
+  if (c.d_hid / 2 * 4 > 1024 || (c.d_hid / 2) % 4) return -1;              // lstm block = 4h threads
+  if (c.n_lstm < 1 || c.n_layers < 1 || c.max_dur < 1 || c.d_time < 2 || c.d_time % 2) return -1;
+  return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise_slices) {
+  Workspace& w = H->ws;
+  if (w.base && B <= w.B && T <= w.T && P <= w.P && E <= w.E && noise_slices <= w.noise_slices) return 0;
+  // grow monotonically; all cached graphs point into the old arena
+  for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
+  H->graphs.clear();
+  if (w.base) { CK(H, cudaDeviceSynchronize()); CK(H, cudaFree(w.base)); w.base = nullptr; }
+  B = B > w.B ? B : w.B; T = T > w.T ? T : w.T; P = P > w.P ? P : w.P; E = E > w.E ? E : w.E;
+  noise_slices = noise_slices > w.noise_slices ? noise_slices : w.noise_slices;
+  const stz_config& c = H->cfg;
+  const size_t d = c.d_model, Ds = c.d_style, L = c.n_layers, K = c.n_style, n_mod = (9 * L + 2) * d;
+  const size_t BT = (size_t)B * T, BP = (size_t)B * P, BK = (size_t)B * K, R = 2 * BK, NS = 2 * (size_t)B;
+  const size_t ds = c.d_sty_tok, dh = c.d_hid, h8 = 4 * dh;  // 8h = 4 * d_hid
+  size_t off = 0;
+  std::vector<std::pair<void**, size_t>> plan;
+  auto want = [&](void** p, size_t bytes) { plan.push_back({p, off}); off = align_up(off + bytes, 1024); };
+#define WANT(field, count, type) want((void**)&w.field, (size_t)(count) * sizeof(type))
+  WANT(text_bf, BT * c.d_text, bf16); WANT(prompt_bf, BP * c.d_prompt, bf16);
+  WANT(ctx_text, BT * d, bf16); WANT(ctx_prompt, BP * d, bf16);
+  WANT(kv_text, BT * L * 2 * d, bf16); WANT(kv_prompt, BP * L * 2 * d, bf16);
+  WANT(cvec, (size_t)E * NS * d + 128 * d, bf16);  // + one tile of slack rows for the last eval's TMA box
+  WANT(pool_text, (size_t)B * c.d_text, float); WANT(pool_prompt, (size_t)B * c.d_prompt, float);
+  WANT(pt, (size_t)B * d, float); WANT(pp, (size_t)B * d, float);
+  WANT(ctx_pre, (BT > BP ? BT : BP) * d, float);
+  WANT(tfeat, (size_t)E * c.d_time, float); WANT(t1, (size_t)E * d, float); WANT(temb, (size_t)E * d, float);
+  WANT(coef, (size_t)E * 8, float);
+  WANT(mod, NS * n_mod, float); WANT(x, BK * Ds, float); WANT(xmid, BK * Ds, float); WANT(h, R * d, float);
+  WANT(noise, (size_t)noise_slices * BK * Ds, float);
+  WANT(xin, R * Ds, bf16); WANT(u, R * d, bf16); WANT(qkv, R * 3 * d, bf16); WANT(att, R * d, bf16);
+  WANT(ffh, R * c.d_ff, bf16);
+  WANT(sq, BT * ds, float); WANT(sk, BK * ds, float); WANT(sv, BK * ds, float); WANT(sa, BT * ds, float);
+  WANT(stok, BT * ds, float); WANT(G, BT * h8, float); WANT(xa, BT * dh, float); WANT(xb, BT * dh, float);
+  WANT(gb, BT * 2 * dh, float); WANT(lens, B, int);
+  WANT(st_text, BT * c.d_text, float); WANT(st_prompt, BP * c.d_prompt, float);
+  WANT(st_noise, (size_t)(noise_slices > 1 ? noise_slices : 1) * BK * Ds, float); WANT(st_style, BK * Ds, float);
+  WANT(st_tmask, BT, uint8_t); WANT(st_pmask, BP, uint8_t); WANT(st_dur, BT, int32_t);
+  WANT(hs_tmask, BT, uint8_t); WANT(hs_pmask, BP, uint8_t);
+#undef WANT
+  cudaError_t e = cudaMalloc(&w.base, off);
+  if (e != cudaSuccess) {
+    w = Workspace();
+    return fail(H, STZ_E_NOMEM, "workspace of %zu bytes: %s", off, cudaGetErrorString(e));
+  }
+  for (auto& pr : plan) *pr.first = w.base + pr.second;
+  w.bytes = off; w.B = B; w.T = T; w.P = P; w.E = E; w.noise_slices = noise_slices;
+  CK(H, cudaMemsetAsync(w.cvec, 0, ((size_t)E * NS * d + 128 * d) * sizeof(bf16), H->stream));
+  CK(H, cudaStreamSynchronize(H->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// sampler schedule (a-1, a-2, a-6) — fp64 on the host, uploaded as fp32 tables
+// ------------------------------------------------------------------------------------------
+struct EvalPlan {
+  std::vector<double> sigma;   // sigma fed to the denoiser at eval e
+  std::vector<float> coef;     // [E][8]
+  std::vector<float> tfeat;    // [E][d_time]
+  double sigma0 = 0, cin0 = 0;
+};
+
+static std::vector<double> karras(int n, double smin, double smax, double rho) {
+  std::vector<double> s(n);
+  if (n == 1) { s[0] = smax; return s; }
+  const double a = pow(smax, 1.0 / rho), b = pow(smin, 1.0 / rho);
+  for (int i = 0; i < n; ++i) s[i] = pow(a + (double)i / (n - 1) * (b - a), rho);
+  return s;
+}
+
+static void precond(double sigma, double sd, double* cskip, double* cout_, double* cin) {
+  const double s2 = sigma * sigma, d2 = sd * sd;
+  *cskip = d2 / (s2 + d2);
+  *cout_ = sigma * sd / sqrt(s2 + d2);
+  *cin = 1.0 / sqrt(s2 + d2);
+}
+
+static EvalPlan make_plan(const stz_config& c, int steps, int kind, float cfg_scale) {
+  EvalPlan pl;
+  const double sd = c.sigma_data;
+  auto push = [&](double sigma, double cx, double cm, double cF, double cn, double sigma_next_in, int dest) {
+    double cin_next = 0.0;
+    if (sigma_next_in > 0.0) { double a, b; precond(sigma_next_in, sd, &a, &b, &cin_next); }
+    pl.sigma.push_back(sigma);
+    const float row[8] = {(float)cx, (float)cm, (float)cF, (float)cn, (float)cin_next, cfg_scale, (float)dest, 0.f};
+    pl.coef.insert(pl.coef.end(), row, row + 8);
+  };
+  if (kind == STZ_SAMPLER_STUDENT) {
+    std::vector<double> s = karras(steps, c.sigma_min, c.sigma_max, c.rho);
+    s.push_back(0.0);
+    for (int i = 0; i < steps; ++i) {
+      double cskip, cout_, cin;
+      precond(s[i], sd, &cskip, &cout_, &cin);
+      const double r = (s[i + 1] - s[i]) / s[i];
+      // x' = x + (x - D) r,  D = cskip x + cout F   ->   x' = (1 + (1 - cskip) r) x - cout r F
+      push(s[i], 1.0 + (1.0 - cskip) * r, 0.0, -cout_ * r, 0.0, s[i + 1], 0);
+    }
+  } else {
+    std::vector<double> s = karras(steps + 1, c.sigma_min, c.sigma_max, c.rho);
+    for (int i = 0; i < steps; ++i) {
+      const double sg = s[i], sn = s[i + 1];
+      const double sup = sqrt(sn * sn * (sg * sg - sn * sn) / (sg * sg));
+      const double sdown = sqrt(fmax(sn * sn - sup * sup, 0.0));
+      const double smid = 0.5 * (sg + sdown);
+      double cskip, cout_, cin;
+      precond(sg, sd, &cskip, &cout_, &cin);
+      const double r1 = (smid - sg) / sg;
+      // x_mid = x + (x - D(x)) r1
+      push(sg, 1.0 + (1.0 - cskip) * r1, 0.0, -cout_ * r1, 0.0, smid, 1);
+      precond(smid, sd, &cskip, &cout_, &cin);
+      const double r2 = (sdown - sg) / smid;
+      // x' = x + (x_mid - D(x_mid)) r2 + sigma_up * noise_{i+1}
+      push(smid, 1.0, (1.0 - cskip) * r2, -cout_ * r2, sup, sn, 0);
+    }
+  }
+  pl.sigma0 = pl.sigma[0];
+  { double a, b; precond(pl.sigma0, sd, &a, &b, &pl.cin0); }
+  const int half = c.d_time / 2;
+  for (double sg : pl.sigma) {
+    const double cn = log(sg) / 4.0;
+    for (int i = 0; i < half; ++i) pl.tfeat.push_back((float)sin(cn * exp(log(100.0) * i / (half > 1 ? half - 1 : 1))));
+    for (int i = 0; i < half; ++i) pl.tfeat.push_back((float)cos(cn * exp(log(100.0) * i / (half > 1 ? half - 1 : 1))));
+  }
+  return pl;
+}
+
+// ------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------
+extern "C" int stz_abi_version(void) { return STZ_ABI_VERSION; }
+
+extern "C" size_t stz_weights_nfloats(const stz_config* cfg) {
+  if (!cfg) return 0;
+  size_t total = 0;
+  build_layout(*cfg, &total);
+  return total;
+}
+
+extern "C" int64_t stz_weight_offset(const stz_config* cfg, const char* name) {
+  if (!cfg || !name) return -1;
+  size_t total = 0;
+  for (const WeightEntry& e : build_layout(*cfg, &total))
+    if (e.name == name) return (int64_t)e.off;
+  return -1;
+}
+
+extern "C" const char* stz_last_error(const stz_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void stz_destroy(stz_handle* H) {
+  if (!H) return;
+  cudaSetDevice(H->device);
+  cudaDeviceSynchronize();
+  for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
+  cudaFree(H->ws.base); cudaFree(H->w32); cudaFree(H->wbf); cudaFree(H->ctx_text_b); cudaFree(H->ctx_prompt_b);
+  cudaFree(H->kv_null); cudaFree(H->whhT); cudaFree(H->lstm_b);
+  if (H->stream) cudaStreamDestroy(H->stream);
+  delete H;
+}
+
+__global__ void transpose_whh_kernel(const float* __restrict__ w, float* __restrict__ wT, int rows, int cols) {
+  // w [rows = 4h, cols = h]  ->  wT [cols, rows]
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    wT[(size_t)c * rows + r] = w[i];
+  }
+}
+
+static int create_impl(stz_handle* H, const float* weights_host) {
+  const stz_config& c = H->cfg;
+  const int d = c.d_model, L = c.n_layers, h = c.d_hid / 2;
+  CK(H, cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
+  CK(H, init_kernel_attrs());
+  cudaStream_t st = H->stream;
+  CK(H, cudaMalloc(&H->w32, H->n_floats * sizeof(float)));
+  CK(H, cudaMalloc(&H->wbf, H->n_floats * sizeof(bf16)));
+  CK(H, cudaMemcpyAsync(H->w32, weights_host, H->n_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+  f32_to_bf16_kernel<<<ew_grid(H->n_floats), 256, 0, st>>>(H->w32, H->wbf, H->n_floats);
+  KCHECK(H);
+  // ctx biases with the token-type embedding folded in
+  CK(H, cudaMalloc(&H->ctx_text_b, d * sizeof(float)));
+  CK(H, cudaMalloc(&H->ctx_prompt_b, d * sizeof(float)));
+  add_vec_kernel<<<1, 256, 0, st>>>(W32(H, "ctx_text.b"), W32(H, "type_emb"), H->ctx_text_b, d, d); KCHECK(H);
+  add_vec_kernel<<<1, 256, 0, st>>>(W32(H, "ctx_prompt.b"), W32(H, "type_emb") + d, H->ctx_prompt_b, d, d); KCHECK(H);
+  // null-prompt context token: LN(null_tok + e1) -> per-layer K/V
+  float* tmp = nullptr; bf16* nullc = nullptr;
+  CK(H, cudaMalloc(&tmp, d * sizeof(float)));
+  CK(H, cudaMalloc(&nullc, 128 * d * sizeof(bf16)));  // padded to one M tile
+  CK(H, cudaMemsetAsync(nullc, 0, 128 * d * sizeof(bf16), st));
+  CK(H, cudaMalloc(&H->kv_null, (size_t)L * 2 * d * sizeof(bf16)));
+  add_vec_kernel<<<1, 256, 0, st>>>(W32(H, "null_tok"), W32(H, "type_emb") + d, tmp, d, d); KCHECK(H);
+  RET(ln_mod(H, st, tmp, 1, d, nullptr, 0, 0, 0, 1, nullc));
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "l" + std::to_string(l) + ".kv2.";
+    GemmParams gp{};
+    gp.M = 1; gp.N = 2 * d; gp.K = d; gp.bias = W32(H, p + "b"); gp.out = H->kv_null + (size_t)l * 2 * d; gp.ldo = L * 2 * d;
+    RET(gemm<EPI_BF16>(H, st, 1, nullc, d, 128, WBF(H, p + "w"), gp));  // M = 1: CUDA-core kernel, create time only
+  }
+  // predictor: recurrent weights k-major, biases summed
+  CK(H, cudaMalloc(&H->whhT, (size_t)c.n_lstm * 2 * h * 4 * h * sizeof(float)));
+  CK(H, cudaMalloc(&H->lstm_b, (size_t)c.n_lstm * 2 * 4 * h * sizeof(float)));
+  for (int l = 0; l < c.n_lstm; ++l)
+    for (int dr = 0; dr < 2; ++dr) {
+      const std::string p = "lstm" + std::to_string(l) + (dr ? ".r." : ".f.");
+      transpose_whh_kernel<<<ew_grid((size_t)4 * h * h), 256, 0, st>>>(W32(H, p + "w_hh"),
+                                                                        H->whhT + ((size_t)l * 2 + dr) * h * 4 * h, 4 * h, h);
+      KCHECK(H);
+      add_vec_kernel<<<ew_grid(4 * h), 256, 0, st>>>(W32(H, p + "b_ih"), W32(H, p + "b_hh"),
+                                                     H->lstm_b + ((size_t)l * 2 + dr) * 4 * h, 4 * h, 4 * h);
+      KCHECK(H);
+    }
+  CK(H, cudaStreamSynchronize(st));
+  cudaFree(tmp); cudaFree(nullc);
+  return 0;
+}
+
+extern "C" int stz_create(const stz_config* cfg, const float* weights_host, size_t nfloats, int device,
+                          stz_handle** out) {
+  if (!cfg || !weights_host || !out) return fail(nullptr, STZ_E_ARG, "null argument");
+  *out = nullptr;
+  if (check_config(*cfg)) return fail(nullptr, STZ_E_SHAPE, "configuration outside kernel support (see check_config)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(nullptr, STZ_E_DEVICE, "CUDA device %d not available (count %d): no CPU fallback", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, STZ_E_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, STZ_E_DEVICE, "cudaSetDevice(%d) failed", device);
+  if (load_encode()) return fail(nullptr, STZ_E_DEVICE, "cuTensorMapEncodeTiled entry point not found");
+  stz_handle* H = new stz_handle();
+  H->cfg = *cfg;
+  H->device = device;
+  H->layout = build_layout(*cfg, &H->n_floats);
+  for (const WeightEntry& e : H->layout) H->off[e.name] = e.off;
+  if (nfloats != H->n_floats) {
+    fail(nullptr, STZ_E_ARG, "weight blob has %zu floats, layout needs %zu", nfloats, H->n_floats);
+    delete H;
+    return STZ_E_ARG;
+  }
+  int rc = create_impl(H, weights_host);
+  if (rc != 0) {
+    g_create_error = H->err;
+    stz_destroy(H);
+    return rc;
+  }
+  H->launches = 0; H->cur_launches = 0;
+  *out = H;
+  return 0;
+}
+
+extern "C" int64_t stz_launch_count(const stz_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
+  if (!H || !key) return STZ_E_ARG;
+  if (!strcmp(key, "use_graph")) H->use_graph = value;
+  else if (!strcmp(key, "gemm_impl")) {
+    if (H->gemm_impl != value) {
+      for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
+      H->graphs.clear();
+    }
+    H->gemm_impl = value;
+  } else if (!strcmp(key, "lstm_impl")) { /* single implementation this round */ }
+  else return fail(H, STZ_E_ARG, "unknown option %s", key);
+  return 0;
+}
+
+extern "C" int stz_debug_set_tap(stz_handle* H, int eval, int layer, int stage, float* tap_dev) {
+  if (!H) return STZ_E_ARG;
+  H->tap_eval = eval; H->tap_layer = layer; H->tap_stage = stage; H->tap_buf = tap_dev;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// sample_style
+// ------------------------------------------------------------------------------------------
+static int tap(stz_handle* H, cudaStream_t st, int e, int l, int s, size_t R) {
+  if (H->tap_buf && !H->capturing && H->tap_eval == e && H->tap_layer == l && H->tap_stage == s)
+    CK(H, cudaMemcpyAsync(H->tap_buf, H->ws.h, R * H->cfg.d_model * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B) {
+  dim3 grid(H->cfg.n_heads, B);
+  attention_kernel<<<grid, cdiv(ap.n_q, 16) * 32, 0, st>>>(ap);
+  KCHECK(H);
+  return 0;
+}
+
+// One denoiser evaluation + fused guidance/sampler update (a-4, a-5, a-6).
+static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, const uint8_t* tmask, const uint8_t* pmask) {
+  const stz_config& c = H->cfg;
+  Workspace& w = H->ws;
+  const int d = c.d_model, L = c.n_layers, K = c.n_style, Ds = c.d_style, n_mod = (9 * L + 2) * d;
+  const int R = 2 * B * K, NS = 2 * B, impl = H->gemm_impl;
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)(d / c.n_heads));
+  GemmParams base{};
+  base.mod = w.mod; base.n_mod = n_mod; base.rows_per_utt = 2 * K; base.n_style = K;
+
+  {  // AdaLN modulations of this eval: mod[NS, n_mod] = c[e] · Wmod^T + b
+    GemmParams p = base;
+    p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * NS; p.bias = W32(H, "mod.b"); p.out = w.mod; p.ldo = n_mod;
+    RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
+  }
+  {  // h = x_in · Win^T + b + pos
+    GemmParams p = base;
+    p.M = R; p.N = d; p.K = Ds; p.bias = W32(H, "in.b"); p.out = w.h; p.ldo = d; p.pos = W32(H, "pos");
+    RET(gemm<EPI_F32_POS>(H, st, impl, w.xin, Ds, R, WBF(H, "in.w"), p));
+  }
+  for (int l = 0; l < L; ++l) {
+    const std::string pf = "l" + std::to_string(l) + ".";
+    const int mo = 9 * l * d;
+    // --- self-attention
+    RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, mo + 0 * d, mo + 1 * d, 2 * K, w.u));
+    {
+      GemmParams p = base;
+      p.M = R; p.N = 3 * d; p.K = d; p.bias = W32(H, pf + "qkv.b"); p.out = w.qkv; p.ldo = 3 * d;
+      RET(gemm<EPI_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "qkv.w"), p));
+    }
+    {
+      AttnParams ap{};
+      ap.q = w.qkv; ap.ldq = 3 * d; ap.out = w.att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 1; ap.scale_log2 = scale_log2;
+      ap.seg[0] = AttnSeg{w.qkv + d, w.qkv + 2 * d, 3 * d, 2 * K, 2 * K, nullptr, KEY_SAME_BRANCH};
+      RET(attention(H, st, ap, B));
+    }
+    {
+      GemmParams p = base;
+      p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "o.b"); p.out = w.h; p.ldo = d; p.gate_off = mo + 2 * d;
+      RET(gemm<EPI_GATE_RES>(H, st, impl, w.att, d, R, WBF(H, pf + "o.w"), p));
+    }
+    RET(tap(H, st, e, l, 0, R));
+    // --- cross-attention over [text ; prompt | null]
+    RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, mo + 3 * d, mo + 4 * d, 2 * K, w.u));
+    {
+      GemmParams p = base;
+      p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "q2.b"); p.out = w.qkv; p.ldo = d;
+      RET(gemm<EPI_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "q2.w"), p));
+    }
+    {
+      AttnParams ap{};
+      const int ldkv = L * 2 * d;
+      ap.q = w.qkv; ap.ldq = d; ap.out = w.att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 3; ap.scale_log2 = scale_log2;
+      ap.seg[0] = AttnSeg{w.kv_text + l * 2 * d, w.kv_text + l * 2 * d + d, ldkv, T, T, tmask, KEY_ALL};
+      ap.seg[1] = AttnSeg{w.kv_prompt + l * 2 * d, w.kv_prompt + l * 2 * d + d, ldkv, P, P, pmask, KEY_COND};
+      ap.seg[2] = AttnSeg{H->kv_null + l * 2 * d, H->kv_null + l * 2 * d + d, ldkv, 1, 0, nullptr, KEY_UNCOND};
+      RET(attention(H, st, ap, B));
+    }
+    {
+      GemmParams p = base;
+      p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "o2.b"); p.out = w.h; p.ldo = d; p.gate_off = mo + 5 * d;
+      RET(gemm<EPI_GATE_RES>(H, st, impl, w.att, d, R, WBF(H, pf + "o2.w"), p));
+    }
+    RET(tap(H, st, e, l, 1, R));
+    // --- FFN
+    RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, mo + 6 * d, mo + 7 * d, 2 * K, w.u));
+    {
+      GemmParams p = base;
+      p.M = R; p.N = c.d_ff; p.K = d; p.bias = W32(H, pf + "ff1.b"); p.out = w.ffh; p.ldo = c.d_ff;
+      RET(gemm<EPI_GELU_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "ff1.w"), p));
+    }
+    {
+      GemmParams p = base;
+      p.M = R; p.N = d; p.K = c.d_ff; p.bias = W32(H, pf + "ff2.b"); p.out = w.h; p.ldo = d; p.gate_off = mo + 8 * d;
+      RET(gemm<EPI_GATE_RES>(H, st, impl, w.ffh, c.d_ff, R, WBF(H, pf + "ff2.w"), p));
+    }
+    RET(tap(H, st, e, l, 2, R));
+  }
+  RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, 9 * L * d, 9 * L * d + d, 2 * K, w.u));
+  {  // F = u · Wout^T + b, then CFG combine + sampler update + next input in the epilogue
+    GemmParams p = base;
+    p.M = R; p.N = Ds; p.K = d; p.bias = W32(H, "out.b"); p.ldo = Ds;
+    p.x = w.x; p.xmid = w.xmid; p.xin = w.xin; p.coef = w.coef + (size_t)e * 8;
+    // teacher: eval 2i+1 adds sigma_up * noise slice i+1 (slice 0 seeded the state)
+    p.noise = w.noise + (size_t)((e >> 1) + 1) * B * K * Ds;
+    p.tap = (H->tap_buf && !H->capturing && H->tap_eval == e && H->tap_layer == L) ? H->tap_buf : nullptr;
+    RET(gemm<EPI_SAMPLER>(H, st, impl, w.u, d, R, WBF(H, "out.w"), p));
+  }
+  return 0;
+}
+
+static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tmask, const float* prompt,
+                             const uint8_t* pmask, const float* noise, int B, int T, int P, int steps, float cfg_scale,
+                             int kind, float* out, cudaStream_t st) {
+  const stz_config& c = H->cfg;
+  if (!text || !prompt || !noise || !out) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (B < 1 || T < 1 || P < 1 || steps < 1 || steps > 1024) return fail(H, STZ_E_ARG, "bad sizes B=%d T=%d P=%d steps=%d", B, T, P, steps);
+  if (kind != STZ_SAMPLER_STUDENT && kind != STZ_SAMPLER_TEACHER) return fail(H, STZ_E_ARG, "bad sampler kind %d", kind);
+  const int E = kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
+  const int slices = kind == STZ_SAMPLER_TEACHER ? steps + 1 : 1;
+  RET(ensure_workspace(H, B, T, P, E, slices));
+  Workspace& w = H->ws;
+  const int d = c.d_model, L = c.n_layers, K = c.n_style, Ds = c.d_style;
+  const int NS = 2 * B, impl = H->gemm_impl;
+  const size_t BK = (size_t)B * K;
+  H->cur_launches = 0;
+
+  // ---- schedule tables ----------------------------------------------------------------
+  EvalPlan pl = make_plan(c, steps, kind, cfg_scale);
+  CK(H, cudaMemcpyAsync(w.coef, pl.coef.data(), pl.coef.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(H, cudaMemcpyAsync(w.tfeat, pl.tfeat.data(), pl.tfeat.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+
+  // ---- conditioning prep (a-3): once per call ---------------------------------------------
+  cast_pool_kernel<<<B, 256, 0, st>>>(text, tmask, w.text_bf, w.pool_text, T, c.d_text); KCHECK(H);
+  cast_pool_kernel<<<B, 256, 0, st>>>(prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
+  RET(linear_f32(H, st, ACT_NONE, w.pool_text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "ptext.w"), W32(H, "ptext.b"), w.pt, d, B, d));
+  RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
+  RET(linear_f32(H, st, ACT_SILU, w.tfeat, c.d_time, c.d_time, nullptr, 0, 0, W32(H, "time.w1"), W32(H, "time.b1"), w.t1, d, E, d));
+  RET(linear_f32(H, st, ACT_NONE, w.t1, d, d, nullptr, 0, 0, W32(H, "time.w2"), W32(H, "time.b2"), w.temb, d, E, d));
+  cvec_kernel<<<ew_grid((size_t)E * NS * d), 256, 0, st>>>(w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
+  for (int which = 0; which < 2; ++which) {  // context tokens and their per-layer K/V
+    const int rows = which == 0 ? B * T : B * P, din = which == 0 ? c.d_text : c.d_prompt;
+    const bf16* src = which == 0 ? w.text_bf : w.prompt_bf;
+    bf16* ctx = which == 0 ? w.ctx_text : w.ctx_prompt;
+    bf16* kv = which == 0 ? w.kv_text : w.kv_prompt;
+    GemmParams p{};
+    p.M = rows; p.N = d; p.K = din; p.bias = which == 0 ? H->ctx_text_b : H->ctx_prompt_b; p.out = w.ctx_pre; p.ldo = d;
+    RET(gemm<EPI_F32>(H, st, impl, src, din, rows, WBF(H, which == 0 ? "ctx_text.w" : "ctx_prompt.w"), p));
+    RET(ln_mod(H, st, w.ctx_pre, rows, d, nullptr, 0, 0, 0, 1, ctx));
+    for (int l = 0; l < L; ++l) {
+      const std::string pf = "l" + std::to_string(l) + ".kv2.";
+      GemmParams q{};
+      q.M = rows; q.N = 2 * d; q.K = d; q.bias = W32(H, pf + "b"); q.out = kv + (size_t)l * 2 * d; q.ldo = L * 2 * d;
+      RET(gemm<EPI_BF16>(H, st, impl, ctx, d, rows, WBF(H, pf + "w"), q));
+    }
+  }
+  // ---- sampler state --------------------------------------------------------------------
+  init_state_kernel<<<ew_grid(BK * Ds / 4), 256, 0, st>>>(noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0); KCHECK(H);
+  if (kind == STZ_SAMPLER_TEACHER)
+    CK(H, cudaMemcpyAsync(w.noise, noise, (size_t)slices * BK * Ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  H->launches += H->cur_launches;
+  H->cur_launches = 0;
+
+  // ---- the evaluation loop: one CUDA graph per (B, T, P, E, kind) ----------------------------
+  const bool tapping = H->tap_buf != nullptr;
+  if (H->use_graph && !tapping) {
+    auto key = std::make_tuple(B, T, P, E, kind * 2 + (tmask ? 1 : 0) + (pmask ? 4 : 0));
+    auto it = H->graphs.find(key);
+    // the graph bakes in the mask pointers: masks are copied into library-owned staging first
+    const uint8_t* tm = nullptr; const uint8_t* pm = nullptr;
+    if (tmask) { CK(H, cudaMemcpyAsync(w.st_tmask, tmask, (size_t)B * T, cudaMemcpyDeviceToDevice, st)); tm = w.st_tmask; }
+    if (pmask) { CK(H, cudaMemcpyAsync(w.st_pmask, pmask, (size_t)B * P, cudaMemcpyDeviceToDevice, st)); pm = w.st_pmask; }
+    if (it == H->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      CK(H, cudaStreamSynchronize(st));
+      CK(H, cudaStreamBeginCapture(H->stream, cudaStreamCaptureModeThreadLocal));
+      H->capturing = true;
+      int rc = 0;
+      for (int e = 0; e < E && rc == 0; ++e) rc = run_eval(H, H->stream, e, B, T, P, tm, pm);
+      H->capturing = false;
+      cudaError_t ce = cudaStreamEndCapture(H->stream, &graph);
+      if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail(H, STZ_E_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return fail(H, STZ_E_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce));
+      it = H->graphs.emplace(key, std::make_pair(exec, H->cur_launches)).first;
+      H->cur_launches = 0;
+    }
+    CK(H, cudaGraphLaunch(it->second.first, st));
+    H->launches += it->second.second;
+  } else {
+    for (int e = 0; e < E; ++e) RET(run_eval(H, st, e, B, T, P, tmask, pmask));
+    H->launches += H->cur_launches;
+    H->cur_launches = 0;
+  }
+  CK(H, cudaMemcpyAsync(out, w.x, BK * Ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int stz_sample_style(stz_handle* H, const float* text_emb_dev, const uint8_t* text_mask_dev,
+                                const float* prompt_feats_dev, const uint8_t* prompt_mask_dev, const float* noise_dev,
+                                int B, int T, int P, int steps, float cfg_scale, int sampler_kind, float* out_style_dev,
+                                void* cuda_stream) {
+  if (!H) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  return sample_style_impl(H, text_emb_dev, text_mask_dev, prompt_feats_dev, prompt_mask_dev, noise_dev, B, T, P, steps,
+                           cfg_scale, sampler_kind, out_style_dev, (cudaStream_t)cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// predict_duration (a-8 .. a-11)
+// ------------------------------------------------------------------------------------------
+static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t* tmask, const float* style, int B, int T,
+                                 int32_t* out_dur, float* out_presum, cudaStream_t st) {
+  const stz_config& c = H->cfg;
+  if (!text || !style || !out_dur) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (B < 1 || T < 1) return fail(H, STZ_E_ARG, "bad sizes B=%d T=%d", B, T);
+  RET(ensure_workspace(H, B, T, 1, 1, 1));
+  Workspace& w = H->ws;
+  const int ds = c.d_sty_tok, dh = c.d_hid, h = dh / 2, K = c.n_style, Ds = c.d_style;
+  const int BT = B * T, BK = B * K;
+  H->cur_launches = 0;
+  lens_kernel<<<cdiv(B, 128), 128, 0, st>>>(tmask, w.lens, B, T); KCHECK(H);
+  // a-8: per-token style summary
+  RET(linear_f32(H, st, ACT_NONE, text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "sp.q.w"), W32(H, "sp.q.b"), w.sq, ds, BT, ds));
+  RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.k.w"), W32(H, "sp.k.b"), w.sk, ds, BK, ds));
+  RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.v.w"), W32(H, "sp.v.b"), w.sv, ds, BK, ds));
+  style_pool_attn_kernel<<<cdiv(BT, 8), 256, 0, st>>>(w.sq, w.sk, w.sv, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
+  RET(linear_f32(H, st, ACT_NONE, w.sa, ds, ds, nullptr, 0, 0, W32(H, "sp.o.w"), W32(H, "sp.o.b"), w.stok, ds, BT, ds));
+  // a-9: (BiLSTM + AdaLN) x (n_lstm - 1) + BiLSTM
+  const float* x = text;
+  float* bufs[2] = {w.xa, w.xb};
+  constexpr int NB = 8;
+  const size_t lstm_smem = (size_t)NB * h * 5 * sizeof(float);
+  for (int l = 0; l < c.n_lstm; ++l) {
+    for (int dr = 0; dr < 2; ++dr) {
+      const std::string p = "lstm" + std::to_string(l) + (dr ? ".r." : ".f.");
+      RET(linear_f32(H, st, ACT_NONE, x, dh, dh, w.stok, ds, ds, W32(H, p + "w_ih"), H->lstm_b + ((size_t)l * 2 + dr) * 4 * h,
+                     w.G + (size_t)dr * 4 * h, 8 * h, BT, 4 * h));
+    }
+    float* xo = bufs[l & 1];
+    lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
+    KCHECK(H);
+    if (l < c.n_lstm - 1) {
+      const std::string p = "adaln" + std::to_string(l) + ".";
+      RET(linear_f32(H, st, ACT_NONE, w.stok, ds, ds, nullptr, 0, 0, W32(H, p + "w"), W32(H, p + "b"), w.gb, 2 * dh, BT, 2 * dh));
+      dim3 grid(cdiv(BT, 8));
+      switch (dh / 128) {
+        case 1: adaln_pred_kernel<1><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
+        case 2: adaln_pred_kernel<2><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
+        case 4: adaln_pred_kernel<4><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
+        case 8: adaln_pred_kernel<8><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
+        default: return fail(H, STZ_E_SHAPE, "d_hid %d unsupported", dh);
+      }
+      KCHECK(H);
+    }
+    x = xo;
+  }
+  {  // a-10
+    dim3 grid(cdiv(BT, 8));
+    switch (dh / 128) {
+      case 1: dur_head_kernel<1><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 2: dur_head_kernel<2><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 4: dur_head_kernel<4><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 8: dur_head_kernel<8><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      default: return fail(H, STZ_E_SHAPE, "d_hid %d unsupported", dh);
+    }
+    KCHECK(H);
+  }
+  H->launches += H->cur_launches;
+  H->cur_launches = 0;
+  return 0;
+}
+
+extern "C" int stz_predict_duration(stz_handle* H, const float* text_emb_dev, const uint8_t* text_mask_dev,
+                                    const float* style_dev, int B, int T, int32_t* out_dur_dev, float* out_presum_dev,
+                                    void* cuda_stream) {
+  if (!H) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  return predict_duration_impl(H, text_emb_dev, text_mask_dev, style_dev, B, T, out_dur_dev, out_presum_dev,
+                               (cudaStream_t)cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer end-to-end entry point
+// ------------------------------------------------------------------------------------------
+extern "C" int stz_synthesize_host(stz_handle* H, const float* text_emb, const uint8_t* text_mask,
+                                   const float* prompt_feats, const uint8_t* prompt_mask, const float* noise, int B, int T,
+                                   int P, int steps, float cfg_scale, int sampler_kind, float* out_style, int32_t* out_dur) {
+  if (!H) return STZ_E_ARG;
+  if (!text_emb || !prompt_feats || !noise || !out_style) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (B < 1 || T < 1 || P < 1 || steps < 1) return fail(H, STZ_E_ARG, "bad sizes");
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  const stz_config& c = H->cfg;
+  const int E = sampler_kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
+  const int slices = sampler_kind == STZ_SAMPLER_TEACHER ? steps + 1 : 1;
+  RET(ensure_workspace(H, B, T, P, E, slices));
+  Workspace& w = H->ws;
+  cudaStream_t st = H->stream;
+  const size_t BK = (size_t)B * c.n_style, BT = (size_t)B * T, BP = (size_t)B * P;
+  CK(H, cudaMemcpyAsync(w.st_text, text_emb, BT * c.d_text * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(H, cudaMemcpyAsync(w.st_prompt, prompt_feats, BP * c.d_prompt * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(H, cudaMemcpyAsync(w.st_noise, noise, (size_t)slices * BK * c.d_style * sizeof(float), cudaMemcpyHostToDevice, st));
+  uint8_t *tm = nullptr, *pm = nullptr;
+  if (text_mask) { tm = w.hs_tmask; CK(H, cudaMemcpyAsync(tm, text_mask, BT, cudaMemcpyHostToDevice, st)); }
+  if (prompt_mask) { pm = w.hs_pmask; CK(H, cudaMemcpyAsync(pm, prompt_mask, BP, cudaMemcpyHostToDevice, st)); }
+  RET(sample_style_impl(H, w.st_text, tm, w.st_prompt, pm, w.st_noise, B, T, P, steps, cfg_scale, sampler_kind, w.st_style, st));
+  CK(H, cudaMemcpyAsync(out_style, w.st_style, BK * c.d_style * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (out_dur) {
+    int32_t* dur_dev = w.st_dur;
+    RET(predict_duration_impl(H, w.st_text, tm, w.st_style, B, T, dur_dev, nullptr, st));
+    CK(H, cudaMemcpyAsync(out_dur, dur_dev, BT * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  CK(H, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// unit-test entry point
+// ------------------------------------------------------------------------------------------
+extern "C" int stz_op_gemm_bf16(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int impl,
+                                int device, void* cuda_stream) {
+  if (!A || !W || !C) return fail(nullptr, STZ_E_ARG, "null argument");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, STZ_E_DEVICE, "cudaSetDevice(%d) failed", device);
+  if (load_encode()) return fail(nullptr, STZ_E_DEVICE, "cuTensorMapEncodeTiled entry point not found");
+  if (N % GEMM_BN || K % GEMM_BK || M < 1) return fail(nullptr, STZ_E_SHAPE, "N %% 128, K %% 64 required");
+  if (init_kernel_attrs() != cudaSuccess) return fail(nullptr, STZ_E_CUDA, "cudaFuncSetAttribute failed");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = C; p.ldo = N;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc = impl == 0 ? launch_gemm_tc<EPI_F32>(nullptr, st, (const bf16*)A, K, M, (const bf16*)W, p)
+                     : launch_gemm_simt<EPI_F32>(nullptr, st, (const bf16*)A, K, (const bf16*)W, p);
+  if (rc != 0 && g_create_error.empty()) g_create_error = "gemm launch failed";
+  return rc;
+}

@@ -1,0 +1,249 @@
+"""Host side of the drop-in boundary: a ctypes binding of include/stz.h behind the module API
+``sample_style(text_emb, prompt_feats, steps, cfg_scale)`` / ``predict_duration(...)``
+(BASELINE.json north_star).  The reference has no such module to cite
+(/root/reference/README.md:15-16); the oracle in ``oracle/`` exposes the same signatures so the
+parity tests read identically for both.
+
+PyTorch is plumbing only here: device memory, streams, (for multi-GPU) process launch.
+There is NO CPU fallback and nothing in this module imports ``oracle``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .spec import (ABI_VERSION, DEFAULT, SAMPLER_STUDENT, SAMPLER_TEACHER, StzConfig, n_noise_slices,
+                   weight_offsets)
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstz.so")
+_lib = None
+
+
+class StzError(RuntimeError):
+    pass
+
+
+class _CConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_style", "d_style", "d_model", "n_heads", "d_ff", "n_layers",
+                                          "d_text", "d_prompt", "d_time", "d_hid", "d_sty_tok",
+                                          "n_sp_heads", "n_lstm", "max_dur")] + \
+               [(n, C.c_float) for n in ("sigma_data", "sigma_max", "sigma_min", "rho")]
+
+
+def _cconfig(cfg: StzConfig) -> _CConfig:
+    return _CConfig(**{k: v for k, v in cfg.as_dict().items()})
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen csrc/libstz.so and declare every prototype of include/stz.h.  Raises if missing:
+    the product path must fail loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise StzError(f"{p} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"(there is no CPU fallback)")
+    lib = C.CDLL(p)
+    vp, i32, f32, i64, sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+    cfgp = C.POINTER(_CConfig)
+    lib.stz_abi_version.restype = i32
+    lib.stz_abi_version.argtypes = []
+    lib.stz_weights_nfloats.restype = sz
+    lib.stz_weights_nfloats.argtypes = [cfgp]
+    lib.stz_weight_offset.restype = i64
+    lib.stz_weight_offset.argtypes = [cfgp, C.c_char_p]
+    lib.stz_create.restype = i32
+    lib.stz_create.argtypes = [cfgp, vp, sz, i32, C.POINTER(vp)]
+    lib.stz_destroy.restype = None
+    lib.stz_destroy.argtypes = [vp]
+    lib.stz_last_error.restype = C.c_char_p
+    lib.stz_last_error.argtypes = [vp]
+    lib.stz_sample_style.restype = i32
+    lib.stz_sample_style.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
+    lib.stz_predict_duration.restype = i32
+    lib.stz_predict_duration.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    lib.stz_synthesize_host.restype = i32
+    lib.stz_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
+    lib.stz_launch_count.restype = i64
+    lib.stz_launch_count.argtypes = [vp]
+    lib.stz_set_option.restype = i32
+    lib.stz_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.stz_debug_set_tap.restype = i32
+    lib.stz_debug_set_tap.argtypes = [vp, i32, i32, i32, vp]
+    lib.stz_op_gemm_bf16.restype = i32
+    lib.stz_op_gemm_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    if lib.stz_abi_version() != ABI_VERSION:
+        raise StzError(f"ABI mismatch: library {lib.stz_abi_version()} vs python {ABI_VERSION}")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
+                    "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
+                    "stz_synthesize_host", "stz_launch_count", "stz_set_option", "stz_debug_set_tap",
+                    "stz_op_gemm_bf16")
+
+
+def _kind(sampler) -> int:
+    if sampler in ("student", SAMPLER_STUDENT):
+        return SAMPLER_STUDENT
+    if sampler in ("teacher", SAMPLER_TEACHER):
+        return SAMPLER_TEACHER
+    raise ValueError(f"unknown sampler {sampler!r}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class StyleTTSZSPath:
+    """CUDA (sm_100a) implementation of the hot path behind the oracle's module API."""
+
+    def __init__(self, cfg: StzConfig = DEFAULT, weights: Optional[torch.Tensor] = None, device: int = 0,
+                 backend: str = "cuda"):
+        if backend != "cuda":
+            raise StzError("only backend='cuda' exists in the product package; the fp32 CPU oracle lives "
+                           "in oracle/ and is test infrastructure")
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise StzError("no CUDA device: the hot path has no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        if weights is None:
+            from .spec import init_weights
+            weights = init_weights(cfg, 0)
+        w = weights.detach().to(torch.float32).cpu().contiguous()
+        n = weight_offsets(cfg)["__total__"][0]
+        if w.numel() != n or self.lib.stz_weights_nfloats(C.byref(_cconfig(cfg))) != n:
+            raise StzError("weight blob size does not match the layout")
+        h = C.c_void_p()
+        rc = self.lib.stz_create(C.byref(_cconfig(cfg)), C.c_void_p(w.data_ptr()), n, device, C.byref(h))
+        if rc != 0:
+            raise StzError(f"stz_create failed ({rc}): {self.lib.stz_last_error(None).decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.stz_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise StzError(f"{what} failed ({rc}): {self.lib.stz_last_error(self._h).decode()}")
+
+    # ---------------------------------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.stz_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
+
+    def launch_count(self) -> int:
+        return int(self.lib.stz_launch_count(self._h))
+
+    def set_tap(self, ev: int, layer: int, stage: int, buf: Optional[torch.Tensor]):
+        self._check(self.lib.stz_debug_set_tap(self._h, ev, layer, stage, _ptr(buf)), "set_tap")
+
+    def _dev(self, t: torch.Tensor, dtype) -> torch.Tensor:
+        return t.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+
+    def _mask(self, m: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        return None if m is None else self._dev(m.to(torch.uint8) if m.dtype == torch.bool else m, torch.uint8)
+
+    # ---------------------------------------------------------------------------------
+    def sample_style(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
+                     prompt_mask=None, noise=None, sampler="student") -> torch.Tensor:
+        """-> style codes [B,K,Ds] fp32 on this path's device.  ``noise`` [n_slices,B,K,Ds] is an
+        input ("identical seeds" == identical noise tensors)."""
+        cfg, kind = self.cfg, _kind(sampler)
+        B, T, _ = text_emb.shape
+        P = prompt_feats.shape[1]
+        if noise is None:
+            raise ValueError("noise tensor is required")
+        ns = n_noise_slices(steps, kind)
+        if tuple(noise.shape) != (ns, B, cfg.n_style, cfg.d_style):
+            raise ValueError(f"noise must be {(ns, B, cfg.n_style, cfg.d_style)}, got {tuple(noise.shape)}")
+        with torch.cuda.device(self.device):
+            te, pf, nz = self._dev(text_emb, torch.float32), self._dev(prompt_feats, torch.float32), \
+                self._dev(noise, torch.float32)
+            tm, pm = self._mask(text_mask), self._mask(prompt_mask)
+            out = torch.empty(B, cfg.n_style, cfg.d_style, dtype=torch.float32, device=self.device)
+            st = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.stz_sample_style(self._h, _ptr(te), _ptr(tm), _ptr(pf), _ptr(pm), _ptr(nz), B, T, P,
+                                           int(steps), float(cfg_scale), kind, _ptr(out), C.c_void_p(st))
+            self._check(rc, "stz_sample_style")
+            # inputs converted above are kept alive until the work is enqueued *and* ordered:
+            for t in (te, pf, nz, tm, pm):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream())
+        return out
+
+    def predict_duration(self, text_emb, style_codes, *, text_mask=None, return_presum=False):
+        """-> int32 frames per token [B,T] (0 on padding)."""
+        B, T, _ = text_emb.shape
+        with torch.cuda.device(self.device):
+            te, sc = self._dev(text_emb, torch.float32), self._dev(style_codes, torch.float32)
+            tm = self._mask(text_mask)
+            out = torch.empty(B, T, dtype=torch.int32, device=self.device)
+            pre = torch.empty(B, T, dtype=torch.float32, device=self.device) if return_presum else None
+            st = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.stz_predict_duration(self._h, _ptr(te), _ptr(tm), _ptr(sc), B, T, _ptr(out), _ptr(pre),
+                                               C.c_void_p(st))
+            self._check(rc, "stz_predict_duration")
+            for t in (te, sc, tm):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream())
+        return (out, pre) if return_presum else out
+
+    def synthesize_host(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
+                        prompt_mask=None, noise=None, sampler="student", out_style=None, out_dur=None,
+                        with_duration=True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """End-to-end call with HOST tensors (pinned recommended): H2D + sample_style
+        [+ predict_duration] + D2H + sync inside one C-ABI call.  This is what bench.py's `e2e` times."""
+        cfg, kind = self.cfg, _kind(sampler)
+        B, T, _ = text_emb.shape
+        P = prompt_feats.shape[1]
+        for t in (text_emb, prompt_feats, noise):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("synthesize_host takes contiguous fp32 CPU tensors")
+        tm = None if text_mask is None else text_mask.to(torch.uint8).contiguous()
+        pm = None if prompt_mask is None else prompt_mask.to(torch.uint8).contiguous()
+        if out_style is None:
+            out_style = torch.empty(B, cfg.n_style, cfg.d_style, dtype=torch.float32)
+        if with_duration and out_dur is None:
+            out_dur = torch.empty(B, T, dtype=torch.int32)
+        rc = self.lib.stz_synthesize_host(self._h, _ptr(text_emb), _ptr(tm), _ptr(prompt_feats), _ptr(pm),
+                                          _ptr(noise), B, T, P, int(steps), float(cfg_scale), kind,
+                                          _ptr(out_style), _ptr(out_dur) if with_duration else None)
+        self._check(rc, "stz_synthesize_host")
+        return out_style, (out_dur if with_duration else None)
+
+
+def op_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: int = 0) -> torch.Tensor:
+    """Unit-test entry: C = A·W^T + bias with the library's GEMM (A [M,K], W [N,K] bf16 CUDA)."""
+    lib = load_library()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    rc = lib.stz_op_gemm_bf16(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, impl, A.device.index or 0,
+                              C.c_void_p(st))
+    if rc != 0:
+        raise StzError(f"stz_op_gemm_bf16 failed ({rc}): {lib.stz_last_error(None).decode()}")
+    return out
+
+
+def shard_utterances(lengths: Sequence[int], world_size: int) -> List[List[int]]:
+    """Multi-GPU partitioning: utterances are independent, so the batch is split
+    with no collective.  Length-sorted round-robin keeps per-rank padded work similar; returns the
+    utterance indices of each rank (each list sorted by length, longest first)."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    return [order[r::world_size] for r in range(world_size)]
