@@ -103,8 +103,17 @@ int stz_synthesize_host(stz_handle* h, const float* text_emb, const uint8_t* tex
 int64_t stz_launch_count(const stz_handle* h);
 
 /* Knobs: "use_graph" (0/1, default 1), "gemm_impl" (0 = tcgen05, 1 = SIMT reference kernel),
- * "lstm_impl" (0 = default).  Returns STZ_E_ARG for unknown keys. */
+ * "lstm_impl" (0 = default), "profile" (0/1, see stz_profile_read).  Returns STZ_E_ARG for
+ * unknown keys. */
 int stz_set_option(stz_handle* h, const char* key, int value);
+
+/* Profile mode (set_option "profile" = 1; setting it also clears the records): sample_style /
+ * predict_duration run eagerly (no CUDA graph) with a CUDA-event pair around every kernel launch.
+ * stz_profile_read synchronises and returns, for one kernel class, the summed event time (ms), the
+ * summed algorithmic work (flops for classes 0,1,3,4; bytes for 2,5) and the launch count.
+ * Classes: 0 tcgen05 GEMM, 1 fused attention, 2 LayerNorm+modulate, 3 fp32 CUDA-core GEMM,
+ * 4 LSTM recurrence, 5 predictor elementwise, 6 other. */
+int stz_profile_read(stz_handle* h, int kernel_class, double* ms, double* work, int64_t* launches);
 
 /* Copies the fp32 residual stream h [B*K*2, d_model] (row = (b*K+k)*2 + branch) into
  * tap_dev after (eval, layer, stage) during eager (use_graph=0) runs; stage 0/1/2 = after the

@@ -70,6 +70,30 @@ struct stz_handle {
   int tap_eval = -1, tap_layer = -1, tap_stage = -1;
   float* tap_buf = nullptr;
   bool capturing = false;
+  // profile mode (bench.py roofline leg): CUDA-event pair around every launch, eager execution
+  int profile = 0;
+  struct ProfRec { int cls; cudaEvent_t a, b; double work; };
+  std::vector<ProfRec> prof;
+};
+
+// Kernel classes of the profile buckets (include/stz.h: stz_profile_read).
+enum ProfClass : int { PC_GEMM_TC = 0, PC_ATTN = 1, PC_LN = 2, PC_LINEAR_F32 = 3, PC_LSTM = 4, PC_PRED_EW = 5, PC_OTHER = 6, PC_COUNT = 7 };
+
+struct ProfScope {
+  stz_handle* H;
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(stz_handle* H_, cudaStream_t st_, int cls, double work) : H(H_), st(st_) {
+    if (!H || !H->profile || H->capturing) return;
+    stz_handle::ProfRec r{cls, nullptr, nullptr, work};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    H->prof.push_back(r);
+    idx = (int)H->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(H->prof[idx].b, st);
+  }
 };
 
 static int fail(stz_handle* H, int code, const char* fmt, ...) {
@@ -153,6 +177,7 @@ static int launch_gemm_tc(stz_handle* H, cudaStream_t st, const bf16* A, int lda
     return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", p.M, p.N, p.K);
   constexpr int smem = gemm_smem_bytes<GEMM_BN, GEMM_STAGES>();
   dim3 grid(p.N / GEMM_BN, cdiv(p.M, GEMM_BM));
+  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * p.N * p.K);
   gemm_tc_kernel<GEMM_BN, EPI, GEMM_STAGES><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
   if (H) { KCHECK(H); } else if (cudaGetLastError() != cudaSuccess) return STZ_E_CUDA;
   return 0;
@@ -194,6 +219,7 @@ static int gemm(stz_handle* H, cudaStream_t st, int impl, const bf16* A, int lda
 static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, int ld1, int K1, const float* X2, int ld2,
                       int K2, const float* W, const float* b, float* Y, int ldy, int M, int N) {
   dim3 grid(cdiv(N, 64), cdiv(M, 64));
+  ProfScope ps(H, st, PC_LINEAR_F32, 2.0 * M * N * (K1 + K2));
   if (act == ACT_SILU)
     linear_f32_kernel<ACT_SILU><<<grid, 256, 0, st>>>(X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
   else
@@ -205,6 +231,7 @@ static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, 
 static int ln_mod(stz_handle* H, cudaStream_t st, const float* h, int rows, int D, const float* mod, int n_mod,
                   int shift_off, int scale_off, int rows_per_utt, bf16* out) {
   dim3 grid(cdiv(rows, 8));
+  ProfScope ps(H, st, PC_LN, (double)rows * D * 6.0);  // fp32 in + bf16 out
   switch (D / 128) {
     case 1: ln_mod_kernel<1><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
     case 2: ln_mod_kernel<2><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
@@ -501,6 +528,24 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
   return 0;
 }
 
+extern "C" int stz_profile_read(stz_handle* H, int cls, double* ms, double* work, int64_t* launches) {
+  if (!H || cls < 0 || cls >= PC_COUNT) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  CK(H, cudaDeviceSynchronize());
+  double t = 0, w = 0;
+  int64_t n = 0;
+  for (auto& r : H->prof) {
+    if (r.cls != cls) continue;
+    float e = 0.f;
+    CK(H, cudaEventElapsedTime(&e, r.a, r.b));
+    t += e; w += r.work; ++n;
+  }
+  if (ms) *ms = t;
+  if (work) *work = w;
+  if (launches) *launches = n;
+  return 0;
+}
+
 extern "C" int stz_debug_set_tap(stz_handle* H, int eval, int layer, int stage, float* tap_dev) {
   if (!H) return STZ_E_ARG;
   H->tap_eval = eval; H->tap_layer = layer; H->tap_stage = stage; H->tap_buf = tap_dev;
@@ -518,6 +563,9 @@ static int tap(stz_handle* H, cudaStream_t st, int e, int l, int s, size_t R) {
 
 static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B) {
   dim3 grid(H->cfg.n_heads, B);
+  int n_keys = 0;
+  for (int i = 0; i < ap.nseg; ++i) n_keys += ap.seg[i].n;
+  ProfScope ps(H, st, PC_ATTN, 4.0 * B * H->cfg.n_heads * ap.n_q * (double)n_keys * ATT_DH);
   attention_kernel<<<grid, cdiv(ap.n_q, 16) * 32, 0, st>>>(ap);
   KCHECK(H);
   return 0;
@@ -668,7 +716,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
 
   // ---- the evaluation loop: one CUDA graph per (B, T, P, E, kind) ----------------------------
   const bool tapping = H->tap_buf != nullptr;
-  if (H->use_graph && !tapping) {
+  if (H->use_graph && !tapping && !H->profile) {
     auto key = std::make_tuple(B, T, P, E, kind * 2 + (tmask ? 1 : 0) + (pmask ? 4 : 0));
     auto it = H->graphs.find(key);
     // the graph bakes in the mask pointers: masks are copied into library-owned staging first
@@ -746,8 +794,11 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
                      w.G + (size_t)dr * 4 * h, 8 * h, BT, 4 * h));
     }
     float* xo = bufs[l & 1];
-    lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
-    KCHECK(H);
+    {
+      ProfScope ps(H, st, PC_LSTM, 2.0 * BT * 2.0 * h * 4.0 * h);
+      lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
+      KCHECK(H);
+    }
     if (l < c.n_lstm - 1) {
       const std::string p = "adaln" + std::to_string(l) + ".";
       RET(linear_f32(H, st, ACT_NONE, w.stok, ds, ds, nullptr, 0, 0, W32(H, p + "w"), W32(H, p + "b"), w.gb, 2 * dh, BT, 2 * dh));

@@ -72,6 +72,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_launch_count.argtypes = [vp]
     lib.stz_set_option.restype = i32
     lib.stz_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.stz_profile_read.restype = i32
+    lib.stz_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     lib.stz_debug_set_tap.restype = i32
     lib.stz_debug_set_tap.argtypes = [vp, i32, i32, i32, vp]
     lib.stz_op_gemm_bf16.restype = i32
@@ -85,7 +87,8 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
-                    "stz_synthesize_host", "stz_launch_count", "stz_set_option", "stz_debug_set_tap",
+                    "stz_synthesize_host", "stz_launch_count", "stz_set_option", "stz_profile_read",
+                    "stz_debug_set_tap",
                     "stz_op_gemm_bf16")
 
 
@@ -148,6 +151,17 @@ class StyleTTSZSPath:
 
     def launch_count(self) -> int:
         return int(self.lib.stz_launch_count(self._h))
+
+    PROFILE_CLASSES = ("gemm_tc", "attention", "ln_mod", "linear_f32", "lstm_rec", "pred_ew", "other")
+
+    def profile_read(self):
+        """{class: (ms, work, launches)} accumulated since set_option('profile', 1)."""
+        out = {}
+        for i, name in enumerate(self.PROFILE_CLASSES):
+            ms, work, n = C.c_double(), C.c_double(), C.c_int64()
+            self._check(self.lib.stz_profile_read(self._h, i, C.byref(ms), C.byref(work), C.byref(n)), "profile_read")
+            out[name] = (ms.value, work.value, n.value)
+        return out
 
     def set_tap(self, ev: int, layer: int, stage: int, buf: Optional[torch.Tensor]):
         self._check(self.lib.stz_debug_set_tap(self._h, ev, layer, stage, _ptr(buf)), "set_tap")
@@ -239,11 +253,3 @@ def op_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
     if rc != 0:
         raise StzError(f"stz_op_gemm_bf16 failed ({rc}): {lib.stz_last_error(None).decode()}")
     return out
-
-
-def shard_utterances(lengths: Sequence[int], world_size: int) -> List[List[int]]:
-    """Multi-GPU partitioning: utterances are independent, so the batch is split
-    with no collective.  Length-sorted round-robin keeps per-rank padded work similar; returns the
-    utterance indices of each rank (each list sorted by length, longest first)."""
-    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
-    return [order[r::world_size] for r in range(world_size)]

@@ -1,0 +1,72 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo processes shard a variable-length batch, run the
+path's module API on their shard (the oracle stands in for the CUDA path) and gather on the host.
+The result must equal the unsharded run (utterances are independent: SURVEY.md §8e)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import styletts_zs_b200 as stz
+
+
+def test_shard_utterances_balanced_and_complete():
+    lens = [5, 300, 17, 512, 64, 64, 16, 211, 90]
+    for world in (1, 2, 4, 8):
+        sh = stz.shard_utterances(lens, world)
+        assert sorted(i for s in sh for i in s) == list(range(len(lens)))
+        assert max(len(s) for s in sh) - min(len(s) for s in sh) <= 1
+        for s in sh:
+            assert [lens[i] for i in s] == sorted((lens[i] for i in s), reverse=True)
+    assert stz.shard_utterances([], 2) == [[], []]
+
+
+def _oracle_compute(cfg, w):
+    from oracle.model import OraclePath
+    o = OraclePath(cfg, w)
+
+    def compute(text, mask, prompt, pmask, noise):
+        z = o.sample_style(text, prompt, 2, 2.0, text_mask=mask, prompt_mask=pmask, noise=noise)
+        return z, o.predict_duration(text, z, text_mask=mask)
+    return compute
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    cfg = stz.TINY
+    w = stz.init_weights(cfg, 0)
+    inp = stz.synthetic_inputs(cfg, 5, 14, steps=2, seed=11, var_len=(3, 14))
+    res = stz.synthesize_sharded(_oracle_compute(cfg, w), inp, rank, world)
+    if rank == 0:
+        q.put((res[0], res[1]))
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_matches_single_process():
+    cfg = stz.TINY
+    w = stz.init_weights(cfg, 0)
+    inp = stz.synthetic_inputs(cfg, 5, 14, steps=2, seed=11, var_len=(3, 14))
+    ref_style, ref_dur = stz.synthesize_sharded(_oracle_compute(cfg, w), inp, 0, 1)
+    full = _oracle_compute(cfg, w)(inp["text_emb"], inp["text_mask"], inp["prompt_feats"], inp["prompt_mask"], inp["noise"])
+    assert torch.allclose(ref_style, full[0], atol=2e-5) and torch.equal(ref_dur, full[1].to(torch.int32))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    style, dur = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.allclose(style, ref_style, atol=2e-5)
+    assert torch.equal(dur, ref_dur)
