@@ -102,7 +102,7 @@ int stz_synthesize_host(stz_handle* h, const float* text_emb, const uint8_t* tex
 /* Number of kernels launched by this handle since creation (graph nodes count per replay). */
 int64_t stz_launch_count(const stz_handle* h);
 
-/* Knobs: "use_graph" (0/1, default 1), "gemm_impl" (0 = tcgen05, 1 = SIMT reference kernel),
+/* Knobs: "use_graph" (0/1, default 1), "gemm_impl" (0 = tcgen05 persistent v2, 1 = SIMT cross-check kernel, 2 = tcgen05 v1),
  * "lstm_impl" (0 = default), "profile" (0/1, see stz_profile_read).  Returns STZ_E_ARG for
  * unknown keys. */
 int stz_set_option(stz_handle* h, const char* key, int value);

@@ -29,11 +29,12 @@ class _Ops:
     """GEMM operand precision.  emulate_bf16=True rounds tensor-core operands the way the CUDA
     path does (bf16 operands, fp32 accumulate) — a diagnostic for tests, never the reference."""
 
-    def __init__(self, emulate_bf16: bool):
+    def __init__(self, emulate_bf16: bool, exact_tags=()):
         self.emu = emulate_bf16
+        self.exact_tags = set(exact_tags)   # ops the CUDA path runs in split-bf16 (fp32-grade) precision
 
-    def lin(self, x, w, b=None):
-        if self.emu:
+    def lin(self, x, w, b=None, tag=None):
+        if self.emu and tag not in self.exact_tags:
             x, w = _bf16(x), _bf16(w)
         return F.linear(x, w, b)
 
@@ -81,8 +82,8 @@ class Conditioning:
                  ops: _Ops):
         B = text_emb.shape[0]
         self.B = B
-        ct = layer_norm(ops.lin(text_emb, W["ctx_text.w"], W["ctx_text.b"]) + W["type_emb"][0])
-        cp = layer_norm(ops.lin(prompt_feats, W["ctx_prompt.w"], W["ctx_prompt.b"]) + W["type_emb"][1])
+        ct = layer_norm(ops.lin(text_emb, W["ctx_text.w"], W["ctx_text.b"], tag="ctx") + W["type_emb"][0])
+        cp = layer_norm(ops.lin(prompt_feats, W["ctx_prompt.w"], W["ctx_prompt.b"], tag="ctx") + W["type_emb"][1])
         cn = layer_norm(W["null_tok"] + W["type_emb"][1]).view(1, 1, -1).expand(B, 1, -1)
         # cond branch: [text ; prompt], uncond branch: [text ; null token]
         self.ctx = (torch.cat([ct, cp], 1), torch.cat([ct, cn], 1))
@@ -95,7 +96,7 @@ class Conditioning:
         self.kv = []
         for l in range(cfg.n_layers):
             w, b = W[f"l{l}.kv2.w"], W[f"l{l}.kv2.b"]
-            self.kv.append(tuple(ops.lin(c, w, b) for c in self.ctx))
+            self.kv.append(tuple(ops.lin(c, w, b, tag="kv2") for c in self.ctx))
 
 
 def denoiser_F(cfg, W, x_in: torch.Tensor, c_noise: float, cond: Conditioning, branch: int,
@@ -105,28 +106,28 @@ def denoiser_F(cfg, W, x_in: torch.Tensor, c_noise: float, cond: Conditioning, b
     feat = torch.tensor(S.time_features(c_noise, cfg.d_time), dtype=torch.float64).to(torch.float32)
     t = F.linear(F.silu(F.linear(feat, W["time.w1"], W["time.b1"])), W["time.w2"], W["time.b2"])
     c = F.silu(t[None, :] + cond.pooled[branch])                       # [B,d]
-    mod = ops.lin(c, W["mod.w"], W["mod.b"])                           # [B,(9L+2)d]
+    mod = ops.lin(c, W["mod.w"], W["mod.b"], tag="mod")                         # [B,(9L+2)d]
 
     def m(i):  # modulation chunk i -> [B,1,d]
         return mod[:, i * d:(i + 1) * d][:, None, :]
 
-    h = ops.lin(x_in, W["in.w"], W["in.b"]) + W["pos"][None]
+    h = ops.lin(x_in, W["in.w"], W["in.b"], tag="in") + W["pos"][None]
     for l in range(L):
         p, o = f"l{l}.", 9 * l
         u = layer_norm(h) * (1 + m(o + 1)) + m(o + 0)
-        qkv = ops.lin(u, W[p + "qkv.w"], W[p + "qkv.b"])
+        qkv = ops.lin(u, W[p + "qkv.w"], W[p + "qkv.b"], tag="qkv")
         a = attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], H, None, ops)
-        h = h + m(o + 2) * ops.lin(a, W[p + "o.w"], W[p + "o.b"])
+        h = h + m(o + 2) * ops.lin(a, W[p + "o.w"], W[p + "o.b"], tag="o")
         u = layer_norm(h) * (1 + m(o + 4)) + m(o + 3)
-        q = ops.lin(u, W[p + "q2.w"], W[p + "q2.b"])
+        q = ops.lin(u, W[p + "q2.w"], W[p + "q2.b"], tag="q2")
         kv = cond.kv[l][branch]
         a = attention(q, kv[..., :d], kv[..., d:], H, cond.ctx_mask[branch], ops)
-        h = h + m(o + 5) * ops.lin(a, W[p + "o2.w"], W[p + "o2.b"])
+        h = h + m(o + 5) * ops.lin(a, W[p + "o2.w"], W[p + "o2.b"], tag="o2")
         u = layer_norm(h) * (1 + m(o + 7)) + m(o + 6)
-        f = gelu_tanh(ops.lin(u, W[p + "ff1.w"], W[p + "ff1.b"]))
-        h = h + m(o + 8) * ops.lin(f, W[p + "ff2.w"], W[p + "ff2.b"])
+        f = gelu_tanh(ops.lin(u, W[p + "ff1.w"], W[p + "ff1.b"], tag="ff1"))
+        h = h + m(o + 8) * ops.lin(f, W[p + "ff2.w"], W[p + "ff2.b"], tag="ff2")
     u = layer_norm(h) * (1 + m(9 * L + 1)) + m(9 * L)
-    return ops.lin(u, W["out.w"], W["out.b"])
+    return ops.lin(u, W["out.w"], W["out.b"], tag="out")
 
 
 def guided_denoise(cfg, W, x, sigma: float, cond: Conditioning, cfg_scale: float, ops: _Ops,
@@ -167,11 +168,11 @@ def sample_loop(cfg, denoise, noise: torch.Tensor, steps: int, sampler: int) -> 
 class OraclePath:
     """Same module API as the CUDA path, CPU fp32."""
 
-    def __init__(self, cfg, weights: torch.Tensor, emulate_bf16: bool = False):
+    def __init__(self, cfg, weights: torch.Tensor, emulate_bf16: bool = False, exact_tags=()):
         from styletts_zs_b200.spec import view_weights
         self.cfg = cfg
         self.W = view_weights(cfg, weights.detach().to(torch.float32).cpu())
-        self.ops = _Ops(emulate_bf16)
+        self.ops = _Ops(emulate_bf16, exact_tags)
         self._lstm = None
 
     # ---- a-7 ------------------------------------------------------------------------

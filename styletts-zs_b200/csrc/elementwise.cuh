@@ -5,6 +5,16 @@
 
 namespace stz {
 
+// lo parts of a split-bf16 representation: lo = bf16(x - float(hi)), for 4 packed values
+__device__ __forceinline__ uint2 split_lo4(const float4& x, const uint2& hi) {
+  const float h0 = __uint_as_float(hi.x << 16), h1 = __uint_as_float(hi.x & 0xffff0000u);
+  const float h2 = __uint_as_float(hi.y << 16), h3 = __uint_as_float(hi.y & 0xffff0000u);
+  uint2 lo;
+  lo.x = pack_bf16(x.x - h0, x.y - h1);
+  lo.y = pack_bf16(x.z - h2, x.w - h3);
+  return lo;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -41,7 +51,7 @@ __global__ void __launch_bounds__(256) cast_pool_kernel(const float* __restrict_
 template <int VPL>
 __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h, int rows, const float* __restrict__ mod,
                                                      int n_mod, int shift_off, int scale_off, int rows_per_utt,
-                                                     __nv_bfloat16* __restrict__ out) {
+                                                     __nv_bfloat16* __restrict__ out, int split3) {
   constexpr int D = 128 * VPL;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -75,7 +85,14 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h
     }
     uint2 u;
     u.x = pack_bf16(y.x, y.y); u.y = pack_bf16(y.z, y.w);
-    *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D + (i * 32 + lane) * 4) = u;
+    if (!split3) {
+      *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D + (i * 32 + lane) * 4) = u;
+    } else {  // split-bf16 A operand [hi | lo | hi] (row stride 3D) of a fp32-grade GEMM, see split3_weights_kernel
+      __nv_bfloat16* o = out + static_cast<size_t>(row) * 3 * D + (i * 32 + lane) * 4;
+      *reinterpret_cast<uint2*>(o) = u;
+      *reinterpret_cast<uint2*>(o + D) = split_lo4(y, u);
+      *reinterpret_cast<uint2*>(o + 2 * D) = u;
+    }
   }
 }
 
@@ -95,7 +112,7 @@ __global__ void __launch_bounds__(256) cvec_kernel(const float* __restrict__ tem
   }
 }
 
-// x = sigma0 * noise0 ; xin rows 2j, 2j+1 = bf16(c_in0 * x[j])
+// x = sigma0 * noise0 ; xin rows 2j, 2j+1 = split-bf16 [hi | lo | hi] of c_in0 * x[j]  (row stride 3D)
 __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict__ noise0, float* __restrict__ x,
                                                          __nv_bfloat16* __restrict__ xin, size_t n_rows, int D,
                                                          float sigma0, float cin0) {
@@ -107,10 +124,17 @@ __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict
     float4 v = __ldg(reinterpret_cast<const float4*>(noise0) + i);
     v.x *= sigma0; v.y *= sigma0; v.z *= sigma0; v.w *= sigma0;
     reinterpret_cast<float4*>(x)[i] = v;
+    const float4 y = make_float4(cin0 * v.x, cin0 * v.y, cin0 * v.z, cin0 * v.w);
     uint2 u;
-    u.x = pack_bf16(cin0 * v.x, cin0 * v.y); u.y = pack_bf16(cin0 * v.z, cin0 * v.w);
-    *reinterpret_cast<uint2*>(xin + (2 * j) * D + c) = u;
-    *reinterpret_cast<uint2*>(xin + (2 * j + 1) * D + c) = u;
+    u.x = pack_bf16(y.x, y.y); u.y = pack_bf16(y.z, y.w);
+    const uint2 lo = split_lo4(y, u);
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      __nv_bfloat16* o = xin + (2 * j + br) * 3 * D + c;
+      *reinterpret_cast<uint2*>(o) = u;
+      *reinterpret_cast<uint2*>(o + D) = lo;
+      *reinterpret_cast<uint2*>(o + 2 * D) = u;
+    }
   }
 }
 
@@ -118,6 +142,43 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
+}
+
+// W fp32 [N, K] -> W3 bf16 [N, 3K] = [hi | hi | lo]: with A3 = [hi | lo | hi] the plain bf16 GEMM over 3K
+// evaluates a_hi w_hi + a_lo w_hi + a_hi w_lo, i.e. the product to ~2^-16 relative (fp32-grade).  Used for the
+// denoiser's input and output projections, whose rounding error is not damped by later layers.
+__global__ void __launch_bounds__(256) split3_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w3,
+                                                             size_t N, size_t K) {
+  const size_t n = N * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / K, k = i % K;
+    const float x = w[i];
+    const __nv_bfloat16 hi = __float2bfloat16(x);
+    const __nv_bfloat16 lo = __float2bfloat16(x - __bfloat162float(hi));
+    __nv_bfloat16* o = w3 + r * 3 * K + k;
+    o[0] = hi; o[K] = hi; o[2 * K] = lo;
+  }
+}
+
+// Activation side of a split-bf16 GEMM: src fp32 [M, K] (row stride ld) -> dst bf16 row r, three K-segments of
+// width segK: [hi | lo | hi], this source occupying columns [off, off + K) of each segment.  K % 4 == 0.
+__global__ void __launch_bounds__(256) split3_rows_kernel(const float* __restrict__ src, int ld, int K,
+                                                          __nv_bfloat16* __restrict__ dst, int ldd, int segK, int off, size_t M) {
+  const int kv = K >> 2;
+  const size_t n = M * kv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / kv;
+    const int k = static_cast<int>(i % kv) * 4;
+    const float4 x = *reinterpret_cast<const float4*>(src + r * ld + k);
+    uint2 hi;
+    hi.x = pack_bf16(x.x, x.y); hi.y = pack_bf16(x.z, x.w);
+    __nv_bfloat16* o = dst + r * ldd + off + k;
+    *reinterpret_cast<uint2*>(o) = hi;
+    *reinterpret_cast<uint2*>(o + segK) = split_lo4(x, hi);
+    *reinterpret_cast<uint2*>(o + 2 * segK) = hi;
+  }
 }
 
 // y[i] = a[i] + b[i % nb]   (bias folding at create time)

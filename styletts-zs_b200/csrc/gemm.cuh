@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
+#include "elementwise.cuh"
 
 namespace stz {
 
@@ -130,9 +131,14 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int m, int n
         *reinterpret_cast<float4*>((to_mid ? p.xmid : p.x) + so + j) = o;
         if (p.tap != nullptr) *reinterpret_cast<float4*>(p.tap + so + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
+      // next eval's input c_in(sigma') x' as the split-bf16 A operand [hi | lo | hi] (row stride 3N)
+      const float4 y = make_float4(cin * o.x, cin * o.y, cin * o.z, cin * o.w);
       uint2 u;
-      u.x = pack_bf16(cin * o.x, cin * o.y); u.y = pack_bf16(cin * o.z, cin * o.w);
-      *reinterpret_cast<uint2*>(p.xin + static_cast<size_t>(m) * p.N + n0 + j) = u;
+      u.x = pack_bf16(y.x, y.y); u.y = pack_bf16(y.z, y.w);
+      __nv_bfloat16* xo = p.xin + static_cast<size_t>(m) * 3 * p.N + n0 + j;
+      *reinterpret_cast<uint2*>(xo) = u;
+      *reinterpret_cast<uint2*>(xo + p.N) = split_lo4(y, u);
+      *reinterpret_cast<uint2*>(xo + 2 * p.N) = u;
     }
   }
 }

@@ -1,0 +1,263 @@
+// gemm2_kernel — the product GEMM of the style denoiser: C[M,N] = A[M,K] · W[N,K]^T (+ fused epilogue).
+//
+// Persistent, warp-specialised, one CTA per SM (grid = min(#tiles, #SMs)):
+//   warp 0      TMA producer: 128B-swizzled K-major tiles of A (128 x 64) and W (BN x 64) into a smem ring
+//   warp 1      TMEM owner + MMA issuer: tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), 128 x BN accumulator,
+//               DOUBLE-BUFFERED in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop of i+1
+//   warps 2..5  epilogue: tcgen05.ld (thread = row) -> bias / GELU / gate -> 128B-swizzled smem staging ->
+//               TMA store (cp.async.bulk.tensor) or, for the gated residual update h += gate * (acc + b),
+//               TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32): h is never read by an SM.
+// Barriers: full/empty per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator (MMA <-> epilogue).
+//
+// Tiles are visited n-fastest so CTAs running concurrently share A row-blocks in L2.  Rows past M are
+// zero-filled on load and clipped on store by the tensor maps (no tail code).
+#pragma once
+#include "gemm.cuh"
+
+namespace stz {
+
+constexpr int G2_THREADS = 192;
+constexpr int G2_STAGE_BYTES_EPI = 8 * 4096;  // 4 epilogue warps x 2 staging buffers x (32 rows x 128 B)
+
+template <int BN>
+constexpr int g2_stages() { return BN == 256 ? 4 : (BN == 192 ? 4 : 6); }
+template <int BN>
+constexpr int g2_smem_bytes() { return g2_stages<BN>() * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + G2_STAGE_BYTES_EPI + 1024; }
+template <int BN>
+constexpr int g2_tmem_cols() { return BN == 128 ? 256 : 512; }
+
+// ---- TMA store / reduce helpers -----------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.0f + tanh_fast(k0 * (x + k1 * x * x * x)));
+}
+
+// Staged epilogues: EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_GATE_RES.  Direct (row-per-thread global
+// access, legacy epilogue_row32): EPI_F32_POS, EPI_SAMPLER — one launch each per denoiser evaluation.
+template <int EPI>
+constexpr bool g2_staged() { return EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_GATE_RES; }
+template <int EPI>
+constexpr bool g2_out_bf16() { return EPI == EPI_BF16 || EPI == EPI_GELU_BF16; }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmC,
+                                                              const GemmParams p) {
+  constexpr int STAGES = g2_stages<BN>();
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr int TMEM_COLS = g2_tmem_cols<BN>();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + STAGES * (A_BYTES + B_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = p.K / GEMM_BK;
+  const int tiles_n = p.N / BN;
+  const int n_tiles = tiles_n * ((p.M + GEMM_BM - 1) / GEMM_BM);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (g2_staged<EPI>()) prefetch_tmap(&tmC);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK),
+              "r"(p.a_row0 + tile_m * GEMM_BM)
+              : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])),
+              "r"(kb * GEMM_BK), "r"(tile_n * BN)
+              : "memory");
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const uint32_t stage_buf = epi_base + (warp - 2) * 8192;
+    uint32_t acc = 0, acc_phase = 0;
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+      const int m0 = tile_m * GEMM_BM + q * 32;
+      const int m = m0 + lane;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if constexpr (g2_staged<EPI>()) {
+        constexpr int CW = g2_out_bf16<EPI>() ? 64 : 32;  // columns per staged chunk: 128 B per row
+        const float* gate = nullptr;
+        if constexpr (EPI == EPI_GATE_RES) {
+          const int mm = m < p.M ? m : p.M - 1;
+          gate = p.mod + static_cast<size_t>((mm / p.rows_per_utt) * 2 + (mm & 1)) * p.n_mod + p.gate_off;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / CW; ++c) {
+          const int n0 = tile_n * BN + c * CW;
+          float v[CW];
+          {
+            uint32_t r[32];
+            tmem_ld32(t_addr + c * CW, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if constexpr (CW == 64) {
+              tmem_ld32(t_addr + c * CW + 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r[j]);
+            }
+          }
+          if (c == BN / CW - 1) {  // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = gelu_tanh_fast(v[j]);
+          }
+          if constexpr (EPI == EPI_GATE_RES) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(gate + n0 + j));
+              v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+            }
+          }
+          // staging buffer `buf` must have been drained by the TMA store issued two chunks ago
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const uint32_t sb = stage_buf + buf * 4096 + lane * 128;
+          if constexpr (g2_out_bf16<EPI>()) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(sb + ((j ^ (lane & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(sb + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && m0 < p.M) {
+            if constexpr (EPI == EPI_GATE_RES) tma_reduce_add_2d(&tmC, stage_buf + buf * 4096, n0, m0);
+            else tma_store_2d(&tmC, stage_buf + buf * 4096, n0, m0);
+          }
+          if (lane == 0) bulk_commit();
+          buf ^= 1;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_addr + c * 32, r);
+          tmem_ld_wait();
+          if (c == BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_row32<EPI>(p, m, tile_n * BN + c * 32, v);
+        }
+      }
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace stz

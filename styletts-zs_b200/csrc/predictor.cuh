@@ -21,7 +21,7 @@ __global__ void lens_kernel(const uint8_t* __restrict__ mask, int* __restrict__ 
 // a-8: per-token style summary.  q [B*T, ds], k/v [B*K, ds] (already projected), out [B*T, ds];
 // heads of width 32 (lane = channel).  One warp per token, online softmax over the K style codes.
 __global__ void __launch_bounds__(256) style_pool_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
-                                                              const float* __restrict__ v, float* __restrict__ out,
+                                                              const float* __restrict__ v, int ldkv, float* __restrict__ out,
                                                               int n_tok, int T, int K, int ds, float scale) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) style_pool_attn_kernel(const float* __res
     const float qv = q[static_cast<size_t>(tok) * ds + h * 32 + lane] * scale;
     float m = -INFINITY, l = 0.f, acc = 0.f;
     for (int j = 0; j < K; ++j) {
-      const size_t r = (static_cast<size_t>(b) * K + j) * ds + h * 32 + lane;
+      const size_t r = (static_cast<size_t>(b) * K + j) * ldkv + h * 32 + lane;
       const float s = warp_sum(qv * __ldg(k + r));
       const float mn = fmaxf(m, s);
       const float a = expf(m - mn), pj = expf(s - mn);
@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(1024) lstm_rec_kernel(const float* __restrict_
 // a-9: x[r] = (LN(x[r]) * (1 + gamma[r]) + beta[r]) * mask[r], gb[r] = [gamma | beta].  In place.
 template <int VPL>
 __global__ void __launch_bounds__(256) adaln_pred_kernel(float* __restrict__ x, const float* __restrict__ gb,
-                                                         const uint8_t* __restrict__ mask, int rows) {
+                                                         const uint8_t* __restrict__ mask, int rows,
+                                                         __nv_bfloat16* __restrict__ a3, int ldd, int segK) {
   constexpr int D = 128 * VPL;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -136,7 +137,15 @@ __global__ void __launch_bounds__(256) adaln_pred_kernel(float* __restrict__ x, 
   float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
   if (mask != nullptr && mask[row] == 0) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) xr[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < VPL; ++i) {
+      xr[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a3 != nullptr) {
+        __nv_bfloat16* o = a3 + static_cast<size_t>(row) * ldd + (i * 32 + lane) * 4;
+        *reinterpret_cast<uint2*>(o) = make_uint2(0, 0);
+        *reinterpret_cast<uint2*>(o + segK) = make_uint2(0, 0);
+        *reinterpret_cast<uint2*>(o + 2 * segK) = make_uint2(0, 0);
+      }
+    }
     return;
   }
   float4 v[VPL];
@@ -158,8 +167,17 @@ __global__ void __launch_bounds__(256) adaln_pred_kernel(float* __restrict__ x, 
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const float4 ga = __ldg(gr + i * 32 + lane), be = __ldg(gr + (D >> 2) + i * 32 + lane);
-    xr[i * 32 + lane] = make_float4(v[i].x * rstd * (1.f + ga.x) + be.x, v[i].y * rstd * (1.f + ga.y) + be.y,
-                                    v[i].z * rstd * (1.f + ga.z) + be.z, v[i].w * rstd * (1.f + ga.w) + be.w);
+    const float4 y = make_float4(v[i].x * rstd * (1.f + ga.x) + be.x, v[i].y * rstd * (1.f + ga.y) + be.y,
+                                 v[i].z * rstd * (1.f + ga.z) + be.z, v[i].w * rstd * (1.f + ga.w) + be.w);
+    xr[i * 32 + lane] = y;
+    if (a3 != nullptr) {  // next layer's split-bf16 GEMM operand (x part of [x | s_tok])
+      uint2 hi;
+      hi.x = pack_bf16(y.x, y.y); hi.y = pack_bf16(y.z, y.w);
+      __nv_bfloat16* o = a3 + static_cast<size_t>(row) * ldd + (i * 32 + lane) * 4;
+      *reinterpret_cast<uint2*>(o) = hi;
+      *reinterpret_cast<uint2*>(o + segK) = split_lo4(y, hi);
+      *reinterpret_cast<uint2*>(o + 2 * segK) = hi;
+    }
   }
 }
 
@@ -195,6 +213,210 @@ __global__ void __launch_bounds__(256) dur_head_kernel(const float* __restrict__
     if (presum != nullptr) presum[row] = total;
     dur[row] = ok ? static_cast<int32_t>(fmaxf(rintf(total), 1.0f)) : 0;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// a-9, product path: persistent thread-block-cluster BiLSTM recurrence (h = 256).
+//
+// One cluster of 8 CTAs advances NB sequences of one direction through all their time steps.
+// CTA r owns hidden units [32r, 32r+32) = 128 gate columns; its 128 x 256 fp32 slice of W_hh lives
+// in REGISTERS for the whole kernel (512 threads x 64 values: thread = (gate column, k-quarter)), so a
+// step costs no weight traffic at all.  h_t of the NB sequences is replicated in every CTA's shared
+// memory (double-buffered); after the pointwise update each CTA pushes its 32 new units to the 7 peers
+// with st.shared::cluster (DSMEM) and one barrier.cluster per step orders the exchange.
+// Sequences are visited in length-sorted order (perm) so the NB sequences of a cluster have similar
+// lengths; packed-sequence semantics as lstm_rec_kernel (reverse starts at len-1, padded outputs 0).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_t rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+// lens[b] (prefix-mask popcount) and perm = sequence indices sorted by length, longest first (stable).
+__global__ void __launch_bounds__(1024) lens_perm_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lens,
+                                                         int* __restrict__ perm, int B, int T) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int n = T;
+    if (mask != nullptr) {
+      n = 0;
+      for (int t = 0; t < T; ++t) n += mask[static_cast<size_t>(b) * T + t] ? 1 : 0;
+    }
+    lens[b] = n;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int lb = lens[b];
+    int rank = 0;
+    for (int j = 0; j < B; ++j) {
+      const int lj = lens[j];
+      rank += (lj > lb || (lj == lb && j < b)) ? 1 : 0;
+    }
+    perm[rank] = b;
+  }
+}
+
+constexpr int LC_H = 256, LC_CS = 8, LC_UPC = 32, LC_COLS = 128, LC_SL = 8, LC_KS = 32, LC_THREADS = 512;
+
+// DSMEM store that signals the destination CTA's mbarrier with the bytes it delivered (no fence, no cluster barrier)
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "f"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+template <int NB>
+constexpr int lstm_cluster_smem() { return (2 * NB * LC_H + LC_SL * NB * LC_COLS) * 4; }
+
+// Thread layout of the matrix-vector phase: warp w -> k-slice (w >> 1) of 32, gate pair 2*(w & 1), lane = unit;
+// each thread keeps 2 columns x 32 k of W_hh in registers, so one broadcast LDS.128 of h feeds 8 FMAs.
+template <int NB>
+__global__ void __cluster_dims__(LC_CS, 1, 1) __launch_bounds__(LC_THREADS, 1)
+lstm_cluster_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const int* __restrict__ lens,
+                    const int* __restrict__ perm, float* __restrict__ out, int B, int T) {
+  extern __shared__ __align__(16) float lc_smem[];
+  float (*h_s)[NB][LC_H] = reinterpret_cast<float (*)[NB][LC_H]>(lc_smem);                               // [2][NB][H]
+  float (*part_s)[NB][LC_COLS] = reinterpret_cast<float (*)[NB][LC_COLS]>(lc_smem + 2 * NB * LC_H);      // [SL][NB][COLS]
+  __shared__ __align__(8) uint64_t hbar[2];   // hbar[b]: all 8 CTAs' slices of h have landed in h_s[b]
+  __shared__ int len_s[NB], seq_s[NB];
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int group = blockIdx.x / LC_CS, dir = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = warp >> 1, g0 = (warp & 1) * 2;
+
+  float wa[LC_KS], wb[LC_KS];
+  {
+    const size_t row = static_cast<size_t>(dir) * 4 * LC_H + rank * LC_UPC + lane;
+    const float4* ra = reinterpret_cast<const float4*>(Whh + (row + g0 * LC_H) * LC_H + slice * LC_KS);
+    const float4* rb = reinterpret_cast<const float4*>(Whh + (row + (g0 + 1) * LC_H) * LC_H + slice * LC_KS);
+#pragma unroll
+    for (int i = 0; i < LC_KS / 4; ++i) {
+      const float4 a = __ldg(ra + i), b = __ldg(rb + i);
+      wa[4 * i] = a.x; wa[4 * i + 1] = a.y; wa[4 * i + 2] = a.z; wa[4 * i + 3] = a.w;
+      wb[4 * i] = b.x; wb[4 * i + 1] = b.y; wb[4 * i + 2] = b.z; wb[4 * i + 3] = b.w;
+    }
+  }
+  if (tid < NB) {
+    const int idx = group * NB + tid;
+    const int seq = idx < B ? perm[idx] : -1;
+    seq_s[tid] = seq;
+    len_s[tid] = seq >= 0 ? lens[seq] : 0;
+  }
+  if (tid == 0) {
+    mbar_init(&hbar[0], 1);
+    mbar_init(&hbar[1], 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 2 * NB * LC_H; i += LC_THREADS) lc_smem[i] = 0.f;
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int n = 0; n < NB; ++n) maxlen = max(maxlen, len_s[n]);
+  for (int n = 0; n < NB; ++n) {  // zero this CTA's unit slice of the padded tail
+    if (seq_s[n] < 0) continue;
+    for (int t = len_s[n] + warp; t < T; t += LC_THREADS / 32)
+      out[(static_cast<size_t>(seq_s[n]) * T + t) * 2 * LC_H + dir * LC_H + rank * LC_UPC + lane] = 0.f;
+  }
+  cluster_sync_all();   // peers are resident and their barriers initialised before any DSMEM traffic
+
+  const bool upd = warp < NB;   // pointwise update: warp n owns sequence n, lane = unit
+  const int my_len = upd ? len_s[warp] : 0, my_seq = upd ? seq_s[warp] : -1;
+  float c_state = 0.f;
+  float gpre[4] = {0.f, 0.f, 0.f, 0.f};
+  auto load_g = [&](int s) {
+    if (upd && s < my_len) {
+      const int t = dir == 0 ? s : my_len - 1 - s;
+      const float* gp = G + (static_cast<size_t>(my_seq) * T + t) * 8 * LC_H + dir * 4 * LC_H + rank * LC_UPC + lane;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gpre[g] = __ldg(gp + g * LC_H);
+    }
+  };
+  load_g(0);
+  constexpr uint32_t kStepBytes = NB * LC_H * 4;
+  int cur = 0;
+  for (int s = 0; s < maxlen; ++s) {
+    if (tid == 0) mbar_expect_tx(&hbar[cur ^ 1], kStepBytes);   // arm the buffer this step's h will land in
+    float acc_a[NB], acc_b[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) { acc_a[n] = 0.f; acc_b[n] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < LC_KS; i += 4) {
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        const float4 hv = *reinterpret_cast<const float4*>(&h_s[cur][n][slice * LC_KS + i]);
+        acc_a[n] = fmaf(wa[i], hv.x, acc_a[n]);     acc_b[n] = fmaf(wb[i], hv.x, acc_b[n]);
+        acc_a[n] = fmaf(wa[i + 1], hv.y, acc_a[n]); acc_b[n] = fmaf(wb[i + 1], hv.y, acc_b[n]);
+        acc_a[n] = fmaf(wa[i + 2], hv.z, acc_a[n]); acc_b[n] = fmaf(wb[i + 2], hv.z, acc_b[n]);
+        acc_a[n] = fmaf(wa[i + 3], hv.w, acc_a[n]); acc_b[n] = fmaf(wb[i + 3], hv.w, acc_b[n]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      part_s[slice][n][g0 * 32 + lane] = acc_a[n];
+      part_s[slice][n][(g0 + 1) * 32 + lane] = acc_b[n];
+    }
+    __syncthreads();
+    if (upd) {
+      const int n = warp;
+      float hn;
+      if (s < my_len) {
+        float pre[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float a = 0.f;
+#pragma unroll
+          for (int q = 0; q < LC_SL; ++q) a += part_s[q][n][g * 32 + lane];
+          pre[g] = gpre[g] + a;
+        }
+        const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gt = tanhf(pre[2]), og = sigmoidf_(pre[3]);
+        c_state = fg * c_state + ig * gt;
+        hn = og * tanhf(c_state);
+      } else {
+        hn = h_s[cur][n][rank * LC_UPC + lane];
+      }
+      const uint32_t dst = smem_u32(&h_s[cur ^ 1][n][rank * LC_UPC + lane]);
+      const uint32_t bar = smem_u32(&hbar[cur ^ 1]);
+#pragma unroll
+      for (int r = 0; r < LC_CS; ++r) st_async_f32(mapa_u32(dst, r), hn, mapa_u32(bar, r));
+      if (s < my_len) {
+        const int t = dir == 0 ? s : my_len - 1 - s;
+        out[(static_cast<size_t>(my_seq) * T + t) * 2 * LC_H + dir * LC_H + rank * LC_UPC + lane] = hn;
+      }
+      load_g(s + 1);
+    }
+    // wait until every CTA's slice of h_{s} has landed here
+    {
+      const uint32_t parity = (s >> 1) & 1;
+      uint32_t spins = 0;
+      while (!mbar_try_wait_cluster(&hbar[cur ^ 1], parity)) {
+        if (++spins > (1u << 24)) __trap();
+      }
+    }
+    cur ^= 1;
+  }
+  cluster_sync_all();   // nobody exits while a peer could still be sending to it
 }
 
 }  // namespace stz

@@ -18,6 +18,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "predictor.cuh"
 #include "stz_layout.h"
 
@@ -38,10 +39,11 @@ struct Workspace {
   float *pool_text, *pool_prompt, *pt, *pp, *ctx_pre, *tfeat, *t1, *temb, *coef;
   // denoiser
   float *mod, *x, *xmid, *h, *noise;
-  bf16 *xin, *u, *qkv, *att, *ffh;
+  bf16 *xin, *u, *u3, *qkv, *att, *ffh;
   // predictor
-  float *sq, *sk, *sv, *sa, *stok, *G, *xa, *xb, *gb;
-  int* lens;
+  float *sq, *sk, *sv, *sa, *stok, *G, *xa, *xb, *gb, *skv;
+  bf16 *pa, *ps3, *pq, *pstyle3, *psa3;
+  int *lens, *perm;
   // host-call staging (stz_synthesize_host)
   float *st_text, *st_prompt, *st_noise, *st_style;
   uint8_t *st_tmask, *st_pmask, *hs_tmask, *hs_pmask;
@@ -59,12 +61,22 @@ struct stz_handle {
   bf16* wbf = nullptr;    // the same blob rounded to bf16 (same offsets): tensor-core operands
   float *ctx_text_b = nullptr, *ctx_prompt_b = nullptr;  // bias + type embedding
   bf16* kv_null = nullptr;                               // [1, L*2d] K/V of the null-prompt token
-  float* whhT = nullptr;                                 // [n_lstm][2][h][4h]
+  bf16 *w_in3 = nullptr, *w_out3 = nullptr;              // split-bf16 [hi | hi | lo] input / output projection weights
+  float* whhT = nullptr;                                 // [n_lstm][2][h][4h]  (k-major: generic kernel)
+  float* whh = nullptr;                                  // [n_lstm][2][4h][h]  (row-major: cluster kernel)
   float* lstm_b = nullptr;                               // [n_lstm][2][4h] = b_ih + b_hh
+  // predictor GEMMs on tcgen05 at fp32-grade precision: split-bf16 weights [hi | hi | lo] (K tripled)
+  bool pred_tc = false;
+  bf16 *wq3 = nullptr, *wkv3 = nullptr, *wo3 = nullptr, *wih3 = nullptr, *wada3 = nullptr;
+  float* b_kv = nullptr;
   Workspace ws;
   cudaStream_t stream = nullptr;      // internal stream (create-time work, host entry point, capture)
+  // calls share one workspace: a call enqueued on a different stream than the previous one first waits for it
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t last_ev = nullptr;
+  bool has_last = false;
   std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
-  int use_graph = 1, gemm_impl = 0;
+  int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0;
   int64_t launches = 0;
   int cur_launches = 0;  // launches issued since the counter was last sampled (capture bookkeeping)
   int tap_eval = -1, tap_layer = -1, tap_stage = -1;
@@ -127,6 +139,17 @@ static int fail(stz_handle* H, int code, const char* fmt, ...) {
     if (rc_ != 0) return rc_; \
   } while (0)
 
+static int order_after_previous_call(stz_handle* H, cudaStream_t st) {
+  if (H->has_last && st != H->last_stream) CK(H, cudaStreamWaitEvent(st, H->last_ev, 0));
+  return 0;
+}
+static int mark_call_end(stz_handle* H, cudaStream_t st) {
+  CK(H, cudaEventRecord(H->last_ev, st));
+  H->last_stream = st;
+  H->has_last = true;
+  return 0;
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int ew_grid(size_t n, int per_block = 256) {
   size_t g = (n + per_block - 1) / per_block;
@@ -162,6 +185,20 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t c
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Output map of the staged epilogues: row-major [rows, cols], row stride ld (elements), box = 32 rows x 128 bytes
+// (32 fp32 or 64 bf16 columns), 128B swizzle.  Rows >= `rows` are clipped by the TMA unit.
+static int make_tmap_out(CUtensorMap* m, void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld) {
+  const uint64_t es = is_bf16 ? 2 : 4;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 // ------------------------------------------------------------------------------------------
 // GEMM launchers
 // ------------------------------------------------------------------------------------------
@@ -183,6 +220,60 @@ static int launch_gemm_tc(stz_handle* H, cudaStream_t st, const bf16* A, int lda
   return 0;
 }
 
+// ---- v2: persistent, TMEM double-buffered, TMA-store epilogue (gemm2.cuh) -------------------------
+static int g_num_sms = 148;
+
+static int pick_bn(int M, int N) {
+  int best = 0;
+  long best_cost = 0;
+  for (int bn : {256, 192, 128}) {
+    if (N % bn) continue;
+    const long tiles = (long)(N / bn) * cdiv(M, GEMM_BM);
+    const long cost = (long)cdiv(tiles, g_num_sms) * bn;
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+template <int BN, int EPI>
+static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, const GemmParams& p) {
+  CUtensorMap ta, tb, tc;
+  memset(&tc, 0, sizeof tc);
+  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
+      make_tmap(&tb, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, BN))
+    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", p.M, p.N, p.K);
+  if (g2_staged<EPI>() && make_tmap_out(&tc, p.out, g2_out_bf16<EPI>(), (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo))
+    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (output) failed (M=%d N=%d ldo=%d)", p.M, p.N, p.ldo);
+  const int tiles = (p.N / BN) * cdiv(p.M, GEMM_BM);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * p.N * p.K);
+  gemm2_kernel<BN, EPI><<<grid, G2_THREADS, g2_smem_bytes<BN>(), st>>>(ta, tb, tc, p);
+  if (H) { KCHECK(H); } else if (cudaGetLastError() != cudaSuccess) return STZ_E_CUDA;
+  return 0;
+}
+
+template <int EPI>
+static int launch_gemm2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, const GemmParams& p) {
+  switch (pick_bn(p.M, p.N)) {
+    case 256: return launch_gemm2_bn<256, EPI>(H, st, A, lda, a_rows, W, p);
+    case 192: return launch_gemm2_bn<192, EPI>(H, st, A, lda, a_rows, W, p);
+    case 128: return launch_gemm2_bn<128, EPI>(H, st, A, lda, a_rows, W, p);
+  }
+  return fail(H, STZ_E_SHAPE, "gemm N=%d is not a multiple of 128", p.N);
+}
+
+template <int BN, int EPI>
+static cudaError_t set_gemm2_attr() {
+  return cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
+}
+template <int EPI>
+static cudaError_t set_gemm2_attrs() {
+  cudaError_t e;
+  if ((e = set_gemm2_attr<256, EPI>()) != cudaSuccess) return e;
+  if ((e = set_gemm2_attr<192, EPI>()) != cudaSuccess) return e;
+  return set_gemm2_attr<128, EPI>();
+}
+
 template <int EPI>
 static cudaError_t set_gemm_attr() {
   return cudaFuncSetAttribute(gemm_tc_kernel<GEMM_BN, EPI, GEMM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -197,6 +288,16 @@ static cudaError_t init_kernel_attrs() {
   if ((e = set_gemm_attr<EPI_GELU_BF16>()) != cudaSuccess) return e;
   if ((e = set_gemm_attr<EPI_GATE_RES>()) != cudaSuccess) return e;
   if ((e = set_gemm_attr<EPI_SAMPLER>()) != cudaSuccess) return e;
+  if ((e = set_gemm2_attrs<EPI_F32>()) != cudaSuccess) return e;
+  if ((e = set_gemm2_attrs<EPI_F32_POS>()) != cudaSuccess) return e;
+  if ((e = set_gemm2_attrs<EPI_BF16>()) != cudaSuccess) return e;
+  if ((e = set_gemm2_attrs<EPI_GELU_BF16>()) != cudaSuccess) return e;
+  if ((e = set_gemm2_attrs<EPI_GATE_RES>()) != cudaSuccess) return e;
+  if ((e = set_gemm2_attrs<EPI_SAMPLER>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    g_num_sms = sms;
   return cudaSuccess;
 }
 
@@ -213,7 +314,9 @@ static int gemm(stz_handle* H, cudaStream_t st, int impl, const bf16* A, int lda
                 const GemmParams& p) {
   if (p.N % GEMM_BN != 0 || p.K % GEMM_BK != 0 || p.M <= 0)
     return fail(H, STZ_E_SHAPE, "gemm shape M=%d N=%d K=%d unsupported (N %% 128, K %% 64)", p.M, p.N, p.K);
-  return impl == 0 ? launch_gemm_tc<EPI>(H, st, A, lda, a_rows, W, p) : launch_gemm_simt<EPI>(H, st, A, lda, W, p);
+  if (impl == 0) return launch_gemm2<EPI>(H, st, A, lda, a_rows, W, p);
+  if (impl == 2) return launch_gemm_tc<EPI>(H, st, A, lda, a_rows, W, p);
+  return launch_gemm_simt<EPI>(H, st, A, lda, W, p);
 }
 
 static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, int ld1, int K1, const float* X2, int ld2,
@@ -229,14 +332,14 @@ static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, 
 }
 
 static int ln_mod(stz_handle* H, cudaStream_t st, const float* h, int rows, int D, const float* mod, int n_mod,
-                  int shift_off, int scale_off, int rows_per_utt, bf16* out) {
+                  int shift_off, int scale_off, int rows_per_utt, bf16* out, int split3 = 0) {
   dim3 grid(cdiv(rows, 8));
   ProfScope ps(H, st, PC_LN, (double)rows * D * 6.0);  // fp32 in + bf16 out
   switch (D / 128) {
-    case 1: ln_mod_kernel<1><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
-    case 2: ln_mod_kernel<2><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
-    case 4: ln_mod_kernel<4><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
-    case 8: ln_mod_kernel<8><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out); break;
+    case 1: ln_mod_kernel<1><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 2: ln_mod_kernel<2><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 4: ln_mod_kernel<4><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 8: ln_mod_kernel<8><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
     default: return fail(H, STZ_E_SHAPE, "d_model %d unsupported by ln_mod", D);
   }
   KCHECK(H);
@@ -292,11 +395,14 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   WANT(coef, (size_t)E * 8, float);
   WANT(mod, NS * n_mod, float); WANT(x, BK * Ds, float); WANT(xmid, BK * Ds, float); WANT(h, R * d, float);
   WANT(noise, (size_t)noise_slices * BK * Ds, float);
-  WANT(xin, R * Ds, bf16); WANT(u, R * d, bf16); WANT(qkv, R * 3 * d, bf16); WANT(att, R * d, bf16);
+  WANT(xin, R * 3 * Ds, bf16); WANT(u, R * d, bf16); WANT(u3, R * 3 * d, bf16); WANT(qkv, R * 3 * d, bf16); WANT(att, R * d, bf16);
   WANT(ffh, R * c.d_ff, bf16);
   WANT(sq, BT * ds, float); WANT(sk, BK * ds, float); WANT(sv, BK * ds, float); WANT(sa, BT * ds, float);
   WANT(stok, BT * ds, float); WANT(G, BT * h8, float); WANT(xa, BT * dh, float); WANT(xb, BT * dh, float);
-  WANT(gb, BT * 2 * dh, float); WANT(lens, B, int);
+  WANT(gb, BT * 2 * dh, float); WANT(lens, B, int); WANT(perm, B, int);
+  WANT(skv, BK * 2 * ds, float);
+  WANT(pa, (BT + 128) * 3 * (dh + ds), bf16); WANT(ps3, (BT + 128) * 3 * ds, bf16); WANT(pq, (BT + 128) * 3 * c.d_text, bf16);
+  WANT(pstyle3, (BK + 128) * 3 * Ds, bf16); WANT(psa3, (BT + 128) * 3 * ds, bf16);
   WANT(st_text, BT * c.d_text, float); WANT(st_prompt, BP * c.d_prompt, float);
   WANT(st_noise, (size_t)(noise_slices > 1 ? noise_slices : 1) * BK * Ds, float); WANT(st_style, BK * Ds, float);
   WANT(st_tmask, BT, uint8_t); WANT(st_pmask, BP, uint8_t); WANT(st_dur, BT, int32_t);
@@ -416,7 +522,9 @@ extern "C" void stz_destroy(stz_handle* H) {
   cudaDeviceSynchronize();
   for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
   cudaFree(H->ws.base); cudaFree(H->w32); cudaFree(H->wbf); cudaFree(H->ctx_text_b); cudaFree(H->ctx_prompt_b);
-  cudaFree(H->kv_null); cudaFree(H->whhT); cudaFree(H->lstm_b);
+  cudaFree(H->wq3); cudaFree(H->wkv3); cudaFree(H->wo3); cudaFree(H->wih3); cudaFree(H->wada3); cudaFree(H->b_kv);
+  cudaFree(H->kv_null); cudaFree(H->w_in3); cudaFree(H->w_out3); cudaFree(H->whhT); cudaFree(H->whh); cudaFree(H->lstm_b);
+  if (H->last_ev) cudaEventDestroy(H->last_ev);
   if (H->stream) cudaStreamDestroy(H->stream);
   delete H;
 }
@@ -434,6 +542,7 @@ static int create_impl(stz_handle* H, const float* weights_host) {
   const stz_config& c = H->cfg;
   const int d = c.d_model, L = c.n_layers, h = c.d_hid / 2;
   CK(H, cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
+  CK(H, cudaEventCreateWithFlags(&H->last_ev, cudaEventDisableTiming));
   CK(H, init_kernel_attrs());
   cudaStream_t st = H->stream;
   CK(H, cudaMalloc(&H->w32, H->n_floats * sizeof(float)));
@@ -441,6 +550,11 @@ static int create_impl(stz_handle* H, const float* weights_host) {
   CK(H, cudaMemcpyAsync(H->w32, weights_host, H->n_floats * sizeof(float), cudaMemcpyHostToDevice, st));
   f32_to_bf16_kernel<<<ew_grid(H->n_floats), 256, 0, st>>>(H->w32, H->wbf, H->n_floats);
   KCHECK(H);
+  // fp32-grade input / output projections: split-bf16 weights (see split3_weights_kernel)
+  CK(H, cudaMalloc(&H->w_in3, (size_t)d * 3 * c.d_style * sizeof(bf16)));
+  CK(H, cudaMalloc(&H->w_out3, (size_t)c.d_style * 3 * d * sizeof(bf16)));
+  split3_weights_kernel<<<ew_grid((size_t)d * c.d_style), 256, 0, st>>>(W32(H, "in.w"), H->w_in3, d, c.d_style); KCHECK(H);
+  split3_weights_kernel<<<ew_grid((size_t)d * c.d_style), 256, 0, st>>>(W32(H, "out.w"), H->w_out3, c.d_style, d); KCHECK(H);
   // ctx biases with the token-type embedding folded in
   CK(H, cudaMalloc(&H->ctx_text_b, d * sizeof(float)));
   CK(H, cudaMalloc(&H->ctx_prompt_b, d * sizeof(float)));
@@ -463,9 +577,12 @@ static int create_impl(stz_handle* H, const float* weights_host) {
   // predictor: recurrent weights k-major, biases summed
   CK(H, cudaMalloc(&H->whhT, (size_t)c.n_lstm * 2 * h * 4 * h * sizeof(float)));
   CK(H, cudaMalloc(&H->lstm_b, (size_t)c.n_lstm * 2 * 4 * h * sizeof(float)));
+  CK(H, cudaMalloc(&H->whh, (size_t)c.n_lstm * 2 * 4 * h * h * sizeof(float)));
   for (int l = 0; l < c.n_lstm; ++l)
     for (int dr = 0; dr < 2; ++dr) {
       const std::string p = "lstm" + std::to_string(l) + (dr ? ".r." : ".f.");
+      CK(H, cudaMemcpyAsync(H->whh + ((size_t)l * 2 + dr) * 4 * h * h, W32(H, p + "w_hh"), (size_t)4 * h * h * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
       transpose_whh_kernel<<<ew_grid((size_t)4 * h * h), 256, 0, st>>>(W32(H, p + "w_hh"),
                                                                         H->whhT + ((size_t)l * 2 + dr) * h * 4 * h, 4 * h, h);
       KCHECK(H);
@@ -473,6 +590,36 @@ static int create_impl(stz_handle* H, const float* weights_host) {
                                                      H->lstm_b + ((size_t)l * 2 + dr) * 4 * h, 4 * h, 4 * h);
       KCHECK(H);
     }
+  {  // split-bf16 predictor weights
+    const size_t ds = c.d_sty_tok, dh = c.d_hid, Ds = c.d_style, kin = dh + ds;
+    H->pred_tc = ds % 128 == 0 && dh % 128 == 0 && kin % 64 == 0 && c.d_text % 64 == 0 && Ds % 64 == 0;
+    if (H->pred_tc) {
+      auto split = [&](const float* src, bf16* dst, size_t N, size_t K) -> int {
+        split3_weights_kernel<<<ew_grid(N * K), 256, 0, st>>>(src, dst, N, K);
+        KCHECK(H);
+        return 0;
+      };
+      CK(H, cudaMalloc(&H->wq3, ds * 3 * c.d_text * sizeof(bf16)));
+      CK(H, cudaMalloc(&H->wkv3, 2 * ds * 3 * Ds * sizeof(bf16)));
+      CK(H, cudaMalloc(&H->wo3, ds * 3 * ds * sizeof(bf16)));
+      CK(H, cudaMalloc(&H->wih3, (size_t)c.n_lstm * 8 * h * 3 * kin * sizeof(bf16)));
+      CK(H, cudaMalloc(&H->wada3, (size_t)(c.n_lstm > 1 ? c.n_lstm - 1 : 1) * 2 * dh * 3 * ds * sizeof(bf16)));
+      CK(H, cudaMalloc(&H->b_kv, 2 * ds * sizeof(float)));
+      RET(split(W32(H, "sp.q.w"), H->wq3, ds, c.d_text));
+      RET(split(W32(H, "sp.k.w"), H->wkv3, ds, Ds));
+      RET(split(W32(H, "sp.v.w"), H->wkv3 + ds * 3 * Ds, ds, Ds));
+      RET(split(W32(H, "sp.o.w"), H->wo3, ds, ds));
+      CK(H, cudaMemcpyAsync(H->b_kv, W32(H, "sp.k.b"), ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      CK(H, cudaMemcpyAsync(H->b_kv + ds, W32(H, "sp.v.b"), ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      for (int l = 0; l < c.n_lstm; ++l) {
+        for (int dr = 0; dr < 2; ++dr)
+          RET(split(W32(H, "lstm" + std::to_string(l) + (dr ? ".r.w_ih" : ".f.w_ih")),
+                    H->wih3 + ((size_t)l * 8 * h + (size_t)dr * 4 * h) * 3 * kin, 4 * h, kin));
+        if (l < c.n_lstm - 1)
+          RET(split(W32(H, "adaln" + std::to_string(l) + ".w"), H->wada3 + (size_t)l * 2 * dh * 3 * ds, 2 * dh, ds));
+      }
+    }
+  }
   CK(H, cudaStreamSynchronize(st));
   cudaFree(tmp); cudaFree(nullc);
   return 0;
@@ -524,7 +671,11 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     }
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) { /* single implementation this round */ }
-  else return fail(H, STZ_E_ARG, "unknown option %s", key);
+  else if (!strcmp(key, "profile")) {
+    H->profile = value;
+    for (auto& r : H->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    H->prof.clear();
+  } else return fail(H, STZ_E_ARG, "unknown option %s", key);
   return 0;
 }
 
@@ -588,8 +739,8 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
   }
   {  // h = x_in · Win^T + b + pos
     GemmParams p = base;
-    p.M = R; p.N = d; p.K = Ds; p.bias = W32(H, "in.b"); p.out = w.h; p.ldo = d; p.pos = W32(H, "pos");
-    RET(gemm<EPI_F32_POS>(H, st, impl, w.xin, Ds, R, WBF(H, "in.w"), p));
+    p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = w.h; p.ldo = d; p.pos = W32(H, "pos");
+    RET(gemm<EPI_F32_POS>(H, st, impl, w.xin, 3 * Ds, R, H->w_in3, p));
   }
   for (int l = 0; l < L; ++l) {
     const std::string pf = "l" + std::to_string(l) + ".";
@@ -649,15 +800,15 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
     }
     RET(tap(H, st, e, l, 2, R));
   }
-  RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, 9 * L * d, 9 * L * d + d, 2 * K, w.u));
+  RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, 9 * L * d, 9 * L * d + d, 2 * K, w.u3, 1));
   {  // F = u · Wout^T + b, then CFG combine + sampler update + next input in the epilogue
     GemmParams p = base;
-    p.M = R; p.N = Ds; p.K = d; p.bias = W32(H, "out.b"); p.ldo = Ds;
+    p.M = R; p.N = Ds; p.K = 3 * d; p.bias = W32(H, "out.b"); p.ldo = Ds;
     p.x = w.x; p.xmid = w.xmid; p.xin = w.xin; p.coef = w.coef + (size_t)e * 8;
     // teacher: eval 2i+1 adds sigma_up * noise slice i+1 (slice 0 seeded the state)
     p.noise = w.noise + (size_t)((e >> 1) + 1) * B * K * Ds;
     p.tap = (H->tap_buf && !H->capturing && H->tap_eval == e && H->tap_layer == L) ? H->tap_buf : nullptr;
-    RET(gemm<EPI_SAMPLER>(H, st, impl, w.u, d, R, WBF(H, "out.w"), p));
+    RET(gemm<EPI_SAMPLER>(H, st, impl, w.u3, 3 * d, R, H->w_out3, p));
   }
   return 0;
 }
@@ -672,6 +823,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   const int E = kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
   const int slices = kind == STZ_SAMPLER_TEACHER ? steps + 1 : 1;
   RET(ensure_workspace(H, B, T, P, E, slices));
+  RET(order_after_previous_call(H, st));
   Workspace& w = H->ws;
   const int d = c.d_model, L = c.n_layers, K = c.n_style, Ds = c.d_style;
   const int NS = 2 * B, impl = H->gemm_impl;
@@ -749,7 +901,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     H->cur_launches = 0;
   }
   CK(H, cudaMemcpyAsync(out, w.x, BK * Ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return mark_call_end(H, st);
 }
 
 extern "C" int stz_sample_style(stz_handle* H, const float* text_emb_dev, const uint8_t* text_mask_dev,
@@ -771,43 +923,82 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
   if (!text || !style || !out_dur) return fail(H, STZ_E_ARG, "null tensor argument");
   if (B < 1 || T < 1) return fail(H, STZ_E_ARG, "bad sizes B=%d T=%d", B, T);
   RET(ensure_workspace(H, B, T, 1, 1, 1));
+  RET(order_after_previous_call(H, st));
   Workspace& w = H->ws;
   const int ds = c.d_sty_tok, dh = c.d_hid, h = dh / 2, K = c.n_style, Ds = c.d_style;
   const int BT = B * T, BK = B * K;
   H->cur_launches = 0;
-  lens_kernel<<<cdiv(B, 128), 128, 0, st>>>(tmask, w.lens, B, T); KCHECK(H);
+  lens_perm_kernel<<<1, 1024, 0, st>>>(tmask, w.lens, w.perm, B, T); KCHECK(H);
+  const bool tc = H->pred_tc && H->pred_gemm_impl == 0;   // split-bf16 tcgen05 GEMMs vs fp32 CUDA-core GEMMs
+  const int kin = dh + ds, impl = H->gemm_impl;
+  auto split_rows = [&](const float* src, int ld, int Kc, bf16* dst, int ldd, int segK, int off, size_t M) -> int {
+    ProfScope ps(H, st, PC_PRED_EW, (double)M * Kc * 10.0);
+    split3_rows_kernel<<<ew_grid(M * (Kc / 4)), 256, 0, st>>>(src, ld, Kc, dst, ldd, segK, off, M);
+    KCHECK(H);
+    return 0;
+  };
+  auto gemm3 = [&](const bf16* A, int K3, int rows, const bf16* W3, const float* bias, float* out, int N) -> int {
+    GemmParams p{};
+    p.M = rows; p.N = N; p.K = K3; p.bias = bias; p.out = out; p.ldo = N;
+    return gemm<EPI_F32>(H, st, impl, A, K3, rows, W3, p);
+  };
   // a-8: per-token style summary
-  RET(linear_f32(H, st, ACT_NONE, text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "sp.q.w"), W32(H, "sp.q.b"), w.sq, ds, BT, ds));
-  RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.k.w"), W32(H, "sp.k.b"), w.sk, ds, BK, ds));
-  RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.v.w"), W32(H, "sp.v.b"), w.sv, ds, BK, ds));
-  style_pool_attn_kernel<<<cdiv(BT, 8), 256, 0, st>>>(w.sq, w.sk, w.sv, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
-  RET(linear_f32(H, st, ACT_NONE, w.sa, ds, ds, nullptr, 0, 0, W32(H, "sp.o.w"), W32(H, "sp.o.b"), w.stok, ds, BT, ds));
+  if (tc) {
+    RET(split_rows(text, c.d_text, c.d_text, w.pq, 3 * c.d_text, c.d_text, 0, BT));
+    RET(split_rows(text, c.d_text, c.d_text, w.pa, 3 * kin, kin, 0, BT));          // x part of layer 0's [x | s_tok]
+    RET(split_rows(style, Ds, Ds, w.pstyle3, 3 * Ds, Ds, 0, BK));
+    RET(gemm3(w.pq, 3 * c.d_text, BT, H->wq3, W32(H, "sp.q.b"), w.sq, ds));
+    RET(gemm3(w.pstyle3, 3 * Ds, BK, H->wkv3, H->b_kv, w.skv, 2 * ds));
+    style_pool_attn_kernel<<<cdiv(BT, 8), 256, 0, st>>>(w.sq, w.skv, w.skv + ds, 2 * ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
+    RET(split_rows(w.sa, ds, ds, w.psa3, 3 * ds, ds, 0, BT));
+    RET(gemm3(w.psa3, 3 * ds, BT, H->wo3, W32(H, "sp.o.b"), w.stok, ds));
+    RET(split_rows(w.stok, ds, ds, w.pa, 3 * kin, kin, dh, BT));                    // s_tok part, shared by all layers
+    RET(split_rows(w.stok, ds, ds, w.ps3, 3 * ds, ds, 0, BT));
+  } else {
+    RET(linear_f32(H, st, ACT_NONE, text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "sp.q.w"), W32(H, "sp.q.b"), w.sq, ds, BT, ds));
+    RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.k.w"), W32(H, "sp.k.b"), w.sk, ds, BK, ds));
+    RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.v.w"), W32(H, "sp.v.b"), w.sv, ds, BK, ds));
+    style_pool_attn_kernel<<<cdiv(BT, 8), 256, 0, st>>>(w.sq, w.sk, w.sv, ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
+    RET(linear_f32(H, st, ACT_NONE, w.sa, ds, ds, nullptr, 0, 0, W32(H, "sp.o.w"), W32(H, "sp.o.b"), w.stok, ds, BT, ds));
+  }
   // a-9: (BiLSTM + AdaLN) x (n_lstm - 1) + BiLSTM
   const float* x = text;
   float* bufs[2] = {w.xa, w.xb};
   constexpr int NB = 8;
   const size_t lstm_smem = (size_t)NB * h * 5 * sizeof(float);
   for (int l = 0; l < c.n_lstm; ++l) {
-    for (int dr = 0; dr < 2; ++dr) {
-      const std::string p = "lstm" + std::to_string(l) + (dr ? ".r." : ".f.");
-      RET(linear_f32(H, st, ACT_NONE, x, dh, dh, w.stok, ds, ds, W32(H, p + "w_ih"), H->lstm_b + ((size_t)l * 2 + dr) * 4 * h,
-                     w.G + (size_t)dr * 4 * h, 8 * h, BT, 4 * h));
+    if (tc) {  // G = [x | s_tok] W_ih^T + (b_ih + b_hh), both directions in one GEMM (N = 8h)
+      RET(gemm3(w.pa, 3 * kin, BT, H->wih3 + (size_t)l * 8 * h * 3 * kin, H->lstm_b + (size_t)l * 8 * h, w.G, 8 * h));
+    } else {
+      for (int dr = 0; dr < 2; ++dr) {
+        const std::string p = "lstm" + std::to_string(l) + (dr ? ".r." : ".f.");
+        RET(linear_f32(H, st, ACT_NONE, x, dh, dh, w.stok, ds, ds, W32(H, p + "w_ih"), H->lstm_b + ((size_t)l * 2 + dr) * 4 * h,
+                       w.G + (size_t)dr * 4 * h, 8 * h, BT, 4 * h));
+      }
     }
     float* xo = bufs[l & 1];
     {
       ProfScope ps(H, st, PC_LSTM, 2.0 * BT * 2.0 * h * 4.0 * h);
-      lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
+      if (h == LC_H && H->lstm_impl == 0) {  // product path: register-resident W_hh, cluster of 8 CTAs, DSMEM exchange
+        lstm_cluster_kernel<NB><<<dim3(cdiv(B, NB) * LC_CS, 2), LC_THREADS, lstm_cluster_smem<NB>(), st>>>(
+            w.G, H->whh + (size_t)l * 2 * 4 * h * h, w.lens, w.perm, xo, B, T);
+      } else {
+        lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
+      }
       KCHECK(H);
     }
     if (l < c.n_lstm - 1) {
       const std::string p = "adaln" + std::to_string(l) + ".";
-      RET(linear_f32(H, st, ACT_NONE, w.stok, ds, ds, nullptr, 0, 0, W32(H, p + "w"), W32(H, p + "b"), w.gb, 2 * dh, BT, 2 * dh));
+      if (tc) RET(gemm3(w.ps3, 3 * ds, BT, H->wada3 + (size_t)l * 2 * dh * 3 * ds, W32(H, p + "b"), w.gb, 2 * dh));
+      else RET(linear_f32(H, st, ACT_NONE, w.stok, ds, ds, nullptr, 0, 0, W32(H, p + "w"), W32(H, p + "b"), w.gb, 2 * dh, BT, 2 * dh));
       dim3 grid(cdiv(BT, 8));
+      bf16* a3 = tc ? w.pa : nullptr;
+      ProfScope ps(H, st, PC_PRED_EW, (double)BT * dh * 16.0);
       switch (dh / 128) {
-        case 1: adaln_pred_kernel<1><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
-        case 2: adaln_pred_kernel<2><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
-        case 4: adaln_pred_kernel<4><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
-        case 8: adaln_pred_kernel<8><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT); break;
+        case 1: adaln_pred_kernel<1><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
+        case 2: adaln_pred_kernel<2><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
+        case 4: adaln_pred_kernel<4><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
+        case 8: adaln_pred_kernel<8><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
         default: return fail(H, STZ_E_SHAPE, "d_hid %d unsupported", dh);
       }
       KCHECK(H);
@@ -827,7 +1018,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
   }
   H->launches += H->cur_launches;
   H->cur_launches = 0;
-  return 0;
+  return mark_call_end(H, st);
 }
 
 extern "C" int stz_predict_duration(stz_handle* H, const float* text_emb_dev, const uint8_t* text_mask_dev,
@@ -855,6 +1046,7 @@ extern "C" int stz_synthesize_host(stz_handle* H, const float* text_emb, const u
   RET(ensure_workspace(H, B, T, P, E, slices));
   Workspace& w = H->ws;
   cudaStream_t st = H->stream;
+  RET(order_after_previous_call(H, st));
   const size_t BK = (size_t)B * c.n_style, BT = (size_t)B * T, BP = (size_t)B * P;
   CK(H, cudaMemcpyAsync(w.st_text, text_emb, BT * c.d_text * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(H, cudaMemcpyAsync(w.st_prompt, prompt_feats, BP * c.d_prompt * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -886,8 +1078,9 @@ extern "C" int stz_op_gemm_bf16(const void* A, const void* W, const float* bias,
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = C; p.ldo = N;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int rc = impl == 0 ? launch_gemm_tc<EPI_F32>(nullptr, st, (const bf16*)A, K, M, (const bf16*)W, p)
-                     : launch_gemm_simt<EPI_F32>(nullptr, st, (const bf16*)A, K, (const bf16*)W, p);
+  int rc = impl == 0   ? launch_gemm2<EPI_F32>(nullptr, st, (const bf16*)A, K, M, (const bf16*)W, p)
+           : impl == 2 ? launch_gemm_tc<EPI_F32>(nullptr, st, (const bf16*)A, K, M, (const bf16*)W, p)
+                       : launch_gemm_simt<EPI_F32>(nullptr, st, (const bf16*)A, K, (const bf16*)W, p);
   if (rc != 0 && g_create_error.empty()) g_create_error = "gemm launch failed";
   return rc;
 }
