@@ -103,7 +103,8 @@ int stz_synthesize_host(stz_handle* h, const float* text_emb, const uint8_t* tex
 int64_t stz_launch_count(const stz_handle* h);
 
 /* Knobs: "use_graph" (0/1, default 1), "gemm_impl" (0 = tcgen05 persistent v2, 1 = SIMT cross-check kernel, 2 = tcgen05 v1),
- * "lstm_impl" (0 = default), "profile" (0/1, see stz_profile_read).  Returns STZ_E_ARG for
+ * "lstm_impl" (0 = cluster kernel, 1 = generic), "pred_gemm_impl" (0 = split-bf16 tcgen05,
+ * 1 = fp32 CUDA cores), "use_pdl" (0/1 programmatic dependent launch, process-wide), "profile" (0/1, see stz_profile_read).  Returns STZ_E_ARG for
  * unknown keys. */
 int stz_set_option(stz_handle* h, const char* key, int value);
 
@@ -120,6 +121,9 @@ int stz_profile_read(stz_handle* h, int kernel_class, double* ms, double* work, 
  * self-attention / cross-attention / FFN sub-layer, layer == n_layers -> the guided F.
  * tap_dev = NULL disables. */
 int stz_debug_set_tap(stz_handle* h, int eval, int layer, int stage, float* tap_dev);
+
+/* Max co-resident 8-CTA clusters of the BiLSTM recurrence kernel on the current device (diagnostic). */
+int stz_debug_max_lstm_clusters(void);
 
 /* C[M,N] = A[M,K] · W[N,K]^T + bias, bf16 operands (device), fp32 out.  impl as "gemm_impl". */
 int stz_op_gemm_bf16(const void* A_bf16_dev, const void* W_bf16_dev, const float* bias_dev,

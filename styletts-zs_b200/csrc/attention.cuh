@@ -54,6 +54,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t sad
 }
 
 __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
+  pdl_sync();
   __shared__ __align__(16) __nv_bfloat16 Ks[ATT_KB][ATT_LDS];
   __shared__ __align__(16) __nv_bfloat16 Vs[ATT_KB][ATT_LDS];
   __shared__ uint8_t kvis[ATT_KB];  // bit0: visible to cond (even) query rows, bit1: to uncond (odd) rows

@@ -25,6 +25,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256) cast_pool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
                                                         __nv_bfloat16* __restrict__ xb, float* __restrict__ pooled,
                                                         int T, int D) {
+  pdl_sync();
   const int b = blockIdx.x;
   const int nvec = D >> 2;
   const float* xr = x + static_cast<size_t>(b) * T * D;
@@ -52,6 +53,7 @@ template <int VPL>
 __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h, int rows, const float* __restrict__ mod,
                                                      int n_mod, int shift_off, int scale_off, int rows_per_utt,
                                                      __nv_bfloat16* __restrict__ out, int split3) {
+  pdl_sync();
   constexpr int D = 128 * VPL;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h
 __global__ void __launch_bounds__(256) cvec_kernel(const float* __restrict__ temb, const float* __restrict__ pt,
                                                    const float* __restrict__ pp, const float* __restrict__ null_pp,
                                                    __nv_bfloat16* __restrict__ cvec, int E, int n_seq, int D) {
+  pdl_sync();
   const size_t total = static_cast<size_t>(E) * n_seq * D;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(256) cvec_kernel(const float* __restrict__ tem
 __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict__ noise0, float* __restrict__ x,
                                                          __nv_bfloat16* __restrict__ xin, size_t n_rows, int D,
                                                          float sigma0, float cin0) {
+  pdl_sync();
   const size_t nvec = n_rows * (D >> 2);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(256) split3_weights_kernel(const float* __rest
 // width segK: [hi | lo | hi], this source occupying columns [off, off + K) of each segment.  K % 4 == 0.
 __global__ void __launch_bounds__(256) split3_rows_kernel(const float* __restrict__ src, int ld, int K,
                                                           __nv_bfloat16* __restrict__ dst, int ldd, int segK, int off, size_t M) {
+  pdl_sync();
   const int kv = K >> 2;
   const size_t n = M * kv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;

@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
                                                          const float* __restrict__ X2, int ld2, int K2,
                                                          const float* __restrict__ W, const float* __restrict__ b,
                                                          float* __restrict__ Y, int ldy, int M, int N) {
+  pdl_sync();
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float xs[BK][BM + 4];
   __shared__ float wsm[BK][BN + 4];

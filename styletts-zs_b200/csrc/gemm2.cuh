@@ -4,7 +4,7 @@
 //   warp 0      TMA producer: 128B-swizzled K-major tiles of A (128 x 64) and W (BN x 64) into a smem ring
 //   warp 1      TMEM owner + MMA issuer: tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), 128 x BN accumulator,
 //               DOUBLE-BUFFERED in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop of i+1
-//   warps 2..5  epilogue: tcgen05.ld (thread = row) -> bias / GELU / gate -> 128B-swizzled smem staging ->
+//   warps 2..9  epilogue (two per TMEM lane quadrant, alternating column chunks): tcgen05.ld (thread = row) -> bias / GELU / gate -> 128B-swizzled smem staging ->
 //               TMA store (cp.async.bulk.tensor) or, for the gated residual update h += gate * (acc + b),
 //               TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32): h is never read by an SM.
 // Barriers: full/empty per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator (MMA <-> epilogue).
@@ -16,8 +16,8 @@
 
 namespace stz {
 
-constexpr int G2_THREADS = 192;
-constexpr int G2_STAGE_BYTES_EPI = 8 * 4096;  // 4 epilogue warps x 2 staging buffers x (32 rows x 128 B)
+constexpr int G2_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int G2_STAGE_BYTES_EPI = 8 * 4096;  // 8 epilogue warps x one staging tile (32 rows x 128 B)
 
 template <int BN>
 constexpr int g2_stages() { return BN == 256 ? 4 : (BN == 192 ? 4 : 6); }
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 8);
     }
     fence_barrier_init();
   }
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -151,95 +152,117 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    const uint32_t stage_buf = epi_base + (warp - 2) * 8192;
+    // 8 epilogue warps: warp w reads TMEM lane quadrant (w & 3) and every second column chunk, starting at `half`.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t stage_buf = epi_base + (warp - 2) * 4096;   // one 32-row x 128-byte staging tile per warp
     uint32_t acc = 0, acc_phase = 0;
-    int buf = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
       const int m0 = tile_m * GEMM_BM + q * 32;
       const int m = m0 + lane;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if constexpr (g2_staged<EPI>()) {
-        constexpr int CW = g2_out_bf16<EPI>() ? 64 : 32;  // columns per staged chunk: 128 B per row
+        // a staged 128-byte row holds 32 fp32 (one 32-column sub-chunk) or 64 bf16 (two sub-chunks)
+        constexpr int SUB = g2_out_bf16<EPI>() ? 2 : 1;
+        constexpr int NCH = BN / (32 * SUB);
         const float* gate = nullptr;
         if constexpr (EPI == EPI_GATE_RES) {
           const int mm = m < p.M ? m : p.M - 1;
           gate = p.mod + static_cast<size_t>((mm / p.rows_per_utt) * 2 + (mm & 1)) * p.n_mod + p.gate_off;
         }
-#pragma unroll 1
-        for (int c = 0; c < BN / CW; ++c) {
-          const int n0 = tile_n * BN + c * CW;
-          float v[CW];
-          {
-            uint32_t r[32];
-            tmem_ld32(t_addr + c * CW, r);
-            tmem_ld_wait();
+        // bias / gate of the NEXT sub-chunk are fetched while the current one is processed (and, for the first,
+        // while the accumulator is still being produced): no dependent global latency inside the loop
+        float4 bq[8], gq[EPI == EPI_GATE_RES ? 8 : 1];
+        auto prefetch = [&](int col) {
+          const int n0 = tile_n * BN + col;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if constexpr (CW == 64) {
-              tmem_ld32(t_addr + c * CW + 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r[j]);
-            }
-          }
-          if (c == BN / CW - 1) {  // accumulator fully read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if constexpr (EPI == EPI_GELU_BF16) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = gelu_tanh_fast(v[j]);
-          }
+          for (int j = 0; j < 8; ++j)
+            bq[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (EPI == EPI_GATE_RES) {
 #pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(gate + n0 + j));
-              v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-            }
+            for (int j = 0; j < 8; ++j) gq[j] = __ldg(reinterpret_cast<const float4*>(gate + n0) + j);
           }
-          // staging buffer `buf` must have been drained by the TMA store issued two chunks ago
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-          const uint32_t sb = stage_buf + buf * 4096 + lane * 128;
-          if constexpr (g2_out_bf16<EPI>()) {
+        };
+        if (half < NCH) prefetch(half * SUB * 32);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half; c < NCH; c += 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              st_shared_v4(sb + ((j ^ (lane & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          } else {
+          for (int sub = 0; sub < SUB; ++sub) {
+            const int col = (c * SUB + sub) * 32;
+            float v[32];
+            {
+              uint32_t r[32];
+              tmem_ld32(t_addr + col, r);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              st_shared_v4(sb + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            }
+            if (c + 2 >= NCH && sub == SUB - 1) {  // this warp's last read of the accumulator: hand it back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += bq[j].x; v[4 * j + 1] += bq[j].y; v[4 * j + 2] += bq[j].z; v[4 * j + 3] += bq[j].w;
+            }
+            if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+            }
+            if constexpr (EPI == EPI_GATE_RES) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] *= gq[j].x; v[4 * j + 1] *= gq[j].y; v[4 * j + 2] *= gq[j].z; v[4 * j + 3] *= gq[j].w;
+              }
+            }
+            if (sub + 1 < SUB) prefetch(col + 32);
+            else if (c + 2 < NCH) prefetch((c + 2) * SUB * 32);
+            if (sub == 0) {  // the staging tile must have been drained by this warp's previous TMA store
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+            }
+            const uint32_t sb = stage_buf + lane * 128;
+            if constexpr (g2_out_bf16<EPI>()) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                st_shared_v4(sb + (((sub * 4 + j) ^ (lane & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
+                             pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                             pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                st_shared_v4(sb + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                             __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            }
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && m0 < p.M) {
-            if constexpr (EPI == EPI_GATE_RES) tma_reduce_add_2d(&tmC, stage_buf + buf * 4096, n0, m0);
-            else tma_store_2d(&tmC, stage_buf + buf * 4096, n0, m0);
+          if (lane == 0) {
+            const int n0 = tile_n * BN + c * SUB * 32;
+            if (m0 < p.M) {
+              if constexpr (EPI == EPI_GATE_RES) tma_reduce_add_2d(&tmC, stage_buf, n0, m0);
+              else tma_store_2d(&tmC, stage_buf, n0, m0);
+            }
+            bulk_commit();
           }
-          if (lane == 0) bulk_commit();
-          buf ^= 1;
+        }
+        if (half >= NCH) {  // (never with NCH >= 2; keeps the barrier count right for any tile shape)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
       } else {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        constexpr int NCH = BN / 32;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < NCH; c += 2) {
           uint32_t r[32];
           tmem_ld32(t_addr + c * 32, r);
           tmem_ld_wait();
-          if (c == BN / 32 - 1) {
+          if (c + 2 >= NCH) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);

@@ -23,6 +23,7 @@ __global__ void lens_kernel(const uint8_t* __restrict__ mask, int* __restrict__ 
 __global__ void __launch_bounds__(256) style_pool_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                               const float* __restrict__ v, int ldkv, float* __restrict__ out,
                                                               int n_tok, int T, int K, int ds, float scale) {
+  pdl_sync();
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (tok >= n_tok) return;
@@ -130,6 +131,7 @@ template <int VPL>
 __global__ void __launch_bounds__(256) adaln_pred_kernel(float* __restrict__ x, const float* __restrict__ gb,
                                                          const uint8_t* __restrict__ mask, int rows,
                                                          __nv_bfloat16* __restrict__ a3, int ldd, int segK) {
+  pdl_sync();
   constexpr int D = 128 * VPL;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(256) dur_head_kernel(const float* __restrict__
                                                        const float* __restrict__ bd, const uint8_t* __restrict__ mask,
                                                        int32_t* __restrict__ dur, float* __restrict__ presum, int rows,
                                                        int max_dur) {
+  pdl_sync();
   constexpr int D = 128 * VPL;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -245,6 +248,7 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_
 // lens[b] (prefix-mask popcount) and perm = sequence indices sorted by length, longest first (stable).
 __global__ void __launch_bounds__(1024) lens_perm_kernel(const uint8_t* __restrict__ mask, int* __restrict__ lens,
                                                          int* __restrict__ perm, int B, int T) {
+  pdl_sync();
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     int n = T;
     if (mask != nullptr) {
@@ -277,11 +281,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
   return remote;
 }
+// CTA-scope wait: st.async data is written through the async proxy and published by the barrier's complete_tx,
+// exactly like a TMA load, so no cluster-scope acquire (which would invalidate L1 every step) is needed.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
@@ -292,10 +298,14 @@ constexpr int lstm_cluster_smem() { return (2 * NB * LC_H + LC_SL * NB * LC_COLS
 
 // Thread layout of the matrix-vector phase: warp w -> k-slice (w >> 1) of 32, gate pair 2*(w & 1), lane = unit;
 // each thread keeps 2 columns x 32 k of W_hh in registers, so one broadcast LDS.128 of h feeds 8 FMAs.
-template <int NB>
+// A cluster advances NB = NBI * PASSES sequences: PASSES sweeps of NBI sequences over the same weight registers
+// (NB is chosen on the host so that all clusters of a launch are co-resident: one wave).
+template <int NBI, int PASSES>
 __global__ void __cluster_dims__(LC_CS, 1, 1) __launch_bounds__(LC_THREADS, 1)
 lstm_cluster_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const int* __restrict__ lens,
                     const int* __restrict__ perm, float* __restrict__ out, int B, int T) {
+  constexpr int NB = NBI * PASSES;
+  static_assert(NB <= LC_THREADS / 32, "one pointwise-update warp per sequence");
   extern __shared__ __align__(16) float lc_smem[];
   float (*h_s)[NB][LC_H] = reinterpret_cast<float (*)[NB][LC_H]>(lc_smem);                               // [2][NB][H]
   float (*part_s)[NB][LC_COLS] = reinterpret_cast<float (*)[NB][LC_COLS]>(lc_smem + 2 * NB * LC_H);      // [SL][NB][COLS]
@@ -318,6 +328,7 @@ lstm_cluster_kernel(const float* __restrict__ G, const float* __restrict__ Whh, 
       wb[4 * i] = b.x; wb[4 * i + 1] = b.y; wb[4 * i + 2] = b.z; wb[4 * i + 3] = b.w;
     }
   }
+  pdl_sync();   // W_hh (constant) was loaded above, under the previous kernel's tail
   if (tid < NB) {
     const int idx = group * NB + tid;
     const int seq = idx < B ? perm[idx] : -1;
@@ -358,24 +369,27 @@ lstm_cluster_kernel(const float* __restrict__ G, const float* __restrict__ Whh, 
   int cur = 0;
   for (int s = 0; s < maxlen; ++s) {
     if (tid == 0) mbar_expect_tx(&hbar[cur ^ 1], kStepBytes);   // arm the buffer this step's h will land in
-    float acc_a[NB], acc_b[NB];
 #pragma unroll
-    for (int n = 0; n < NB; ++n) { acc_a[n] = 0.f; acc_b[n] = 0.f; }
+    for (int pass = 0; pass < PASSES; ++pass) {
+      float acc_a[NBI], acc_b[NBI];
 #pragma unroll
-    for (int i = 0; i < LC_KS; i += 4) {
+      for (int n = 0; n < NBI; ++n) { acc_a[n] = 0.f; acc_b[n] = 0.f; }
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        const float4 hv = *reinterpret_cast<const float4*>(&h_s[cur][n][slice * LC_KS + i]);
-        acc_a[n] = fmaf(wa[i], hv.x, acc_a[n]);     acc_b[n] = fmaf(wb[i], hv.x, acc_b[n]);
-        acc_a[n] = fmaf(wa[i + 1], hv.y, acc_a[n]); acc_b[n] = fmaf(wb[i + 1], hv.y, acc_b[n]);
-        acc_a[n] = fmaf(wa[i + 2], hv.z, acc_a[n]); acc_b[n] = fmaf(wb[i + 2], hv.z, acc_b[n]);
-        acc_a[n] = fmaf(wa[i + 3], hv.w, acc_a[n]); acc_b[n] = fmaf(wb[i + 3], hv.w, acc_b[n]);
+      for (int i = 0; i < LC_KS; i += 4) {
+#pragma unroll
+        for (int n = 0; n < NBI; ++n) {
+          const float4 hv = *reinterpret_cast<const float4*>(&h_s[cur][pass * NBI + n][slice * LC_KS + i]);
+          acc_a[n] = fmaf(wa[i], hv.x, acc_a[n]);     acc_b[n] = fmaf(wb[i], hv.x, acc_b[n]);
+          acc_a[n] = fmaf(wa[i + 1], hv.y, acc_a[n]); acc_b[n] = fmaf(wb[i + 1], hv.y, acc_b[n]);
+          acc_a[n] = fmaf(wa[i + 2], hv.z, acc_a[n]); acc_b[n] = fmaf(wb[i + 2], hv.z, acc_b[n]);
+          acc_a[n] = fmaf(wa[i + 3], hv.w, acc_a[n]); acc_b[n] = fmaf(wb[i + 3], hv.w, acc_b[n]);
+        }
       }
-    }
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-      part_s[slice][n][g0 * 32 + lane] = acc_a[n];
-      part_s[slice][n][(g0 + 1) * 32 + lane] = acc_b[n];
+      for (int n = 0; n < NBI; ++n) {
+        part_s[slice][pass * NBI + n][g0 * 32 + lane] = acc_a[n];
+        part_s[slice][pass * NBI + n][(g0 + 1) * 32 + lane] = acc_b[n];
+      }
     }
     __syncthreads();
     if (upd) {
@@ -404,7 +418,6 @@ lstm_cluster_kernel(const float* __restrict__ G, const float* __restrict__ Whh, 
         const int t = dir == 0 ? s : my_len - 1 - s;
         out[(static_cast<size_t>(my_seq) * T + t) * 2 * LC_H + dir * LC_H + rank * LC_UPC + lane] = hn;
       }
-      load_g(s + 1);
     }
     // wait until every CTA's slice of h_{s} has landed here
     {
@@ -415,6 +428,7 @@ lstm_cluster_kernel(const float* __restrict__ G, const float* __restrict__ Whh, 
       }
     }
     cur ^= 1;
+    load_g(s + 1);   // consumed after the next matrix-vector phase: the L2 latency hides under it
   }
   cluster_sync_all();   // nobody exits while a peer could still be sending to it
 }

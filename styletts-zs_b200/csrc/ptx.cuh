@@ -136,6 +136,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// pdl_launch: lets the next kernel in the stream be scheduled early.  pdl_wait: blocks until the previous kernel
+// has completed and its writes are visible.  Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_launch(); pdl_wait(); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -66,6 +66,7 @@ struct stz_handle {
   float* whh = nullptr;                                  // [n_lstm][2][4h][h]  (row-major: cluster kernel)
   float* lstm_b = nullptr;                               // [n_lstm][2][4h] = b_ih + b_hh
   // predictor GEMMs on tcgen05 at fp32-grade precision: split-bf16 weights [hi | hi | lo] (K tripled)
+  int lstm_max_clusters = 15;   // co-resident 8-CTA clusters of lstm_cluster_kernel on this device
   bool pred_tc = false;
   bf16 *wq3 = nullptr, *wkv3 = nullptr, *wo3 = nullptr, *wih3 = nullptr, *wada3 = nullptr;
   float* b_kv = nullptr;
@@ -150,6 +151,25 @@ static int mark_call_end(stz_handle* H, cudaStream_t st) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Kernel launch with programmatic dependent launch (PDL): the next kernel's CTAs are scheduled and run their
+// prologue while the previous kernel drains; every kernel launched this way executes griddepcontrol.wait
+// before touching global memory (ptx.cuh: pdl_wait), so completion stays transitive along the stream.
+// ------------------------------------------------------------------------------------------
+static int g_use_pdl = 1;
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int ew_grid(size_t n, int per_block = 256) {
   size_t g = (n + per_block - 1) / per_block;
@@ -223,7 +243,9 @@ static int launch_gemm_tc(stz_handle* H, cudaStream_t st, const bf16* A, int lda
 // ---- v2: persistent, TMEM double-buffered, TMA-store epilogue (gemm2.cuh) -------------------------
 static int g_num_sms = 148;
 
+static int g_bn_override = 0;   // tuning knob ("gemm_bn"): 0 = heuristic
 static int pick_bn(int M, int N) {
+  if (g_bn_override && N % g_bn_override == 0) return g_bn_override;
   int best = 0;
   long best_cost = 0;
   for (int bn : {256, 192, 128}) {
@@ -247,7 +269,7 @@ static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int ld
   const int tiles = (p.N / BN) * cdiv(p.M, GEMM_BM);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * p.N * p.K);
-  gemm2_kernel<BN, EPI><<<grid, G2_THREADS, g2_smem_bytes<BN>(), st>>>(ta, tb, tc, p);
+  launch_k(gemm2_kernel<BN, EPI>, grid, G2_THREADS, g2_smem_bytes<BN>(), st, ta, tb, tc, p);
   if (H) { KCHECK(H); } else if (cudaGetLastError() != cudaSuccess) return STZ_E_CUDA;
   return 0;
 }
@@ -294,7 +316,10 @@ static cudaError_t init_kernel_attrs() {
   if ((e = set_gemm2_attrs<EPI_GELU_BF16>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_GATE_RES>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_SAMPLER>()) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<10>())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<16>())) != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     g_num_sms = sms;
@@ -324,9 +349,9 @@ static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, 
   dim3 grid(cdiv(N, 64), cdiv(M, 64));
   ProfScope ps(H, st, PC_LINEAR_F32, 2.0 * M * N * (K1 + K2));
   if (act == ACT_SILU)
-    linear_f32_kernel<ACT_SILU><<<grid, 256, 0, st>>>(X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
+    launch_k(linear_f32_kernel<ACT_SILU>, grid, 256, 0, st, X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
   else
-    linear_f32_kernel<ACT_NONE><<<grid, 256, 0, st>>>(X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
+    launch_k(linear_f32_kernel<ACT_NONE>, grid, 256, 0, st, X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
   KCHECK(H);
   return 0;
 }
@@ -336,10 +361,10 @@ static int ln_mod(stz_handle* H, cudaStream_t st, const float* h, int rows, int 
   dim3 grid(cdiv(rows, 8));
   ProfScope ps(H, st, PC_LN, (double)rows * D * 6.0);  // fp32 in + bf16 out
   switch (D / 128) {
-    case 1: ln_mod_kernel<1><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
-    case 2: ln_mod_kernel<2><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
-    case 4: ln_mod_kernel<4><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
-    case 8: ln_mod_kernel<8><<<grid, 256, 0, st>>>(h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 1: launch_k(ln_mod_kernel<1>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 2: launch_k(ln_mod_kernel<2>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 4: launch_k(ln_mod_kernel<4>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 8: launch_k(ln_mod_kernel<8>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
     default: return fail(H, STZ_E_SHAPE, "d_model %d unsupported by ln_mod", D);
   }
   KCHECK(H);
@@ -590,6 +615,7 @@ static int create_impl(stz_handle* H, const float* weights_host) {
                                                      H->lstm_b + ((size_t)l * 2 + dr) * 4 * h, 4 * h, 4 * h);
       KCHECK(H);
     }
+  { const int mc = stz_debug_max_lstm_clusters(); if (mc > 0) H->lstm_max_clusters = mc; }
   {  // split-bf16 predictor weights
     const size_t ds = c.d_sty_tok, dh = c.d_hid, Ds = c.d_style, kin = dh + ds;
     H->pred_tc = ds % 128 == 0 && dh % 128 == 0 && kin % 64 == 0 && c.d_text % 64 == 0 && Ds % 64 == 0;
@@ -670,13 +696,32 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
       H->graphs.clear();
     }
     H->gemm_impl = value;
-  } else if (!strcmp(key, "lstm_impl")) { /* single implementation this round */ }
-  else if (!strcmp(key, "profile")) {
+  } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
+  else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
+  else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl")) {   // process-wide knobs baked into captured graphs
+    for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
+    H->graphs.clear();
+    if (key[0] == 'g') g_bn_override = value; else g_use_pdl = value;
+  } else if (!strcmp(key, "profile")) {
     H->profile = value;
     for (auto& r : H->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     H->prof.clear();
   } else return fail(H, STZ_E_ARG, "unknown option %s", key);
   return 0;
+}
+
+// Max co-resident clusters of the BiLSTM recurrence kernel on the current device (diagnostic).
+extern "C" int stz_debug_max_lstm_clusters(void) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(LC_CS * 64, 2); cfg.blockDim = dim3(LC_THREADS); cfg.dynamicSmemBytes = lstm_cluster_smem<16>();
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = LC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = -1;
+  if (init_kernel_attrs() != cudaSuccess) return -2;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel<8, 2>, &cfg) != cudaSuccess) return -1;
+  return n;
 }
 
 extern "C" int stz_profile_read(stz_handle* H, int cls, double* ms, double* work, int64_t* launches) {
@@ -717,7 +762,7 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
   int n_keys = 0;
   for (int i = 0; i < ap.nseg; ++i) n_keys += ap.seg[i].n;
   ProfScope ps(H, st, PC_ATTN, 4.0 * B * H->cfg.n_heads * ap.n_q * (double)n_keys * ATT_DH);
-  attention_kernel<<<grid, cdiv(ap.n_q, 16) * 32, 0, st>>>(ap);
+  launch_k(attention_kernel, grid, cdiv(ap.n_q, 16) * 32, 0, st, ap);
   KCHECK(H);
   return 0;
 }
@@ -836,13 +881,13 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   CK(H, cudaMemcpyAsync(w.tfeat, pl.tfeat.data(), pl.tfeat.size() * sizeof(float), cudaMemcpyHostToDevice, st));
 
   // ---- conditioning prep (a-3): once per call ---------------------------------------------
-  cast_pool_kernel<<<B, 256, 0, st>>>(text, tmask, w.text_bf, w.pool_text, T, c.d_text); KCHECK(H);
-  cast_pool_kernel<<<B, 256, 0, st>>>(prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
+  launch_k(cast_pool_kernel, B, 256, 0, st, text, tmask, w.text_bf, w.pool_text, T, c.d_text); KCHECK(H);
+  launch_k(cast_pool_kernel, B, 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "ptext.w"), W32(H, "ptext.b"), w.pt, d, B, d));
   RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
   RET(linear_f32(H, st, ACT_SILU, w.tfeat, c.d_time, c.d_time, nullptr, 0, 0, W32(H, "time.w1"), W32(H, "time.b1"), w.t1, d, E, d));
   RET(linear_f32(H, st, ACT_NONE, w.t1, d, d, nullptr, 0, 0, W32(H, "time.w2"), W32(H, "time.b2"), w.temb, d, E, d));
-  cvec_kernel<<<ew_grid((size_t)E * NS * d), 256, 0, st>>>(w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
+  launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
   for (int which = 0; which < 2; ++which) {  // context tokens and their per-layer K/V
     const int rows = which == 0 ? B * T : B * P, din = which == 0 ? c.d_text : c.d_prompt;
     const bf16* src = which == 0 ? w.text_bf : w.prompt_bf;
@@ -860,7 +905,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     }
   }
   // ---- sampler state --------------------------------------------------------------------
-  init_state_kernel<<<ew_grid(BK * Ds / 4), 256, 0, st>>>(noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0); KCHECK(H);
+  launch_k(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0); KCHECK(H);
   if (kind == STZ_SAMPLER_TEACHER)
     CK(H, cudaMemcpyAsync(w.noise, noise, (size_t)slices * BK * Ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
   H->launches += H->cur_launches;
@@ -928,12 +973,12 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
   const int ds = c.d_sty_tok, dh = c.d_hid, h = dh / 2, K = c.n_style, Ds = c.d_style;
   const int BT = B * T, BK = B * K;
   H->cur_launches = 0;
-  lens_perm_kernel<<<1, 1024, 0, st>>>(tmask, w.lens, w.perm, B, T); KCHECK(H);
+  launch_k(lens_perm_kernel, 1, 1024, 0, st, tmask, w.lens, w.perm, B, T); KCHECK(H);
   const bool tc = H->pred_tc && H->pred_gemm_impl == 0;   // split-bf16 tcgen05 GEMMs vs fp32 CUDA-core GEMMs
   const int kin = dh + ds, impl = H->gemm_impl;
   auto split_rows = [&](const float* src, int ld, int Kc, bf16* dst, int ldd, int segK, int off, size_t M) -> int {
     ProfScope ps(H, st, PC_PRED_EW, (double)M * Kc * 10.0);
-    split3_rows_kernel<<<ew_grid(M * (Kc / 4)), 256, 0, st>>>(src, ld, Kc, dst, ldd, segK, off, M);
+    launch_k(split3_rows_kernel, ew_grid(M * (Kc / 4)), 256, 0, st, src, ld, Kc, dst, ldd, segK, off, M);
     KCHECK(H);
     return 0;
   };
@@ -949,7 +994,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     RET(split_rows(style, Ds, Ds, w.pstyle3, 3 * Ds, Ds, 0, BK));
     RET(gemm3(w.pq, 3 * c.d_text, BT, H->wq3, W32(H, "sp.q.b"), w.sq, ds));
     RET(gemm3(w.pstyle3, 3 * Ds, BK, H->wkv3, H->b_kv, w.skv, 2 * ds));
-    style_pool_attn_kernel<<<cdiv(BT, 8), 256, 0, st>>>(w.sq, w.skv, w.skv + ds, 2 * ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
+    launch_k(style_pool_attn_kernel, cdiv(BT, 8), 256, 0, st, w.sq, w.skv, w.skv + ds, 2 * ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
     RET(split_rows(w.sa, ds, ds, w.psa3, 3 * ds, ds, 0, BT));
     RET(gemm3(w.psa3, 3 * ds, BT, H->wo3, W32(H, "sp.o.b"), w.stok, ds));
     RET(split_rows(w.stok, ds, ds, w.pa, 3 * kin, kin, dh, BT));                    // s_tok part, shared by all layers
@@ -958,7 +1003,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     RET(linear_f32(H, st, ACT_NONE, text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "sp.q.w"), W32(H, "sp.q.b"), w.sq, ds, BT, ds));
     RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.k.w"), W32(H, "sp.k.b"), w.sk, ds, BK, ds));
     RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.v.w"), W32(H, "sp.v.b"), w.sv, ds, BK, ds));
-    style_pool_attn_kernel<<<cdiv(BT, 8), 256, 0, st>>>(w.sq, w.sk, w.sv, ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
+    launch_k(style_pool_attn_kernel, cdiv(BT, 8), 256, 0, st, w.sq, w.sk, w.sv, ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
     RET(linear_f32(H, st, ACT_NONE, w.sa, ds, ds, nullptr, 0, 0, W32(H, "sp.o.w"), W32(H, "sp.o.b"), w.stok, ds, BT, ds));
   }
   // a-9: (BiLSTM + AdaLN) x (n_lstm - 1) + BiLSTM
@@ -980,8 +1025,22 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     {
       ProfScope ps(H, st, PC_LSTM, 2.0 * BT * 2.0 * h * 4.0 * h);
       if (h == LC_H && H->lstm_impl == 0) {  // product path: register-resident W_hh, cluster of 8 CTAs, DSMEM exchange
-        lstm_cluster_kernel<NB><<<dim3(cdiv(B, NB) * LC_CS, 2), LC_THREADS, lstm_cluster_smem<NB>(), st>>>(
-            w.G, H->whh + (size_t)l * 2 * 4 * h * h, w.lens, w.perm, xo, B, T);
+        // sequences per cluster: fewest waves of co-resident clusters, then least work per step
+        int best = 8;
+        double best_cost = 1e30;
+        for (int nb : {4, 8, 10, 16}) {
+          const int clusters = 2 * cdiv(B, nb);
+          const double cost = (double)cdiv(clusters, H->lstm_max_clusters) * (1800.0 + 440.0 * nb);
+          if (cost < best_cost) { best_cost = cost; best = nb; }
+        }
+        const float* whh = H->whh + (size_t)l * 2 * 4 * h * h;
+        const dim3 grid(cdiv(B, best) * LC_CS, 2);
+        switch (best) {
+          case 4: launch_k(lstm_cluster_kernel<4, 1>, grid, LC_THREADS, lstm_cluster_smem<4>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
+          case 8: launch_k(lstm_cluster_kernel<8, 1>, grid, LC_THREADS, lstm_cluster_smem<8>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
+          case 10: launch_k(lstm_cluster_kernel<5, 2>, grid, LC_THREADS, lstm_cluster_smem<10>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
+          default: launch_k(lstm_cluster_kernel<8, 2>, grid, LC_THREADS, lstm_cluster_smem<16>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
+        }
       } else {
         lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
       }
@@ -995,10 +1054,10 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
       bf16* a3 = tc ? w.pa : nullptr;
       ProfScope ps(H, st, PC_PRED_EW, (double)BT * dh * 16.0);
       switch (dh / 128) {
-        case 1: adaln_pred_kernel<1><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
-        case 2: adaln_pred_kernel<2><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
-        case 4: adaln_pred_kernel<4><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
-        case 8: adaln_pred_kernel<8><<<grid, 256, 0, st>>>(xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
+        case 1: launch_k(adaln_pred_kernel<1>, grid, 256, 0, st, xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
+        case 2: launch_k(adaln_pred_kernel<2>, grid, 256, 0, st, xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
+        case 4: launch_k(adaln_pred_kernel<4>, grid, 256, 0, st, xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
+        case 8: launch_k(adaln_pred_kernel<8>, grid, 256, 0, st, xo, w.gb, tmask, BT, a3, 3 * kin, kin); break;
         default: return fail(H, STZ_E_SHAPE, "d_hid %d unsupported", dh);
       }
       KCHECK(H);
@@ -1008,10 +1067,10 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
   {  // a-10
     dim3 grid(cdiv(BT, 8));
     switch (dh / 128) {
-      case 1: dur_head_kernel<1><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
-      case 2: dur_head_kernel<2><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
-      case 4: dur_head_kernel<4><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
-      case 8: dur_head_kernel<8><<<grid, 256, 0, st>>>(x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 1: launch_k(dur_head_kernel<1>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 2: launch_k(dur_head_kernel<2>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 4: launch_k(dur_head_kernel<4>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 8: launch_k(dur_head_kernel<8>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
       default: return fail(H, STZ_E_SHAPE, "d_hid %d unsupported", dh);
     }
     KCHECK(H);

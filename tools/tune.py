@@ -1,0 +1,37 @@
+"""GPU tuning sweeps (not a bench): time sample_style / predict_duration of cfg2 under library knobs."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import styletts_zs_b200 as stz
+
+cfg = stz.DEFAULT
+path = stz.StyleTTSZSPath(cfg, stz.init_weights(cfg, 0))
+B, T, steps = int(os.environ.get("B", 64)), int(os.environ.get("T", 64)), 4
+inp = stz.synthetic_inputs(cfg, B, T, steps=steps, seed=1234)
+dev = {k: inp[k].cuda() for k in ("text_emb", "prompt_feats", "noise")}
+
+
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+z = path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=dev["noise"])
+samp = lambda: path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=dev["noise"])
+pred = lambda: path.predict_duration(dev["text_emb"], z)
+res = {}
+for knobs in [{}, {"gemm_bn": 128}, {"gemm_bn": 256}, {"use_pdl": 0}, {"use_graph": 0}]:
+    for k, v in knobs.items():
+        path.set_option(k, v)
+    res[json.dumps(knobs)] = (round(timeit(samp), 3), round(timeit(pred), 3))
+    print(knobs, "sample_style ms", res[json.dumps(knobs)][0], "predict_duration ms", res[json.dumps(knobs)][1], flush=True)
+    for k in knobs:
+        path.set_option(k, {"gemm_bn": 0, "use_pdl": 1, "use_graph": 1}[k])
