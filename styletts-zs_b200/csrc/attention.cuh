@@ -53,11 +53,31 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t sad
                : "r"(saddr));
 }
 
-__global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills (masked / out-of-range keys)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int ATT_MAXQ = 128;
+constexpr int ATT_SMEM_BYTES = (ATT_MAXQ + 4 * ATT_KB) * ATT_LDS * 2 + 2 * ATT_KB;   // Q + 2 x (K, V) + visibility
+
+// All global loads are asynchronous (cp.async): Q and the first two 64-key blocks are in flight before any math,
+// later blocks are fetched into the buffer just consumed (double buffering).
+__global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  __nv_bfloat16 (*Qs)[ATT_LDS] = reinterpret_cast<__nv_bfloat16 (*)[ATT_LDS]>(att_smem);
+  __nv_bfloat16 (*KVs)[ATT_LDS] = reinterpret_cast<__nv_bfloat16 (*)[ATT_LDS]>(att_smem + ATT_MAXQ * ATT_LDS * 2);
+  // KVs rows: [buf][0: K | 1: V][ATT_KB]
+  uint8_t* kvis = att_smem + (ATT_MAXQ + 4 * ATT_KB) * ATT_LDS * 2;   // [2][ATT_KB]; bit0: cond rows, bit1: uncond rows
   pdl_sync();
-  __shared__ __align__(16) __nv_bfloat16 Ks[ATT_KB][ATT_LDS];
-  __shared__ __align__(16) __nv_bfloat16 Vs[ATT_KB][ATT_LDS];
-  __shared__ uint8_t kvis[ATT_KB];  // bit0: visible to cond (even) query rows, bit1: to uncond (odd) rows
 
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,37 +85,17 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   const int row0 = warp * 16 + g, row1 = row0 + 8;  // query rows inside the utterance
   const size_t qbase = static_cast<size_t>(b) * p.n_q;
 
-  // Q fragments (A operand, 16 x 64 per warp)
-  uint32_t qa[4][4];
-  {
-    const __nv_bfloat16* q0 = p.q + (qbase + row0) * p.ldq + head * ATT_DH;
-    const __nv_bfloat16* q1 = p.q + (qbase + row1) * p.ldq + head * ATT_DH;
-    const bool v0 = row0 < p.n_q, v1 = row1 < p.n_q;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      qa[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + t * 2) : 0u;
-      qa[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + t * 2) : 0u;
-      qa[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8 + t * 2) : 0u;
-      qa[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + t * 2) : 0u;
-    }
-  }
-  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-
   int n_total = 0;
   for (int s = 0; s < p.nseg; ++s) n_total += p.seg[s].n;
+  const int n_blk = (n_total + ATT_KB - 1) / ATT_KB;
 
-  for (int kb0 = 0; kb0 < n_total; kb0 += ATT_KB) {
-    __syncthreads();
-    // cooperative load of 64 virtual keys: 8 x 16-byte chunks per key row for K and for V
+  auto load_block = [&](int blk, int buf) {
+    const int kb0 = blk * ATT_KB;
     for (int i = threadIdx.x; i < ATT_KB * 8; i += blockDim.x) {
       const int kr = i >> 3, ch = i & 7;
       int vk = kb0 + kr;
-      uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
+      const __nv_bfloat16 *ksrc = p.seg[0].k, *vsrc = p.seg[0].v;
+      uint32_t bytes = 0;
       uint8_t vis = 0;
       if (vk < n_total) {
         int s = 0;
@@ -104,16 +104,50 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
         const bool ok = sg.mask == nullptr || sg.mask[static_cast<size_t>(b) * sg.n + vk] != 0;
         if (ok) {
           const size_t r = static_cast<size_t>(b) * sg.rows_per_utt + vk;
-          kq = *reinterpret_cast<const uint4*>(sg.k + r * sg.ld + head * ATT_DH + ch * 8);
-          vq = *reinterpret_cast<const uint4*>(sg.v + r * sg.ld + head * ATT_DH + ch * 8);
+          ksrc = sg.k + r * sg.ld + head * ATT_DH + ch * 8;
+          vsrc = sg.v + r * sg.ld + head * ATT_DH + ch * 8;
+          bytes = 16;
           vis = sg.rule == KEY_ALL ? 3 : sg.rule == KEY_COND ? 1 : sg.rule == KEY_UNCOND ? 2 : ((vk & 1) ? 2 : 1);
         }
       }
-      *reinterpret_cast<uint4*>(&Ks[kr][ch * 8]) = kq;
-      *reinterpret_cast<uint4*>(&Vs[kr][ch * 8]) = vq;
-      if (ch == 0) kvis[kr] = vis;
+      cp_async16(smem_u32(&KVs[(buf * 2 + 0) * ATT_KB + kr][ch * 8]), ksrc, bytes);
+      cp_async16(smem_u32(&KVs[(buf * 2 + 1) * ATT_KB + kr][ch * 8]), vsrc, bytes);
+      if (ch == 0) kvis[buf * ATT_KB + kr] = vis;
     }
+  };
+
+  // Q tile (rows >= n_q zero-filled) + key blocks 0 and 1
+  for (int i = threadIdx.x; i < (blockDim.x >> 5) * 16 * 8; i += blockDim.x) {
+    const int r = i >> 3, ch = i & 7;
+    const bool ok = r < p.n_q;
+    cp_async16(smem_u32(&Qs[r][ch * 8]), p.q + (qbase + (ok ? r : 0)) * p.ldq + head * ATT_DH + ch * 8, ok ? 16u : 0u);
+  }
+  load_block(0, 0);
+  cp_async_commit();
+  if (n_blk > 1) load_block(1, 1);
+  cp_async_commit();
+
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  uint32_t qa[4][4];
+
+  for (int blk = 0; blk < n_blk; ++blk) {
+    const int buf = blk & 1;
+    cp_async_wait<1>();      // this block's group (and Q) has landed; the next block may still be in flight
     __syncthreads();
+    if (blk == 0) {          // Q fragments (A operand, 16 x 64 per warp) via ldmatrix
+      const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        ldmatrix_x4(qa[kk], smem_u32(&Qs[warp * 16 + (mi & 1) * 8 + r][kk * 16 + (mi >> 1) * 8]));
+    }
+    const __nv_bfloat16 (*Ks)[ATT_LDS] = &KVs[(buf * 2 + 0) * ATT_KB];
+    const __nv_bfloat16 (*Vs)[ATT_LDS] = &KVs[(buf * 2 + 1) * ATT_KB];
+    const uint8_t* kv = kvis + buf * ATT_KB;
 
     // S = Q K^T  (16 x 64 per warp)
     float sc[8][4];
@@ -133,7 +167,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const uint8_t vis = kvis[nt * 8 + t * 2 + j];
+        const uint8_t vis = kv[nt * 8 + t * 2 + j];
         const bool s0 = (vis >> (row0 & 1)) & 1, s1 = (vis >> (row1 & 1)) & 1;
         sc[nt][j] = s0 ? sc[nt][j] * p.scale_log2 : -INFINITY;
         sc[nt][2 + j] = s1 ? sc[nt][2 + j] * p.scale_log2 : -INFINITY;
@@ -185,6 +219,9 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
         mma_bf16_16816(o[2 * ntp + 1], pa, vb[2], vb[3]);
       }
     }
+    __syncthreads();                       // everyone is done with buffer `buf`
+    if (blk + 2 < n_blk) load_block(blk + 2, buf);
+    cp_async_commit();                     // (possibly empty) keeps the group count in step with the block index
   }
   // finalize
 #pragma unroll

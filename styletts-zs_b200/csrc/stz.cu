@@ -316,6 +316,7 @@ static cudaError_t init_kernel_attrs() {
   if ((e = set_gemm2_attrs<EPI_GELU_BF16>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_GATE_RES>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_SAMPLER>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<10>())) != cudaSuccess) return e;
@@ -762,7 +763,7 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
   int n_keys = 0;
   for (int i = 0; i < ap.nseg; ++i) n_keys += ap.seg[i].n;
   ProfScope ps(H, st, PC_ATTN, 4.0 * B * H->cfg.n_heads * ap.n_q * (double)n_keys * ATT_DH);
-  launch_k(attention_kernel, grid, cdiv(ap.n_q, 16) * 32, 0, st, ap);
+  launch_k(attention_kernel, grid, cdiv(ap.n_q, 16) * 32, ATT_SMEM_BYTES, st, ap);
   KCHECK(H);
   return 0;
 }
