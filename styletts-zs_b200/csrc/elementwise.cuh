@@ -21,29 +21,39 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// x [B,T,D] fp32 -> xb [B,T,D] bf16 and pooled [B,D] = masked mean over T (a-3).  grid = B.
+// x [B,T,D] fp32 -> xb [B,T,D] bf16 and pooled [B,D] = masked mean over T (a-3).
+// grid = (B, D/128): a CTA owns 32 float4 columns of one utterance; 8 time slices x 32 column lanes.
 __global__ void __launch_bounds__(256) cast_pool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
                                                         __nv_bfloat16* __restrict__ xb, float* __restrict__ pooled,
                                                         int T, int D) {
   pdl_sync();
-  const int b = blockIdx.x;
-  const int nvec = D >> 2;
+  __shared__ float4 part[8][32];
+  __shared__ int cnt_s[8];
+  const int b = blockIdx.x, cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cl;     // float4 column
   const float* xr = x + static_cast<size_t>(b) * T * D;
   __nv_bfloat16* br = xb + static_cast<size_t>(b) * T * D;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
-  for (int t = 0; t < T; ++t) cnt += (mask == nullptr || mask[static_cast<size_t>(b) * T + t]) ? 1 : 0;
-  const float inv = 1.0f / static_cast<float>(cnt > 0 ? cnt : 1);
-  for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < T; ++t) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(xr + static_cast<size_t>(t) * D) + c);
-      uint2 u;
-      u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
-      *reinterpret_cast<uint2*>(br + static_cast<size_t>(t) * D + c * 4) = u;
-      if (mask == nullptr || mask[static_cast<size_t>(b) * T + t]) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+  for (int t = sl; t < T; t += 8) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xr + static_cast<size_t>(t) * D) + c);
+    uint2 u;
+    u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(br + static_cast<size_t>(t) * D + c * 4) = u;
+    if (mask == nullptr || mask[static_cast<size_t>(b) * T + t]) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; ++cnt; }
+  }
+  part[sl][cl] = acc;
+  if (cl == 0) cnt_s[sl] = cnt;
+  __syncthreads();
+  if (sl == 0) {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      n += cnt_s[i];
+      if (i > 0) { const float4 q = part[i][cl]; acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w; }
     }
-    *reinterpret_cast<float4*>(pooled + static_cast<size_t>(b) * D + c * 4) =
-        make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    const float inv = 1.0f / static_cast<float>(n > 0 ? n : 1);
+    *reinterpret_cast<float4*>(pooled + static_cast<size_t>(b) * D + c * 4) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
   }
 }
 

@@ -335,4 +335,42 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
   }
 }
 
+// Small-M fp32 linear (pooled-conditioning projections, time-embedding MLP: M <= a few hundred rows).
+// One warp per (row m, 8 consecutive outputs): lanes split K with coalesced 128-bit loads, 8 independent
+// accumulators, one batched warp reduction.  K % 128 == 0, N % 8 == 0.
+template <int ACT>
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                          const float* __restrict__ b, float* __restrict__ Y, int ldy,
+                                                          int M, int N, int K) {
+  pdl_sync();
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int ngrp = N >> 3;
+  if (warp >= M * ngrp) return;
+  const int m = warp / ngrp, n0 = (warp % ngrp) << 3;
+  const float4* xr = reinterpret_cast<const float4*>(X + static_cast<size_t>(m) * ldx);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int k4 = lane; k4 < (K >> 2); k4 += 32) {
+    const float4 x = xr[k4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n0 + j) * K) + k4);
+      acc[j] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[j]))));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  if (lane < 8) {
+    float y = acc[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) y = lane == j ? acc[j] : y;
+    y += b != nullptr ? b[n0 + lane] : 0.f;
+    if (ACT == ACT_SILU) y = silu(y);
+    Y[static_cast<size_t>(m) * ldy + n0 + lane] = y;
+  }
+}
+
 }  // namespace stz

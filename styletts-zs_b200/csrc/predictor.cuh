@@ -199,17 +199,29 @@ __global__ void __launch_bounds__(256) dur_head_kernel(const float* __restrict__
   float4 v[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) v[i] = xr[i * 32 + lane];
+  // 10 logits at a time: independent partial dot products, then one batched warp reduction (no serial latency chain)
   float total = 0.f;
-  for (int j = 0; j < max_dur; ++j) {
-    const float4* wr = reinterpret_cast<const float4*>(Wd + static_cast<size_t>(j) * D);
-    float d = 0.f;
+  for (int j0 = 0; j0 < max_dur; j0 += 10) {
+    float d[10];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float4 w = __ldg(wr + i * 32 + lane);
-      d += v[i].x * w.x + v[i].y * w.y + v[i].z * w.z + v[i].w * w.w;
+    for (int jj = 0; jj < 10; ++jj) {
+      d[jj] = 0.f;
+      if (j0 + jj < max_dur) {
+        const float4* wr = reinterpret_cast<const float4*>(Wd + static_cast<size_t>(j0 + jj) * D);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const float4 w = __ldg(wr + i * 32 + lane);
+          d[jj] += v[i].x * w.x + v[i].y * w.y + v[i].z * w.z + v[i].w * w.w;
+        }
+      }
     }
-    d = warp_sum(d) + __ldg(bd + j);
-    total += sigmoidf_(d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int jj = 0; jj < 10; ++jj) d[jj] += __shfl_xor_sync(0xffffffffu, d[jj], o);
+#pragma unroll
+    for (int jj = 0; jj < 10; ++jj)
+      if (j0 + jj < max_dur) total += sigmoidf_(d[jj] + __ldg(bd + j0 + jj));
   }
   if (lane == 0) {
     const bool ok = mask == nullptr || mask[row] != 0;

@@ -19,6 +19,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "gemm_ln.cuh"
 #include "predictor.cuh"
 #include "stz_layout.h"
 
@@ -77,7 +78,7 @@ struct stz_handle {
   cudaEvent_t last_ev = nullptr;
   bool has_last = false;
   std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
-  int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0;
+  int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 0;
   int64_t launches = 0;
   int cur_launches = 0;  // launches issued since the counter was last sampled (capture bookkeeping)
   int tap_eval = -1, tap_layer = -1, tap_stage = -1;
@@ -284,6 +285,22 @@ static int launch_gemm2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, 
   return fail(H, STZ_E_SHAPE, "gemm N=%d is not a multiple of 128", p.N);
 }
 
+// ---- fused GEMM + residual/pos + AdaLN (gemm_ln.cuh): N = d_model = 512 ------------------------------
+template <int MODE>
+static int launch_gemmln(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
+                         const GemmLnParams& p) {
+  CUtensorMap ta, tb, tu, th;
+  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
+      make_tmap(&tb, W, (uint64_t)GLN_N, (uint64_t)p.K, (uint64_t)p.K, 128) ||
+      make_tmap_out(&th, p.h, false, (uint64_t)p.M, (uint64_t)GLN_N, (uint64_t)GLN_N) ||
+      make_tmap_out(&tu, u, true, (uint64_t)p.M, (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N)))
+    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (gemmln M=%d K=%d)", p.M, p.K);
+  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * GLN_N * p.K);
+  launch_k(gemmln_kernel<MODE>, cdiv(p.M, GEMM_BM), GLN_THREADS, GLN_SMEM_BYTES, st, ta, tb, tu, th, p);
+  KCHECK(H);
+  return 0;
+}
+
 template <int BN, int EPI>
 static cudaError_t set_gemm2_attr() {
   return cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
@@ -316,6 +333,8 @@ static cudaError_t init_kernel_attrs() {
   if ((e = set_gemm2_attrs<EPI_GELU_BF16>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_GATE_RES>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_SAMPLER>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
@@ -347,8 +366,15 @@ static int gemm(stz_handle* H, cudaStream_t st, int impl, const bf16* A, int lda
 
 static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, int ld1, int K1, const float* X2, int ld2,
                       int K2, const float* W, const float* b, float* Y, int ldy, int M, int N) {
-  dim3 grid(cdiv(N, 64), cdiv(M, 64));
   ProfScope ps(H, st, PC_LINEAR_F32, 2.0 * M * N * (K1 + K2));
+  if (K2 == 0 && M <= 512 && K1 % 128 == 0 && N % 8 == 0 && ld1 % 4 == 0) {   // tiny-M: warp-per-output kernel
+    const int warps = M * (N / 8);
+    if (act == ACT_SILU) launch_k(small_linear_kernel<ACT_SILU>, cdiv(warps, 8), 256, 0, st, X1, ld1, W, b, Y, ldy, M, N, K1);
+    else launch_k(small_linear_kernel<ACT_NONE>, cdiv(warps, 8), 256, 0, st, X1, ld1, W, b, Y, ldy, M, N, K1);
+    KCHECK(H);
+    return 0;
+  }
+  dim3 grid(cdiv(N, 64), cdiv(M, 64));
   if (act == ACT_SILU)
     launch_k(linear_f32_kernel<ACT_SILU>, grid, 256, 0, st, X1, ld1, K1, X2, ld2, K2, W, b, Y, ldy, M, N);
   else
@@ -381,7 +407,7 @@ static const bf16* WBF(const stz_handle* H, const std::string& name) { return H-
 static int check_config(const stz_config& c) {
   if (c.n_heads <= 0 || c.d_model != c.n_heads * 64) return -1;            // d_head == 64 (attention.cuh)
   if (c.d_model % 128 || c.d_ff % 128 || c.d_style % 128) return -1;       // N tiles of 128
-  if (c.d_text % 64 || c.d_prompt % 64 || c.d_model % 64 || c.d_ff % 64 || c.d_style % 64) return -1;  // K tiles of 64
+  if (c.d_text % 128 || c.d_prompt % 128 || c.d_model % 64 || c.d_ff % 64 || c.d_style % 64) return -1;  // K tiles of 64; cast_pool: 128 columns per CTA
   if (c.d_model > 1024 || c.d_hid > 1024 || c.d_hid % 128) return -1;      // warp-per-row kernels
   if (c.n_style < 1 || c.n_style > 64) return -1;                          // 2K query rows <= 128
   if (c.d_hid != c.d_text) return -1;                                      // x0 = text_emb
@@ -699,6 +725,11 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
+  else if (!strcmp(key, "fuse_ln")) {
+    for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
+    H->graphs.clear();
+    H->fuse_ln = value;
+  }
   else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl")) {   // process-wide knobs baked into captured graphs
     for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
     H->graphs.clear();
@@ -783,16 +814,37 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
     p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * NS; p.bias = W32(H, "mod.b"); p.out = w.mod; p.ldo = n_mod;
     RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
   }
-  {  // h = x_in · Win^T + b + pos
+  const bool fused = H->fuse_ln && impl == 0 && d == GLN_N;   // GEMM + residual + AdaLN in one kernel (gemm_ln.cuh)
+  GemmLnParams lb{};
+  lb.M = R; lb.h = w.h; lb.mod = w.mod; lb.n_mod = n_mod; lb.rows_per_utt = 2 * K; lb.pos = W32(H, "pos"); lb.n_style = K;
+  // residual GEMM of a sub-layer followed by the AdaLN of the next one: (gate, shift, scale) offsets into mod
+  auto res_ln = [&](const bf16* A, int Kc, const bf16* Wt, const float* bias, int gate_off, int ln_off, bool last) -> int {
+    if (fused) {
+      GemmLnParams p = lb;
+      p.K = Kc; p.bias = bias; p.gate_off = gate_off; p.shift_off = ln_off; p.scale_off = ln_off + d; p.split3 = last ? 1 : 0;
+      return launch_gemmln<GLN_RES>(H, st, A, Kc, R, Wt, last ? w.u3 : w.u, p);
+    }
     GemmParams p = base;
-    p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = w.h; p.ldo = d; p.pos = W32(H, "pos");
-    RET(gemm<EPI_F32_POS>(H, st, impl, w.xin, 3 * Ds, R, H->w_in3, p));
+    p.M = R; p.N = d; p.K = Kc; p.bias = bias; p.out = w.h; p.ldo = d; p.gate_off = gate_off;
+    RET(gemm<EPI_GATE_RES>(H, st, impl, A, Kc, R, Wt, p));
+    return ln_mod(H, st, w.h, R, d, w.mod, n_mod, ln_off, ln_off + d, 2 * K, last ? w.u3 : w.u, last ? 1 : 0);
+  };
+  {  // h = x_in · Win^T + b + pos, u = AdaLN_1 of layer 0
+    if (fused) {
+      GemmLnParams p = lb;
+      p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.shift_off = 0; p.scale_off = d; p.split3 = 0;
+      RET(launch_gemmln<GLN_POS>(H, st, w.xin, 3 * Ds, R, H->w_in3, w.u, p));
+    } else {
+      GemmParams p = base;
+      p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = w.h; p.ldo = d; p.pos = W32(H, "pos");
+      RET(gemm<EPI_F32_POS>(H, st, impl, w.xin, 3 * Ds, R, H->w_in3, p));
+      RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, 0, d, 2 * K, w.u));
+    }
   }
   for (int l = 0; l < L; ++l) {
     const std::string pf = "l" + std::to_string(l) + ".";
     const int mo = 9 * l * d;
-    // --- self-attention
-    RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, mo + 0 * d, mo + 1 * d, 2 * K, w.u));
+    // --- self-attention (u holds AdaLN_1(h))
     {
       GemmParams p = base;
       p.M = R; p.N = 3 * d; p.K = d; p.bias = W32(H, pf + "qkv.b"); p.out = w.qkv; p.ldo = 3 * d;
@@ -804,14 +856,9 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
       ap.seg[0] = AttnSeg{w.qkv + d, w.qkv + 2 * d, 3 * d, 2 * K, 2 * K, nullptr, KEY_SAME_BRANCH};
       RET(attention(H, st, ap, B));
     }
-    {
-      GemmParams p = base;
-      p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "o.b"); p.out = w.h; p.ldo = d; p.gate_off = mo + 2 * d;
-      RET(gemm<EPI_GATE_RES>(H, st, impl, w.att, d, R, WBF(H, pf + "o.w"), p));
-    }
+    RET(res_ln(w.att, d, WBF(H, pf + "o.w"), W32(H, pf + "o.b"), mo + 2 * d, mo + 3 * d, false));
     RET(tap(H, st, e, l, 0, R));
-    // --- cross-attention over [text ; prompt | null]
-    RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, mo + 3 * d, mo + 4 * d, 2 * K, w.u));
+    // --- cross-attention over [text ; prompt | null]  (u holds AdaLN_2(h))
     {
       GemmParams p = base;
       p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "q2.b"); p.out = w.qkv; p.ldo = d;
@@ -826,27 +873,17 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
       ap.seg[2] = AttnSeg{H->kv_null + l * 2 * d, H->kv_null + l * 2 * d + d, ldkv, 1, 0, nullptr, KEY_UNCOND};
       RET(attention(H, st, ap, B));
     }
-    {
-      GemmParams p = base;
-      p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "o2.b"); p.out = w.h; p.ldo = d; p.gate_off = mo + 5 * d;
-      RET(gemm<EPI_GATE_RES>(H, st, impl, w.att, d, R, WBF(H, pf + "o2.w"), p));
-    }
+    RET(res_ln(w.att, d, WBF(H, pf + "o2.w"), W32(H, pf + "o2.b"), mo + 5 * d, mo + 6 * d, false));
     RET(tap(H, st, e, l, 1, R));
-    // --- FFN
-    RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, mo + 6 * d, mo + 7 * d, 2 * K, w.u));
+    // --- FFN  (u holds AdaLN_3(h)); its residual GEMM also produces AdaLN_1 of the next layer / the final AdaLN
     {
       GemmParams p = base;
       p.M = R; p.N = c.d_ff; p.K = d; p.bias = W32(H, pf + "ff1.b"); p.out = w.ffh; p.ldo = c.d_ff;
       RET(gemm<EPI_GELU_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "ff1.w"), p));
     }
-    {
-      GemmParams p = base;
-      p.M = R; p.N = d; p.K = c.d_ff; p.bias = W32(H, pf + "ff2.b"); p.out = w.h; p.ldo = d; p.gate_off = mo + 8 * d;
-      RET(gemm<EPI_GATE_RES>(H, st, impl, w.ffh, c.d_ff, R, WBF(H, pf + "ff2.w"), p));
-    }
+    RET(res_ln(w.ffh, c.d_ff, WBF(H, pf + "ff2.w"), W32(H, pf + "ff2.b"), mo + 8 * d, 9 * (l + 1) * d, l == L - 1));
     RET(tap(H, st, e, l, 2, R));
   }
-  RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, 9 * L * d, 9 * L * d + d, 2 * K, w.u3, 1));
   {  // F = u · Wout^T + b, then CFG combine + sampler update + next input in the epilogue
     GemmParams p = base;
     p.M = R; p.N = Ds; p.K = 3 * d; p.bias = W32(H, "out.b"); p.ldo = Ds;
@@ -882,8 +919,8 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   CK(H, cudaMemcpyAsync(w.tfeat, pl.tfeat.data(), pl.tfeat.size() * sizeof(float), cudaMemcpyHostToDevice, st));
 
   // ---- conditioning prep (a-3): once per call ---------------------------------------------
-  launch_k(cast_pool_kernel, B, 256, 0, st, text, tmask, w.text_bf, w.pool_text, T, c.d_text); KCHECK(H);
-  launch_k(cast_pool_kernel, B, 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
+  launch_k(cast_pool_kernel, dim3(B, c.d_text / 128), 256, 0, st, text, tmask, w.text_bf, w.pool_text, T, c.d_text); KCHECK(H);
+  launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "ptext.w"), W32(H, "ptext.b"), w.pt, d, B, d));
   RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
   RET(linear_f32(H, st, ACT_SILU, w.tfeat, c.d_time, c.d_time, nullptr, 0, 0, W32(H, "time.w1"), W32(H, "time.b1"), w.t1, d, E, d));

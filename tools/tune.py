@@ -28,10 +28,10 @@ z = path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=de
 samp = lambda: path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=dev["noise"])
 pred = lambda: path.predict_duration(dev["text_emb"], z)
 res = {}
-for knobs in [{}, {"gemm_bn": 128}, {"gemm_bn": 256}, {"use_pdl": 0}, {"use_graph": 0}]:
+for knobs in [{}, {"fuse_ln": 0}, {"use_pdl": 0}, {"use_graph": 0}]:
     for k, v in knobs.items():
         path.set_option(k, v)
     res[json.dumps(knobs)] = (round(timeit(samp), 3), round(timeit(pred), 3))
     print(knobs, "sample_style ms", res[json.dumps(knobs)][0], "predict_duration ms", res[json.dumps(knobs)][1], flush=True)
     for k in knobs:
-        path.set_option(k, {"gemm_bn": 0, "use_pdl": 1, "use_graph": 1}[k])
+        path.set_option(k, {"gemm_bn": 0, "use_pdl": 1, "use_graph": 1, "fuse_ln": 1}[k])
