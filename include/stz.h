@@ -122,6 +122,11 @@ int stz_profile_read(stz_handle* h, int kernel_class, double* ms, double* work, 
  * tap_dev = NULL disables. */
 int stz_debug_set_tap(stz_handle* h, int eval, int layer, int stage, float* tap_dev);
 
+/* Roofline measurement hook (bench.py): `iters` back-to-back launches of the product GEMM kernel for one shape
+ * (C[M,N] = A[M,K] W[N,K]^T, epi 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual reduce-add) on the handle's
+ * internal stream, timed with a CUDA-event pair; *avg_us = mean microseconds per launch.  Zero-filled operands. */
+int stz_bench_gemm(stz_handle* h, int M, int N, int K, int epi, int iters, double* avg_us);
+
 /* Max co-resident 8-CTA clusters of the BiLSTM recurrence kernel on the current device (diagnostic). */
 int stz_debug_max_lstm_clusters(void);
 

@@ -69,7 +69,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 constexpr int ATT_MAXQ = 128;
 constexpr int ATT_SMEM_BYTES = (ATT_MAXQ + 4 * ATT_KB) * ATT_LDS * 2 + 2 * ATT_KB;   // Q + 2 x (K, V) + visibility
 
-// All global loads are asynchronous (cp.async): Q and the first two 64-key blocks are in flight before any math,
+// Warps are split by CFG branch: warp w handles 16 style tokens of branch w / nwb (nwb = ceil(K / 16)), so a warp
+// only ever multiplies against keys its branch can see:
+//   self-attention : keys are de-interleaved at load time, block 0 = conditional rows, block 1 = unconditional
+//                    rows; a warp processes exactly one 64-key block (instead of 2 x 64 half-masked keys);
+//   cross-attention: 8-key tiles without a visible key for the warp's branch are skipped (warp-uniform predicate).
+// All global loads are asynchronous (cp.async): Q and the first two key blocks are in flight before any math,
 // later blocks are fetched into the buffer just consumed (double buffering).
 __global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -82,45 +87,53 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int row0 = warp * 16 + g, row1 = row0 + 8;  // query rows inside the utterance
+  const int n_tok = p.n_q >> 1;                       // style tokens per branch
+  const int nwb = (blockDim.x >> 5) >> 1;             // warps per branch
+  const int br = warp / nwb, qt = warp - br * nwb;
+  const int tok0 = qt * 16 + g, tok1 = tok0 + 8;      // this thread's two style tokens (rows of the MMA tile)
   const size_t qbase = static_cast<size_t>(b) * p.n_q;
+  const bool self_attn = p.nseg == 1 && p.seg[0].rule == KEY_SAME_BRANCH;
 
   int n_total = 0;
   for (int s = 0; s < p.nseg; ++s) n_total += p.seg[s].n;
-  const int n_blk = (n_total + ATT_KB - 1) / ATT_KB;
+  const int n_blk = self_attn ? 2 : (n_total + ATT_KB - 1) / ATT_KB;
 
+  // one thread = one key row, two 16-byte chunks of K and of V (blockDim.x == 256: 64 rows x 4 threads)
   auto load_block = [&](int blk, int buf) {
-    const int kb0 = blk * ATT_KB;
-    for (int i = threadIdx.x; i < ATT_KB * 8; i += blockDim.x) {
-      const int kr = i >> 3, ch = i & 7;
-      int vk = kb0 + kr;
+    for (int i = threadIdx.x; i < ATT_KB * 4; i += blockDim.x) {
+      const int kr = i >> 2, c0 = (i & 3) * 2;
       const __nv_bfloat16 *ksrc = p.seg[0].k, *vsrc = p.seg[0].v;
       uint32_t bytes = 0;
       uint8_t vis = 0;
-      if (vk < n_total) {
+      int vk = self_attn ? 2 * kr + blk : blk * ATT_KB + kr;   // self: block = branch, slot = token
+      if (vk < n_total && (!self_attn || kr < n_tok)) {
         int s = 0;
         while (vk >= p.seg[s].n) { vk -= p.seg[s].n; ++s; }
         const AttnSeg& sg = p.seg[s];
         const bool ok = sg.mask == nullptr || sg.mask[static_cast<size_t>(b) * sg.n + vk] != 0;
         if (ok) {
           const size_t r = static_cast<size_t>(b) * sg.rows_per_utt + vk;
-          ksrc = sg.k + r * sg.ld + head * ATT_DH + ch * 8;
-          vsrc = sg.v + r * sg.ld + head * ATT_DH + ch * 8;
+          ksrc = sg.k + r * sg.ld + head * ATT_DH;
+          vsrc = sg.v + r * sg.ld + head * ATT_DH;
           bytes = 16;
           vis = sg.rule == KEY_ALL ? 3 : sg.rule == KEY_COND ? 1 : sg.rule == KEY_UNCOND ? 2 : ((vk & 1) ? 2 : 1);
         }
       }
-      cp_async16(smem_u32(&KVs[(buf * 2 + 0) * ATT_KB + kr][ch * 8]), ksrc, bytes);
-      cp_async16(smem_u32(&KVs[(buf * 2 + 1) * ATT_KB + kr][ch * 8]), vsrc, bytes);
-      if (ch == 0) kvis[buf * ATT_KB + kr] = vis;
+#pragma unroll
+      for (int c = c0; c < c0 + 2; ++c) {
+        cp_async16(smem_u32(&KVs[(buf * 2 + 0) * ATT_KB + kr][c * 8]), ksrc + c * 8, bytes);
+        cp_async16(smem_u32(&KVs[(buf * 2 + 1) * ATT_KB + kr][c * 8]), vsrc + c * 8, bytes);
+      }
+      if (c0 == 0) kvis[buf * ATT_KB + kr] = vis;
     }
   };
 
-  // Q tile (rows >= n_q zero-filled) + key blocks 0 and 1
+  // Q tile, de-interleaved: smem row (br * nwb + qt) * 16 + i  <-  global row 2 * tok + br   (tok >= n_tok: zeros)
   for (int i = threadIdx.x; i < (blockDim.x >> 5) * 16 * 8; i += blockDim.x) {
     const int r = i >> 3, ch = i & 7;
-    const bool ok = r < p.n_q;
-    cp_async16(smem_u32(&Qs[r][ch * 8]), p.q + (qbase + (ok ? r : 0)) * p.ldq + head * ATT_DH + ch * 8, ok ? 16u : 0u);
+    const int rb = r / (nwb * 16), tok = r - rb * nwb * 16;
+    const bool ok = tok < n_tok;
+    cp_async16(smem_u32(&Qs[r][ch * 8]), p.q + (qbase + (ok ? 2 * tok + rb : 0)) * p.ldq + head * ATT_DH + ch * 8, ok ? 16u : 0u);
   }
   load_block(0, 0);
   cp_async_commit();
@@ -134,43 +147,47 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   uint32_t qa[4][4];
-
-  for (int blk = 0; blk < n_blk; ++blk) {
-    const int buf = blk & 1;
-    cp_async_wait<1>();      // this block's group (and Q) has landed; the next block may still be in flight
-    __syncthreads();
-    if (blk == 0) {          // Q fragments (A operand, 16 x 64 per warp) via ldmatrix
-      const int mi = lane >> 3, r = lane & 7;
+  auto load_q = [&]() {   // Q fragments (A operand, 16 x 64 per warp) via ldmatrix
+    const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        ldmatrix_x4(qa[kk], smem_u32(&Qs[warp * 16 + (mi & 1) * 8 + r][kk * 16 + (mi >> 1) * 8]));
-    }
+    for (int kk = 0; kk < 4; ++kk)
+      ldmatrix_x4(qa[kk], smem_u32(&Qs[warp * 16 + (mi & 1) * 8 + r][kk * 16 + (mi >> 1) * 8]));
+  };
+
+  auto process = [&](int buf) {
     const __nv_bfloat16 (*Ks)[ATT_LDS] = &KVs[(buf * 2 + 0) * ATT_KB];
     const __nv_bfloat16 (*Vs)[ATT_LDS] = &KVs[(buf * 2 + 1) * ATT_KB];
     const uint8_t* kv = kvis + buf * ATT_KB;
+    // 8-key tiles with at least one key visible to this warp's branch
+    const uint32_t pair = __ballot_sync(0xffffffffu, (((kv[2 * lane] | kv[2 * lane + 1]) >> br) & 1) != 0);
+    uint32_t tmask = 0;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) tmask |= ((pair >> (4 * nt)) & 0xFu) ? (1u << nt) : 0u;
+    if (tmask == 0) return;
 
-    // S = Q K^T  (16 x 64 per warp)
+    // S = Q K^T  (16 x 64 per warp), invisible tiles skipped
     float sc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      if ((tmask >> nt) & 1) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][kk * 16 + t * 2]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][kk * 16 + 8 + t * 2]);
-        mma_bf16_16816(sc[nt], qa[kk], b0, b1);
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][kk * 16 + t * 2]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][kk * 16 + 8 + t * 2]);
+          mma_bf16_16816(sc[nt], qa[kk], b0, b1);
+        }
       }
     }
-    // scale, mask, block row max
+    // scale, mask, block row max (both rows of this thread belong to branch br)
     float bm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const uint8_t vis = kv[nt * 8 + t * 2 + j];
-        const bool s0 = (vis >> (row0 & 1)) & 1, s1 = (vis >> (row1 & 1)) & 1;
-        sc[nt][j] = s0 ? sc[nt][j] * p.scale_log2 : -INFINITY;
-        sc[nt][2 + j] = s1 ? sc[nt][2 + j] * p.scale_log2 : -INFINITY;
+        const bool vis = ((tmask >> nt) & 1) && ((kv[nt * 8 + t * 2 + j] >> br) & 1);
+        sc[nt][j] = vis ? sc[nt][j] * p.scale_log2 : -INFINITY;
+        sc[nt][2 + j] = vis ? sc[nt][2 + j] * p.scale_log2 : -INFINITY;
         bm[0] = fmaxf(bm[0], sc[nt][j]);
         bm[1] = fmaxf(bm[1], sc[nt][2 + j]);
       }
@@ -193,17 +210,22 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+      if ((tmask >> nt) & 1) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        sc[nt][j] = exp2f(sc[nt][j] - mnew[0]);
-        sc[nt][2 + j] = exp2f(sc[nt][2 + j] - mnew[1]);
-        lrow[0] += sc[nt][j];
-        lrow[1] += sc[nt][2 + j];
+        for (int j = 0; j < 2; ++j) {
+          sc[nt][j] = exp2f(sc[nt][j] - mnew[0]);
+          sc[nt][2 + j] = exp2f(sc[nt][2 + j] - mnew[1]);
+          lrow[0] += sc[nt][j];
+          lrow[1] += sc[nt][2 + j];
+        }
+      } else {
+        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
       }
     }
-    // O += P V  (P rounded to bf16 as the MMA A operand; row sums stay fp32)
+    // O += P V  (P rounded to bf16 as the MMA A operand; row sums stay fp32); 16-key steps without visible keys skipped
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      if (((tmask >> (2 * kk)) & 3u) == 0) continue;
       uint32_t pa[4];
       pa[0] = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
       pa[1] = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
@@ -219,9 +241,24 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
         mma_bf16_16816(o[2 * ntp + 1], pa, vb[2], vb[3]);
       }
     }
-    __syncthreads();                       // everyone is done with buffer `buf`
-    if (blk + 2 < n_blk) load_block(blk + 2, buf);
-    cp_async_commit();                     // (possibly empty) keeps the group count in step with the block index
+  };
+
+  if (self_attn) {
+    cp_async_wait<0>();
+    __syncthreads();
+    load_q();
+    process(br);            // block br holds exactly the keys of this warp's branch
+  } else {
+    for (int blk = 0; blk < n_blk; ++blk) {
+      const int buf = blk & 1;
+      cp_async_wait<1>();      // this block's group (and Q) has landed; the next block may still be in flight
+      __syncthreads();
+      if (blk == 0) load_q();
+      process(buf);
+      __syncthreads();                       // everyone is done with buffer `buf`
+      if (blk + 2 < n_blk) load_block(blk + 2, buf);
+      cp_async_commit();                     // (possibly empty) keeps the group count in step with the block index
+    }
   }
   // finalize
 #pragma unroll
@@ -230,13 +267,13 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
     lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
   }
   const float inv0 = lrow[0] > 0.f ? 1.f / lrow[0] : 0.f, inv1 = lrow[1] > 0.f ? 1.f / lrow[1] : 0.f;
-  if (row0 < p.n_q) {
-    __nv_bfloat16* op = p.out + (qbase + row0) * p.ldo + head * ATT_DH + t * 2;
+  if (tok0 < n_tok) {
+    __nv_bfloat16* op = p.out + (qbase + 2 * tok0 + br) * p.ldo + head * ATT_DH + t * 2;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
   }
-  if (row1 < p.n_q) {
-    __nv_bfloat16* op = p.out + (qbase + row1) * p.ldo + head * ATT_DH + t * 2;
+  if (tok1 < n_tok) {
+    __nv_bfloat16* op = p.out + (qbase + 2 * tok1 + br) * p.ldo + head * ATT_DH + t * 2;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
   }

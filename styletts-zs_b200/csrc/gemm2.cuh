@@ -58,7 +58,23 @@ constexpr bool g2_staged() { return EPI == EPI_F32 || EPI == EPI_BF16 || EPI == 
 template <int EPI>
 constexpr bool g2_out_bf16() { return EPI == EPI_BF16 || EPI == EPI_GELU_BF16; }
 
-template <int BN, int EPI>
+// CM = 2: launched as clusters of two CTAs that own vertically adjacent tiles (same n-tile).  Each CTA fetches
+// half of the shared W tile and TMA-multicasts it into both CTAs' stages (L2 -> SM weight traffic halves); a smem
+// stage is recycled only when the MMA warps of BOTH CTAs have consumed it (multicast tcgen05.commit).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t g2_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void g2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int BN, int EPI, int CM = 1>
 __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmC,
@@ -79,7 +95,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.K / GEMM_BK;
   const int tiles_n = p.N / BN;
-  const int n_tiles = tiles_n * ((p.M + GEMM_BM - 1) / GEMM_BM);
+  // work units: CM vertically adjacent tiles x one n-tile; unit u -> tile_m = CM * (u / tiles_n) + rank, tile_n = u % tiles_n
+  const int n_tiles = tiles_n * (((p.M + GEMM_BM - 1) / GEMM_BM + CM - 1) / CM);
+  const int crank = CM > 1 ? static_cast<int>(g2_cluster_rank()) : 0;
+  const int unit0 = blockIdx.x / CM, unit_stride = gridDim.x / CM;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -87,7 +106,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     if (g2_staged<EPI>()) prefetch_tmap(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CM);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -100,14 +119,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if constexpr (CM > 1) g2_cluster_sync();   // peer barriers are initialised before any multicast / remote arrive
   pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+      for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
+        const int tile_m = CM * (tile / tiles_n) + crank, tile_n = tile % tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -117,11 +137,21 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
               ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK),
               "r"(p.a_row0 + tile_m * GEMM_BM)
               : "memory");
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-              ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])),
-              "r"(kb * GEMM_BK), "r"(tile_n * BN)
-              : "memory");
+          if constexpr (CM == 1) {
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])),
+                "r"(kb * GEMM_BK), "r"(tile_n * BN)
+                : "memory");
+          } else {   // my half of the W tile, multicast to the same stage offset (and full barrier) of both CTAs
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                "[%0], [%1, {%3, %4}], [%2], %5;"
+                ::"r"(sa + A_BYTES + crank * (B_BYTES / CM)), "l"(reinterpret_cast<uint64_t>(&tmB)),
+                "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK), "r"(tile_n * BN + crank * (BN / CM)),
+                "h"(static_cast<uint16_t>((1u << CM) - 1))
+                : "memory");
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -131,7 +161,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -143,7 +173,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
             umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CM == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CM) - 1));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[acc]);
@@ -156,8 +187,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t stage_buf = epi_base + (warp - 2) * 4096;   // one 32-row x 128-byte staging tile per warp
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+    for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
+      const int tile_m = CM * (tile / tiles_n) + crank, tile_n = tile % tiles_n;
       const int m0 = tile_m * GEMM_BM + q * 32;
       const int m = m0 + lane;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -280,6 +311,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) g2_cluster_sync();   // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 

@@ -160,15 +160,28 @@ static int mark_call_end(stz_handle* H, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 static int g_use_pdl = 1;
 template <typename... KArgs, typename... Args>
-static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+static void launch_kc(int cluster_x, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (g_use_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {   // runtime cluster shape (kernels without a compile-time __cluster_dims__)
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_kc(1, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -258,19 +271,30 @@ static int pick_bn(int M, int N) {
   return best;
 }
 
+static int g_gemm_cluster = 1;   // knob "gemm_cluster": 1 = pair CTAs (multicast W tile) when the problem is large enough
+
 template <int BN, int EPI>
 static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, const GemmParams& p) {
+  const int tiles_m = cdiv(p.M, GEMM_BM), tiles_n = p.N / BN;
+  // pairs pay off when the launch is L2-bandwidth-bound: more than one round of tiles over the SMs
+  const bool pair = g_gemm_cluster && g2_staged<EPI>() && tiles_m >= 2 && tiles_m * tiles_n > g_num_sms;
   CUtensorMap ta, tb, tc;
   memset(&tc, 0, sizeof tc);
   if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
-      make_tmap(&tb, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, BN))
+      make_tmap(&tb, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, pair ? BN / 2 : BN))
     return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", p.M, p.N, p.K);
   if (g2_staged<EPI>() && make_tmap_out(&tc, p.out, g2_out_bf16<EPI>(), (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo))
     return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (output) failed (M=%d N=%d ldo=%d)", p.M, p.N, p.ldo);
-  const int tiles = (p.N / BN) * cdiv(p.M, GEMM_BM);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * p.N * p.K);
-  launch_k(gemm2_kernel<BN, EPI>, grid, G2_THREADS, g2_smem_bytes<BN>(), st, ta, tb, tc, p);
+  if (pair) {
+    const int units = cdiv(tiles_m, 2) * tiles_n, max_clusters = g_num_sms / 2;
+    const int clusters = units < max_clusters ? units : max_clusters;
+    launch_kc(2, gemm2_kernel<BN, EPI, 2>, 2 * clusters, G2_THREADS, g2_smem_bytes<BN>(), st, ta, tb, tc, p);
+  } else {
+    const int tiles = tiles_m * tiles_n;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    launch_k(gemm2_kernel<BN, EPI, 1>, grid, G2_THREADS, g2_smem_bytes<BN>(), st, ta, tb, tc, p);
+  }
   if (H) { KCHECK(H); } else if (cudaGetLastError() != cudaSuccess) return STZ_E_CUDA;
   return 0;
 }
@@ -303,7 +327,9 @@ static int launch_gemmln(stz_handle* H, cudaStream_t st, const bf16* A, int lda,
 
 template <int BN, int EPI>
 static cudaError_t set_gemm2_attr() {
-  return cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
+  cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
+  if (e != cudaSuccess || !g2_staged<EPI>()) return e;
+  return cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
 }
 template <int EPI>
 static cudaError_t set_gemm2_attrs() {
@@ -730,10 +756,12 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     H->graphs.clear();
     H->fuse_ln = value;
   }
-  else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl")) {   // process-wide knobs baked into captured graphs
+  else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // process-wide knobs baked into captured graphs
     for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
     H->graphs.clear();
-    if (key[0] == 'g') g_bn_override = value; else g_use_pdl = value;
+    if (!strcmp(key, "gemm_bn")) g_bn_override = value;
+    else if (!strcmp(key, "use_pdl")) g_use_pdl = value;
+    else g_gemm_cluster = value;
   } else if (!strcmp(key, "profile")) {
     H->profile = value;
     for (auto& r : H->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -794,7 +822,7 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
   int n_keys = 0;
   for (int i = 0; i < ap.nseg; ++i) n_keys += ap.seg[i].n;
   ProfScope ps(H, st, PC_ATTN, 4.0 * B * H->cfg.n_heads * ap.n_q * (double)n_keys * ATT_DH);
-  launch_k(attention_kernel, grid, cdiv(ap.n_q, 16) * 32, ATT_SMEM_BYTES, st, ap);
+  launch_k(attention_kernel, grid, 2 * cdiv(ap.n_q / 2, 16) * 32, ATT_SMEM_BYTES, st, ap);   // ceil(K / 16) warps per CFG branch
   KCHECK(H);
   return 0;
 }
@@ -1180,4 +1208,61 @@ extern "C" int stz_op_gemm_bf16(const void* A, const void* W, const float* bias,
                        : launch_gemm_simt<EPI_F32>(nullptr, st, (const bf16*)A, K, (const bf16*)W, p);
   if (rc != 0 && g_create_error.empty()) g_create_error = "gemm launch failed";
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// bench.py roofline leg: one GEMM shape of the denoiser, `iters` back-to-back launches on the handle's
+// stream between two CUDA events (PDL-chained exactly like the evaluation loop), average microseconds.
+// epi: 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual (TMA reduce-add into an fp32 buffer).
+// ------------------------------------------------------------------------------------------
+extern "C" int stz_bench_gemm(stz_handle* H, int M, int N, int K, int epi, int iters, double* avg_us) {
+  if (!H || !avg_us || M < 1 || iters < 1) return STZ_E_ARG;
+  if (N % 128 || K % 64) return fail(H, STZ_E_SHAPE, "N %% 128, K %% 64 required");
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  cudaStream_t st = H->stream;
+  bf16 *A = nullptr, *W = nullptr, *Cb = nullptr;
+  float *Cf = nullptr, *bias = nullptr, *mod = nullptr;
+  const int rpu = 2 * H->cfg.n_style, n_seq = 2 * cdiv(M, rpu) + 2;
+  CK(H, cudaMalloc(&A, (size_t)(M + 128) * K * sizeof(bf16)));
+  CK(H, cudaMalloc(&W, (size_t)N * K * sizeof(bf16)));
+  CK(H, cudaMalloc(&Cb, (size_t)M * N * sizeof(bf16)));
+  CK(H, cudaMalloc(&Cf, (size_t)M * N * sizeof(float)));
+  CK(H, cudaMalloc(&bias, (size_t)N * sizeof(float)));
+  CK(H, cudaMalloc(&mod, (size_t)n_seq * N * sizeof(float)));
+  CK(H, cudaMemsetAsync(A, 0, (size_t)(M + 128) * K * sizeof(bf16), st));
+  CK(H, cudaMemsetAsync(W, 0, (size_t)N * K * sizeof(bf16), st));
+  CK(H, cudaMemsetAsync(Cf, 0, (size_t)M * N * sizeof(float), st));
+  CK(H, cudaMemsetAsync(bias, 0, (size_t)N * sizeof(float), st));
+  CK(H, cudaMemsetAsync(mod, 0, (size_t)n_seq * N * sizeof(float), st));
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.ldo = N; p.mod = mod; p.n_mod = N; p.gate_off = 0; p.rows_per_utt = rpu;
+  p.n_style = H->cfg.n_style;
+  auto once = [&]() -> int {
+    switch (epi) {
+      case 2: p.out = Cb; return gemm<EPI_BF16>(H, st, 0, A, K, M, W, p);
+      case 3: p.out = Cb; return gemm<EPI_GELU_BF16>(H, st, 0, A, K, M, W, p);
+      case 4: p.out = Cf; return gemm<EPI_GATE_RES>(H, st, 0, A, K, M, W, p);
+      default: return fail(H, STZ_E_ARG, "epi %d not benchable", epi);
+    }
+  };
+  const int saved_profile = H->profile;
+  H->profile = 0;
+  int rc = 0;
+  for (int i = 0; i < 3 && rc == 0; ++i) rc = once();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters && rc == 0; ++i) rc = once();
+  cudaEventRecord(e1, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(A); cudaFree(W); cudaFree(Cb); cudaFree(Cf); cudaFree(bias); cudaFree(mod);
+  H->profile = saved_profile;
+  H->cur_launches = 0;
+  if (rc != 0) return rc;
+  if (ce != cudaSuccess) return fail(H, STZ_E_CUDA, "bench gemm -> %s", cudaGetErrorString(ce));
+  *avg_us = (double)ms * 1e3 / iters;
+  return 0;
 }

@@ -74,6 +74,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.stz_profile_read.restype = i32
     lib.stz_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.stz_bench_gemm.restype = i32
+    lib.stz_bench_gemm.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_double)]
     lib.stz_debug_max_lstm_clusters.restype = i32
     lib.stz_debug_max_lstm_clusters.argtypes = []
     lib.stz_debug_set_tap.restype = i32
@@ -90,7 +92,7 @@ def load_library(path: Optional[str] = None):
 EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
                     "stz_synthesize_host", "stz_launch_count", "stz_set_option", "stz_profile_read",
-                    "stz_debug_set_tap", "stz_debug_max_lstm_clusters",
+                    "stz_debug_set_tap", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16")
 
 
@@ -164,6 +166,12 @@ class StyleTTSZSPath:
             self._check(self.lib.stz_profile_read(self._h, i, C.byref(ms), C.byref(work), C.byref(n)), "profile_read")
             out[name] = (ms.value, work.value, n.value)
         return out
+
+    def bench_gemm(self, M: int, N: int, K: int, epi: int, iters: int = 50) -> float:
+        """Mean microseconds per launch of the product GEMM kernel for one shape (back-to-back launches)."""
+        us = C.c_double()
+        self._check(self.lib.stz_bench_gemm(self._h, M, N, K, epi, iters, C.byref(us)), "stz_bench_gemm")
+        return us.value
 
     def set_tap(self, ev: int, layer: int, stage: int, buf: Optional[torch.Tensor]):
         self._check(self.lib.stz_debug_set_tap(self._h, ev, layer, stage, _ptr(buf)), "set_tap")
