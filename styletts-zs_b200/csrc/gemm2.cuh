@@ -58,13 +58,12 @@ constexpr bool g2_staged() { return EPI == EPI_F32 || EPI == EPI_BF16 || EPI == 
 template <int EPI>
 constexpr bool g2_out_bf16() { return EPI == EPI_BF16 || EPI == EPI_GELU_BF16; }
 
-// CM = 2: launched as clusters of two CTAs that own vertically adjacent tiles (same n-tile).  Each CTA fetches
-// half of the shared W tile and TMA-multicasts it into both CTAs' stages (L2 -> SM weight traffic halves); a smem
-// stage is recycled only when the MMA warps of BOTH CTAs have consumed it (multicast tcgen05.commit).
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
+// CM = 2 — CTA pair (tcgen05 cta_group::2): a cluster of two CTAs computes one 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and HALF of the W tile (BN/2 rows), so shared-memory traffic per SM per MMA drops from
+// (128 + BN) to (128 + BN/2) operand rows — the single-CTA kernel is bound by shared-memory bandwidth (operand reads
+// by the tensor core + TMA writes + epilogue staging > 128 B/clk).  The leader CTA (rank 0) issues
+// tcgen05.mma.cta_group::2 (M = 256) for the pair; both CTAs' TMA loads signal the leader's full barrier; stages and
+// accumulators are handed back with multicast tcgen05.commit; each CTA drains its own 128 TMEM lanes.
 __device__ __forceinline__ uint32_t g2_cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -73,15 +72,61 @@ __device__ __forceinline__ uint32_t g2_cluster_rank() {
 __device__ __forceinline__ void g2_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t g2_mapa(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void g2_remote_arrive(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread completed) on the same barrier offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+// TMA load into this CTA's shared memory whose completion bytes are posted on a barrier of the pair's leader
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const void* tmap, uint32_t cluster_bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <int BN, int CM>
+constexpr int g2_stage_bytes() { return GEMM_BM * GEMM_BK * 2 + (BN / CM) * GEMM_BK * 2; }
+template <int BN, int CM>
+constexpr int g2_stages_cm() { return CM == 1 ? g2_stages<BN>() : (BN == 128 ? 8 : 6); }
+template <int BN, int CM>
+constexpr int g2_smem_bytes_cm() { return g2_stages_cm<BN, CM>() * g2_stage_bytes<BN, CM>() + G2_STAGE_BYTES_EPI + 1024; }
 
 template <int BN, int EPI, int CM = 1>
 __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmC,
                                                               const GemmParams p) {
-  constexpr int STAGES = g2_stages<BN>();
+  constexpr int STAGES = g2_stages_cm<BN, CM>();
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr int B_BYTES = (BN / CM) * GEMM_BK * 2;        // this CTA's share of the W tile
   constexpr int TMEM_COLS = g2_tmem_cols<BN>();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -95,9 +140,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.K / GEMM_BK;
   const int tiles_n = p.N / BN;
-  // work units: CM vertically adjacent tiles x one n-tile; unit u -> tile_m = CM * (u / tiles_n) + rank, tile_n = u % tiles_n
+  // work units: (CM * 128) rows x BN columns; unit u -> rows of this CTA: tile_m = CM * (u / tiles_n) + rank
   const int n_tiles = tiles_n * (((p.M + GEMM_BM - 1) / GEMM_BM + CM - 1) / CM);
   const int crank = CM > 1 ? static_cast<int>(g2_cluster_rank()) : 0;
+  const bool leader = crank == 0;
   const int unit0 = blockIdx.x / CM, unit_stride = gridDim.x / CM;
 
   if (warp == 0 && lane == 0) {
@@ -105,21 +151,24 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     prefetch_tmap(&tmB);
     if (g2_staged<EPI>()) prefetch_tmap(&tmC);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CM);
+      mbar_init(&full_bar[s], 1);           // pair: the leader arms the bytes of BOTH CTAs; the peer's TMA posts its bytes remotely
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], 8 * CM);    // 8 epilogue warps per CTA
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_slot);
+  if (warp == 1) {
+    if constexpr (CM == 1) tmem_alloc<TMEM_COLS>(&tmem_slot);
+    else tmem_alloc2<TMEM_COLS>(&tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if constexpr (CM > 1) g2_cluster_sync();   // peer barriers are initialised before any multicast / remote arrive
+  if constexpr (CM > 1) g2_cluster_sync();   // peer barriers are initialised before any remote arrive / commit
   pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
@@ -130,35 +179,32 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         const int tile_m = CM * (tile / tiles_n) + crank, tile_n = tile % tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-              ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK),
-              "r"(p.a_row0 + tile_m * GEMM_BM)
-              : "memory");
           if constexpr (CM == 1) {
+            mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK),
+                "r"(p.a_row0 + tile_m * GEMM_BM)
+                : "memory");
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                 ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])),
                 "r"(kb * GEMM_BK), "r"(tile_n * BN)
                 : "memory");
-          } else {   // my half of the W tile, multicast to the same stage offset (and full barrier) of both CTAs
-            asm volatile(
-                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-                "[%0], [%1, {%3, %4}], [%2], %5;"
-                ::"r"(sa + A_BYTES + crank * (B_BYTES / CM)), "l"(reinterpret_cast<uint64_t>(&tmB)),
-                "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK), "r"(tile_n * BN + crank * (BN / CM)),
-                "h"(static_cast<uint16_t>((1u << CM) - 1))
-                : "memory");
+          } else {
+            const uint32_t lead_full = g2_mapa(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2cta(sa, &tmA, lead_full, kb * GEMM_BK, p.a_row0 + tile_m * GEMM_BM);
+            tma_load_2d_2cta(sa + A_BYTES, &tmB, lead_full, kb * GEMM_BK, tile_n * BN + crank * (BN / CM));
+            if (leader) mbar_expect_tx(&full_bar[stage], CM * (A_BYTES + B_BYTES));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CM, BN);
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
@@ -171,13 +217,16 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if constexpr (CM == 1) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           if constexpr (CM == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CM) - 1));
+          else umma_commit_2cta(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);
+        if constexpr (CM == 1) umma_commit(&tmem_full[acc]);
+        else umma_commit_2cta(&tmem_full[acc]);
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -233,7 +282,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
             if (c + 2 >= NCH && sub == SUB - 1) {  // this warp's last read of the accumulator: hand it back
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+              if (lane == 0) { if (CM == 1 || leader) mbar_arrive(&tmem_empty[acc]); else g2_remote_arrive(g2_mapa(smem_u32(&tmem_empty[acc]), 0)); }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -282,7 +331,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         }
         if (half >= NCH) {  // (never with NCH >= 2; keeps the barrier count right for any tile shape)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) { if (CM == 1 || leader) mbar_arrive(&tmem_empty[acc]); else g2_remote_arrive(g2_mapa(smem_u32(&tmem_empty[acc]), 0)); }
         }
       } else {
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -296,7 +345,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           if (c + 2 >= NCH) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) { if (CM == 1 || leader) mbar_arrive(&tmem_empty[acc]); else g2_remote_arrive(g2_mapa(smem_u32(&tmem_empty[acc]), 0)); }
           }
           float v[32];
 #pragma unroll
@@ -311,8 +360,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CM > 1) g2_cluster_sync();   // the peer may still multicast into / arrive on this CTA's shared memory
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if constexpr (CM > 1) g2_cluster_sync();   // the peer may still arrive on this CTA's barriers / read its operand stages
+  if (warp == 1) {
+    if constexpr (CM == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+    else tmem_dealloc2<TMEM_COLS>(tmem_base);
+  }
 }
 
 }  // namespace stz

@@ -271,12 +271,13 @@ static int pick_bn(int M, int N) {
   return best;
 }
 
-static int g_gemm_cluster = 1;   // knob "gemm_cluster": 1 = pair CTAs (multicast W tile) when the problem is large enough
+static int g_gemm_cluster = 0;   // knob "gemm_cluster": 1 = CTA pairs (cta_group::2, 256 x BN tiles); measured on par with single-CTA tiles at these sizes, off by default
 
 template <int BN, int EPI>
 static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, const GemmParams& p) {
   const int tiles_m = cdiv(p.M, GEMM_BM), tiles_n = p.N / BN;
-  // pairs pay off when the launch is L2-bandwidth-bound: more than one round of tiles over the SMs
+  // CTA pairs (cta_group::2, 256 x BN tiles) relieve the shared-memory bandwidth bound of the single-CTA kernel;
+  // used when there is at least one full round of pair tiles
   const bool pair = g_gemm_cluster && g2_staged<EPI>() && tiles_m >= 2 && tiles_m * tiles_n > g_num_sms;
   CUtensorMap ta, tb, tc;
   memset(&tc, 0, sizeof tc);
@@ -289,7 +290,7 @@ static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int ld
   if (pair) {
     const int units = cdiv(tiles_m, 2) * tiles_n, max_clusters = g_num_sms / 2;
     const int clusters = units < max_clusters ? units : max_clusters;
-    launch_kc(2, gemm2_kernel<BN, EPI, 2>, 2 * clusters, G2_THREADS, g2_smem_bytes<BN>(), st, ta, tb, tc, p);
+    launch_kc(2, gemm2_kernel<BN, EPI, 2>, 2 * clusters, G2_THREADS, g2_smem_bytes_cm<BN, 2>(), st, ta, tb, tc, p);
   } else {
     const int tiles = tiles_m * tiles_n;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
@@ -329,7 +330,7 @@ template <int BN, int EPI>
 static cudaError_t set_gemm2_attr() {
   cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
   if (e != cudaSuccess || !g2_staged<EPI>()) return e;
-  return cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
+  return cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes_cm<BN, 2>());
 }
 template <int EPI>
 static cudaError_t set_gemm2_attrs() {

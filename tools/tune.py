@@ -28,13 +28,13 @@ z = path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=de
 samp = lambda: path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=dev["noise"])
 pred = lambda: path.predict_duration(dev["text_emb"], z)
 res = {}
-for knobs in [{}, {"gemm_cluster": 0}, {"use_pdl": 0}]:
+for knobs in [{}, {"gemm_cluster": 1}, {"use_pdl": 0}]:
     for k, v in knobs.items():
         path.set_option(k, v)
     res[json.dumps(knobs)] = (round(timeit(samp), 3), round(timeit(pred), 3))
     print(knobs, "sample_style ms", res[json.dumps(knobs)][0], "predict_duration ms", res[json.dumps(knobs)][1], flush=True)
     for k in knobs:
-        path.set_option(k, {"gemm_bn": 0, "use_pdl": 1, "use_graph": 1, "fuse_ln": 0, "gemm_cluster": 1}[k])
+        path.set_option(k, {"gemm_bn": 0, "use_pdl": 1, "use_graph": 1, "fuse_ln": 0, "gemm_cluster": 0}[k])
 for name, N, K, epi in [("qkv", 1536, 512, 2), ("attn_out", 512, 512, 4), ("q_cross", 512, 512, 2), ("ffn1", 2048, 512, 3), ("ffn2", 512, 2048, 4)]:
     R = 2 * B * cfg.n_style
     out = {}
@@ -42,5 +42,5 @@ for name, N, K, epi in [("qkv", 1536, 512, 2), ("attn_out", 512, 512, 4), ("q_cr
         path.set_option("gemm_cluster", cl)
         us = path.bench_gemm(R, N, K, epi, 50)
         out[cl] = (round(us, 2), round(2.0 * R * N * K / us * 1e-6, 1))
-    path.set_option("gemm_cluster", 1)
+    path.set_option("gemm_cluster", 0)
     print(name, "M", R, "N", N, "K", K, "cluster:", out[1], "no cluster:", out[0], "(us, TFLOP/s)", flush=True)
