@@ -79,6 +79,7 @@ struct stz_handle {
   bool has_last = false;
   std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
   int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 0;
+  int ablate = 0;   // tools/ablate.py: bit mask of kernel families skipped inside run_eval (timing attribution only; results are wrong)
   int64_t launches = 0;
   int cur_launches = 0;  // launches issued since the counter was last sampled (capture bookkeeping)
   int tap_eval = -1, tap_layer = -1, tap_stage = -1;
@@ -752,10 +753,10 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
-  else if (!strcmp(key, "fuse_ln")) {
+  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate")) {
     for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
     H->graphs.clear();
-    H->fuse_ln = value;
+    if (!strcmp(key, "ablate")) H->ablate = value; else H->fuse_ln = value;
   }
   else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // process-wide knobs baked into captured graphs
     for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
@@ -837,8 +838,10 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)(d / c.n_heads));
   GemmParams base{};
   base.mod = w.mod; base.n_mod = n_mod; base.rows_per_utt = 2 * K; base.n_style = K;
+  // ablation bits: 1 self-attn, 2 cross-attn, 4 ln_mod, 8 qkv, 16 attention out-projections, 32 q2, 64 ff1, 128 ff2, 256 mod
+  const int ab = H->ablate;
 
-  {  // AdaLN modulations of this eval: mod[NS, n_mod] = c[e] · Wmod^T + b
+  if (!(ab & 256)) {  // AdaLN modulations of this eval: mod[NS, n_mod] = c[e] · Wmod^T + b
     GemmParams p = base;
     p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * NS; p.bias = W32(H, "mod.b"); p.out = w.mod; p.ldo = n_mod;
     RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
@@ -855,7 +858,8 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
     }
     GemmParams p = base;
     p.M = R; p.N = d; p.K = Kc; p.bias = bias; p.out = w.h; p.ldo = d; p.gate_off = gate_off;
-    RET(gemm<EPI_GATE_RES>(H, st, impl, A, Kc, R, Wt, p));
+    if (!(ab & (Kc == d ? 16 : 128))) RET(gemm<EPI_GATE_RES>(H, st, impl, A, Kc, R, Wt, p));
+    if (ab & 4) return 0;
     return ln_mod(H, st, w.h, R, d, w.mod, n_mod, ln_off, ln_off + d, 2 * K, last ? w.u3 : w.u, last ? 1 : 0);
   };
   {  // h = x_in · Win^T + b + pos, u = AdaLN_1 of layer 0
@@ -874,12 +878,12 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
     const std::string pf = "l" + std::to_string(l) + ".";
     const int mo = 9 * l * d;
     // --- self-attention (u holds AdaLN_1(h))
-    {
+    if (!(ab & 8)) {
       GemmParams p = base;
       p.M = R; p.N = 3 * d; p.K = d; p.bias = W32(H, pf + "qkv.b"); p.out = w.qkv; p.ldo = 3 * d;
       RET(gemm<EPI_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "qkv.w"), p));
     }
-    {
+    if (!(ab & 1)) {
       AttnParams ap{};
       ap.q = w.qkv; ap.ldq = 3 * d; ap.out = w.att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 1; ap.scale_log2 = scale_log2;
       ap.seg[0] = AttnSeg{w.qkv + d, w.qkv + 2 * d, 3 * d, 2 * K, 2 * K, nullptr, KEY_SAME_BRANCH};
@@ -888,12 +892,12 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
     RET(res_ln(w.att, d, WBF(H, pf + "o.w"), W32(H, pf + "o.b"), mo + 2 * d, mo + 3 * d, false));
     RET(tap(H, st, e, l, 0, R));
     // --- cross-attention over [text ; prompt | null]  (u holds AdaLN_2(h))
-    {
+    if (!(ab & 32)) {
       GemmParams p = base;
       p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "q2.b"); p.out = w.qkv; p.ldo = d;
       RET(gemm<EPI_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "q2.w"), p));
     }
-    {
+    if (!(ab & 2)) {
       AttnParams ap{};
       const int ldkv = L * 2 * d;
       ap.q = w.qkv; ap.ldq = d; ap.out = w.att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 3; ap.scale_log2 = scale_log2;
@@ -905,7 +909,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
     RET(res_ln(w.att, d, WBF(H, pf + "o2.w"), W32(H, pf + "o2.b"), mo + 5 * d, mo + 6 * d, false));
     RET(tap(H, st, e, l, 1, R));
     // --- FFN  (u holds AdaLN_3(h)); its residual GEMM also produces AdaLN_1 of the next layer / the final AdaLN
-    {
+    if (!(ab & 64)) {
       GemmParams p = base;
       p.M = R; p.N = c.d_ff; p.K = d; p.bias = W32(H, pf + "ff1.b"); p.out = w.ffh; p.ldo = c.d_ff;
       RET(gemm<EPI_GELU_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "ff1.w"), p));
