@@ -45,6 +45,63 @@ __global__ void __launch_bounds__(256) style_pool_attn_kernel(const float* __res
   }
 }
 
+// a-8, product kernel: one CTA = SP_TOK consecutive tokens of one utterance; the utterance's projected K / V
+// (K x ds fp32 each) are staged in shared memory once, then a warp handles one token at a time:
+//   scores  : lane = key (keys j and j + 32), q broadcast by shuffle, K rows padded to ds + 1 (conflict-free);
+//   softmax : two warp reductions per (token, head) instead of one per key;
+//   output  : lane = channel, p_j broadcast by shuffle, V rows read conflict-free.
+constexpr int SP_TOK = 16;
+__global__ void __launch_bounds__(256) style_pool_attn2_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                               const float* __restrict__ v, int ldkv, float* __restrict__ out,
+                                                               int T, int K, int ds, float scale) {
+  extern __shared__ float sp_smem[];
+  float* Ks = sp_smem;                  // [K][ds + 1]
+  float* Vs = sp_smem + ((K * (ds + 1) + 3) & ~3);   // [K][ds], 16-byte aligned
+  pdl_sync();
+  const int b = blockIdx.y, t0 = blockIdx.x * SP_TOK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < K * (ds >> 2); i += blockDim.x) {
+    const int j = i / (ds >> 2), c = (i % (ds >> 2)) * 4;
+    const size_t r = (static_cast<size_t>(b) * K + j) * ldkv + c;
+    const float4 kk = __ldg(reinterpret_cast<const float4*>(k + r)), vv = __ldg(reinterpret_cast<const float4*>(v + r));
+    float* kd = Ks + j * (ds + 1) + c;
+    kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+    *reinterpret_cast<float4*>(Vs + j * ds + c) = vv;
+  }
+  __syncthreads();
+  const int nh = ds >> 5;
+  const int j0 = lane < K ? lane : K - 1, j1 = lane + 32 < K ? lane + 32 : K - 1;
+  for (int tt = warp; tt < SP_TOK && t0 + tt < T; tt += blockDim.x >> 5) {
+    const size_t tok = static_cast<size_t>(b) * T + t0 + tt;
+    for (int h = 0; h < nh; ++h) {
+      const float qv = q[tok * ds + h * 32 + lane] * scale;
+      const float* k0 = Ks + j0 * (ds + 1) + h * 32;
+      const float* k1 = Ks + j1 * (ds + 1) + h * 32;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float qc = __shfl_sync(0xffffffffu, qv, c);
+        s0 = fmaf(qc, k0[c], s0);
+        s1 = fmaf(qc, k1[c], s1);
+      }
+      if (lane >= K) s0 = -INFINITY;
+      if (lane + 32 >= K) s1 = -INFINITY;
+      float m = fmaxf(s0, s1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float p0 = expf(s0 - m), p1 = expf(s1 - m);   // exp(-inf) = 0 for the slots past K
+      const float l = warp_sum(p0 + p1);
+      float acc = 0.f;
+      const float* vc = Vs + h * 32 + lane;
+      for (int j = 0; j < K; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
+        acc = fmaf(pj, vc[j * ds], acc);
+      }
+      out[tok * ds + h * 32 + lane] = acc / l;
+    }
+  }
+}
+
 // a-9: one direction of one BiLSTM layer for a chunk of NB sequences (packed-sequence semantics:
 // the reverse direction starts at each sequence's own last valid token; padded outputs are 0).
 //   G    [B*T, 8h]   W_ih·[x, s_tok] + b_ih + b_hh for both directions, column = dir*4h + gate*h + unit
@@ -230,6 +287,70 @@ __global__ void __launch_bounds__(256) dur_head_kernel(const float* __restrict__
   }
 }
 
+
+// a-10, product kernel: one CTA = 32 tokens staged in shared memory; warp w evaluates logits w, w + 8, ... against
+// all 32 tokens (the logit's weight row lives in registers: W is read once per CTA, not once per token), the 32
+// per-token dot products of a logit are reduced together with a 31-shuffle transpose reduction (lane r ends up
+// with token r), and the per-warp sigmoid sums are combined in a fixed order (deterministic).
+template <int VPL>
+__global__ void __launch_bounds__(256) dur_head2_kernel(const float* __restrict__ x, const float* __restrict__ Wd,
+                                                        const float* __restrict__ bd, const uint8_t* __restrict__ mask,
+                                                        int32_t* __restrict__ dur, float* __restrict__ presum, int rows,
+                                                        int max_dur) {
+  constexpr int D = 128 * VPL;
+  extern __shared__ __align__(16) float dh_smem[];
+  float4* xs = reinterpret_cast<float4*>(dh_smem);                 // [32][D / 4]
+  float* part = dh_smem + 32 * D;                                   // [8][32]
+  pdl_sync();
+  const int row0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 32 * (D >> 2); i += blockDim.x) {
+    const int r = i / (D >> 2);
+    xs[i] = row0 + r < rows ? __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(row0) * D) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  float total = 0.f;   // lane r: sum over this warp's logits of sigmoid(logit) for token r
+  for (int j = warp; j < max_dur; j += 8) {
+    float4 w[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(Wd + static_cast<size_t>(j) * D) + i * 32 + lane);
+    float d[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const float4 xv = xs[r * (D >> 2) + i * 32 + lane];
+        a = fmaf(xv.x, w[i].x, fmaf(xv.y, w[i].y, fmaf(xv.z, w[i].z, fmaf(xv.w, w[i].w, a))));
+      }
+      d[r] = a;
+    }
+    // transpose reduction: after the step with offset o, lane keeps the rows whose bit o equals its own bit o
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int r = 0; r < o; ++r) {
+        const float keep = up ? d[r + o] : d[r], give = up ? d[r] : d[r + o];
+        d[r] = keep + __shfl_xor_sync(0xffffffffu, give, o);
+      }
+    }
+    total += sigmoidf_(d[0] + __ldg(bd + j));   // d[0] now holds the full dot product of token `lane`
+  }
+  part[warp * 32 + lane] = total;
+  __syncthreads();
+  if (warp == 0) {
+    const int row = row0 + lane;
+    if (row < rows) {
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += part[w8 * 32 + lane];
+      const bool ok = mask == nullptr || mask[row] != 0;
+      if (presum != nullptr) presum[row] = t;
+      dur[row] = ok ? static_cast<int32_t>(fmaxf(rintf(t), 1.0f)) : 0;
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // a-9, product path: persistent thread-block-cluster BiLSTM recurrence (h = 256).

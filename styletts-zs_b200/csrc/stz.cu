@@ -62,6 +62,8 @@ struct stz_handle {
   bf16* wbf = nullptr;    // the same blob rounded to bf16 (same offsets): tensor-core operands
   float *ctx_text_b = nullptr, *ctx_prompt_b = nullptr;  // bias + type embedding
   bf16* kv_null = nullptr;                               // [1, L*2d] K/V of the null-prompt token
+  bf16* wkv_all = nullptr;                               // [L*2d, d] every layer's context K/V projection, stacked (one GEMM per call)
+  float* bkv_all = nullptr;                              // [L*2d]
   bf16 *w_in3 = nullptr, *w_out3 = nullptr;              // split-bf16 [hi | hi | lo] input / output projection weights
   float* whhT = nullptr;                                 // [n_lstm][2][h][4h]  (k-major: generic kernel)
   float* whh = nullptr;                                  // [n_lstm][2][4h][h]  (row-major: cluster kernel)
@@ -73,6 +75,11 @@ struct stz_handle {
   float* b_kv = nullptr;
   Workspace ws;
   cudaStream_t stream = nullptr;      // internal stream (create-time work, host entry point, capture)
+  // host entry point: prompt / noise H2D and the style D2H run on a second stream, overlapping the text-side
+  // conditioning prep and the duration predictor
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_prompt = nullptr, ev_noise = nullptr, ev_style = nullptr;
+  bool wait_prompt = false, wait_noise = false;
   // calls share one workspace: a call enqueued on a different stream than the previous one first waits for it
   cudaStream_t last_stream = nullptr;
   cudaEvent_t last_ev = nullptr;
@@ -341,6 +348,8 @@ static cudaError_t set_gemm2_attrs() {
   return set_gemm2_attr<128, EPI>();
 }
 
+static constexpr int dur_head2_smem(int vpl) { return (32 * 128 * vpl + 8 * 32) * 4; }
+
 template <int EPI>
 static cudaError_t set_gemm_attr() {
   return cudaFuncSetAttribute(gemm_tc_kernel<GEMM_BN, EPI, GEMM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -368,6 +377,10 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<10>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<16>())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(style_pool_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (2 * 256 + 1) + 4) * 4)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dur_head2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(1))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dur_head2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(2))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dur_head2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(4))) != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     g_num_sms = sms;
@@ -465,12 +478,14 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   auto want = [&](void** p, size_t bytes) { plan.push_back({p, off}); off = align_up(off + bytes, 1024); };
 #define WANT(field, count, type) want((void**)&w.field, (size_t)(count) * sizeof(type))
   WANT(text_bf, BT * c.d_text, bf16); WANT(prompt_bf, BP * c.d_prompt, bf16);
-  WANT(ctx_text, BT * d, bf16); WANT(ctx_prompt, BP * d, bf16);
-  WANT(kv_text, BT * L * 2 * d, bf16); WANT(kv_prompt, BP * L * 2 * d, bf16);
+  // context tokens [text rows ; prompt rows] and their per-layer K/V are contiguous (one LN, one K/V GEMM per call);
+  // ctx_prompt / kv_prompt are derived per call from the actual B*T (sample_style_impl)
+  WANT(ctx_text, (BT + BP + 128) * d, bf16);
+  WANT(kv_text, (BT + BP) * L * 2 * d, bf16);
   WANT(cvec, (size_t)E * NS * d + 128 * d, bf16);  // + one tile of slack rows for the last eval's TMA box
   WANT(pool_text, (size_t)B * c.d_text, float); WANT(pool_prompt, (size_t)B * c.d_prompt, float);
   WANT(pt, (size_t)B * d, float); WANT(pp, (size_t)B * d, float);
-  WANT(ctx_pre, (BT > BP ? BT : BP) * d, float);
+  WANT(ctx_pre, (BT + BP) * d, float);
   WANT(tfeat, (size_t)E * c.d_time, float); WANT(t1, (size_t)E * d, float); WANT(temb, (size_t)E * d, float);
   WANT(coef, (size_t)E * 8, float);
   WANT(mod, NS * n_mod, float); WANT(x, BK * Ds, float); WANT(xmid, BK * Ds, float); WANT(h, R * d, float);
@@ -603,6 +618,11 @@ extern "C" void stz_destroy(stz_handle* H) {
   for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
   cudaFree(H->ws.base); cudaFree(H->w32); cudaFree(H->wbf); cudaFree(H->ctx_text_b); cudaFree(H->ctx_prompt_b);
   cudaFree(H->wq3); cudaFree(H->wkv3); cudaFree(H->wo3); cudaFree(H->wih3); cudaFree(H->wada3); cudaFree(H->b_kv);
+  cudaFree(H->wkv_all); cudaFree(H->bkv_all);
+  if (H->ev_prompt) cudaEventDestroy(H->ev_prompt);
+  if (H->ev_noise) cudaEventDestroy(H->ev_noise);
+  if (H->ev_style) cudaEventDestroy(H->ev_style);
+  if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
   cudaFree(H->kv_null); cudaFree(H->w_in3); cudaFree(H->w_out3); cudaFree(H->whhT); cudaFree(H->whh); cudaFree(H->lstm_b);
   if (H->last_ev) cudaEventDestroy(H->last_ev);
   if (H->stream) cudaStreamDestroy(H->stream);
@@ -623,6 +643,10 @@ static int create_impl(stz_handle* H, const float* weights_host) {
   const int d = c.d_model, L = c.n_layers, h = c.d_hid / 2;
   CK(H, cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
   CK(H, cudaEventCreateWithFlags(&H->last_ev, cudaEventDisableTiming));
+  CK(H, cudaStreamCreateWithFlags(&H->copy_stream, cudaStreamNonBlocking));
+  CK(H, cudaEventCreateWithFlags(&H->ev_prompt, cudaEventDisableTiming));
+  CK(H, cudaEventCreateWithFlags(&H->ev_noise, cudaEventDisableTiming));
+  CK(H, cudaEventCreateWithFlags(&H->ev_style, cudaEventDisableTiming));
   CK(H, init_kernel_attrs());
   cudaStream_t st = H->stream;
   CK(H, cudaMalloc(&H->w32, H->n_floats * sizeof(float)));
@@ -648,8 +672,12 @@ static int create_impl(stz_handle* H, const float* weights_host) {
   CK(H, cudaMalloc(&H->kv_null, (size_t)L * 2 * d * sizeof(bf16)));
   add_vec_kernel<<<1, 256, 0, st>>>(W32(H, "null_tok"), W32(H, "type_emb") + d, tmp, d, d); KCHECK(H);
   RET(ln_mod(H, st, tmp, 1, d, nullptr, 0, 0, 0, 1, nullc));
+  CK(H, cudaMalloc(&H->wkv_all, (size_t)L * 2 * d * d * sizeof(bf16)));
+  CK(H, cudaMalloc(&H->bkv_all, (size_t)L * 2 * d * sizeof(float)));
   for (int l = 0; l < L; ++l) {
     const std::string p = "l" + std::to_string(l) + ".kv2.";
+    CK(H, cudaMemcpyAsync(H->wkv_all + (size_t)l * 2 * d * d, WBF(H, p + "w"), (size_t)2 * d * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+    CK(H, cudaMemcpyAsync(H->bkv_all + (size_t)l * 2 * d, W32(H, p + "b"), (size_t)2 * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GemmParams gp{};
     gp.M = 1; gp.N = 2 * d; gp.K = d; gp.bias = W32(H, p + "b"); gp.out = H->kv_null + (size_t)l * 2 * d; gp.ldo = L * 2 * d;
     RET(gemm<EPI_BF16>(H, st, 1, nullc, d, 128, WBF(H, p + "w"), gp));  // M = 1: CUDA-core kernel, create time only
@@ -952,29 +980,36 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   CK(H, cudaMemcpyAsync(w.tfeat, pl.tfeat.data(), pl.tfeat.size() * sizeof(float), cudaMemcpyHostToDevice, st));
 
   // ---- conditioning prep (a-3): once per call ---------------------------------------------
+  // text side first: with the host entry point the prompt / noise H2D copies are still in flight on the copy stream
+  w.ctx_prompt = w.ctx_text + (size_t)B * T * d;
+  w.kv_prompt = w.kv_text + (size_t)B * T * L * 2 * d;
+  const int rows_all = B * (T + P);
   launch_k(cast_pool_kernel, dim3(B, c.d_text / 128), 256, 0, st, text, tmask, w.text_bf, w.pool_text, T, c.d_text); KCHECK(H);
-  launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "ptext.w"), W32(H, "ptext.b"), w.pt, d, B, d));
-  RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
   RET(linear_f32(H, st, ACT_SILU, w.tfeat, c.d_time, c.d_time, nullptr, 0, 0, W32(H, "time.w1"), W32(H, "time.b1"), w.t1, d, E, d));
   RET(linear_f32(H, st, ACT_NONE, w.t1, d, d, nullptr, 0, 0, W32(H, "time.w2"), W32(H, "time.b2"), w.temb, d, E, d));
-  launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
-  for (int which = 0; which < 2; ++which) {  // context tokens and their per-layer K/V
-    const int rows = which == 0 ? B * T : B * P, din = which == 0 ? c.d_text : c.d_prompt;
-    const bf16* src = which == 0 ? w.text_bf : w.prompt_bf;
-    bf16* ctx = which == 0 ? w.ctx_text : w.ctx_prompt;
-    bf16* kv = which == 0 ? w.kv_text : w.kv_prompt;
+  {
     GemmParams p{};
-    p.M = rows; p.N = d; p.K = din; p.bias = which == 0 ? H->ctx_text_b : H->ctx_prompt_b; p.out = w.ctx_pre; p.ldo = d;
-    RET(gemm<EPI_F32>(H, st, impl, src, din, rows, WBF(H, which == 0 ? "ctx_text.w" : "ctx_prompt.w"), p));
-    RET(ln_mod(H, st, w.ctx_pre, rows, d, nullptr, 0, 0, 0, 1, ctx));
-    for (int l = 0; l < L; ++l) {
-      const std::string pf = "l" + std::to_string(l) + ".kv2.";
-      GemmParams q{};
-      q.M = rows; q.N = 2 * d; q.K = d; q.bias = W32(H, pf + "b"); q.out = kv + (size_t)l * 2 * d; q.ldo = L * 2 * d;
-      RET(gemm<EPI_BF16>(H, st, impl, ctx, d, rows, WBF(H, pf + "w"), q));
-    }
+    p.M = B * T; p.N = d; p.K = c.d_text; p.bias = H->ctx_text_b; p.out = w.ctx_pre; p.ldo = d;
+    RET(gemm<EPI_F32>(H, st, impl, w.text_bf, c.d_text, B * T, WBF(H, "ctx_text.w"), p));
   }
+  if (H->wait_prompt) { CK(H, cudaStreamWaitEvent(st, H->ev_prompt, 0)); H->wait_prompt = false; }
+  launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
+  RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
+  launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
+  {
+    GemmParams p{};
+    p.M = B * P; p.N = d; p.K = c.d_prompt; p.bias = H->ctx_prompt_b; p.out = w.ctx_pre + (size_t)B * T * d; p.ldo = d;
+    RET(gemm<EPI_F32>(H, st, impl, w.prompt_bf, c.d_prompt, B * P, WBF(H, "ctx_prompt.w"), p));
+  }
+  // context tokens [text ; prompt]: one LayerNorm, then every layer's K/V in ONE GEMM (N = L * 2d)
+  RET(ln_mod(H, st, w.ctx_pre, rows_all, d, nullptr, 0, 0, 0, 1, w.ctx_text));
+  {
+    GemmParams q{};
+    q.M = rows_all; q.N = L * 2 * d; q.K = d; q.bias = H->bkv_all; q.out = w.kv_text; q.ldo = L * 2 * d;
+    RET(gemm<EPI_BF16>(H, st, impl, w.ctx_text, d, rows_all, H->wkv_all, q));
+  }
+  if (H->wait_noise) { CK(H, cudaStreamWaitEvent(st, H->ev_noise, 0)); H->wait_noise = false; }
   // ---- sampler state --------------------------------------------------------------------
   launch_k(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0); KCHECK(H);
   if (kind == STZ_SAMPLER_TEACHER)
@@ -1059,13 +1094,22 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     return gemm<EPI_F32>(H, st, impl, A, K3, rows, W3, p);
   };
   // a-8: per-token style summary
+  auto style_pool = [&](const float* kp, const float* vp, int ldkv) -> int {
+    ProfScope ps(H, st, PC_PRED_EW, (double)BT * ds * 8.0);
+    if (ds <= 256 && K <= 64)   // product kernel: K / V of the utterance staged in shared memory
+      launch_k(style_pool_attn2_kernel, dim3(cdiv(T, SP_TOK), B), 256, (size_t)(K * (2 * ds + 1) + 4) * 4, st, w.sq, kp, vp, ldkv, w.sa, T, K, ds, 1.0f / sqrtf(32.0f));
+    else
+      launch_k(style_pool_attn_kernel, cdiv(BT, 8), 256, 0, st, w.sq, kp, vp, ldkv, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f));
+    KCHECK(H);
+    return 0;
+  };
   if (tc) {
     RET(split_rows(text, c.d_text, c.d_text, w.pq, 3 * c.d_text, c.d_text, 0, BT));
     RET(split_rows(text, c.d_text, c.d_text, w.pa, 3 * kin, kin, 0, BT));          // x part of layer 0's [x | s_tok]
     RET(split_rows(style, Ds, Ds, w.pstyle3, 3 * Ds, Ds, 0, BK));
     RET(gemm3(w.pq, 3 * c.d_text, BT, H->wq3, W32(H, "sp.q.b"), w.sq, ds));
     RET(gemm3(w.pstyle3, 3 * Ds, BK, H->wkv3, H->b_kv, w.skv, 2 * ds));
-    launch_k(style_pool_attn_kernel, cdiv(BT, 8), 256, 0, st, w.sq, w.skv, w.skv + ds, 2 * ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
+    RET(style_pool(w.skv, w.skv + ds, 2 * ds));
     RET(split_rows(w.sa, ds, ds, w.psa3, 3 * ds, ds, 0, BT));
     RET(gemm3(w.psa3, 3 * ds, BT, H->wo3, W32(H, "sp.o.b"), w.stok, ds));
     RET(split_rows(w.stok, ds, ds, w.pa, 3 * kin, kin, dh, BT));                    // s_tok part, shared by all layers
@@ -1074,7 +1118,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     RET(linear_f32(H, st, ACT_NONE, text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "sp.q.w"), W32(H, "sp.q.b"), w.sq, ds, BT, ds));
     RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.k.w"), W32(H, "sp.k.b"), w.sk, ds, BK, ds));
     RET(linear_f32(H, st, ACT_NONE, style, Ds, Ds, nullptr, 0, 0, W32(H, "sp.v.w"), W32(H, "sp.v.b"), w.sv, ds, BK, ds));
-    launch_k(style_pool_attn_kernel, cdiv(BT, 8), 256, 0, st, w.sq, w.sk, w.sv, ds, w.sa, BT, T, K, ds, 1.0f / sqrtf(32.0f)); KCHECK(H);
+    RET(style_pool(w.sk, w.sv, ds));
     RET(linear_f32(H, st, ACT_NONE, w.sa, ds, ds, nullptr, 0, 0, W32(H, "sp.o.w"), W32(H, "sp.o.b"), w.stok, ds, BT, ds));
   }
   // a-9: (BiLSTM + AdaLN) x (n_lstm - 1) + BiLSTM
@@ -1137,10 +1181,12 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
   }
   {  // a-10
     dim3 grid(cdiv(BT, 8));
+    const dim3 grid2(cdiv(BT, 32));
+    ProfScope ps(H, st, PC_PRED_EW, (double)BT * dh * 4.0);
     switch (dh / 128) {
-      case 1: launch_k(dur_head_kernel<1>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
-      case 2: launch_k(dur_head_kernel<2>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
-      case 4: launch_k(dur_head_kernel<4>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 1: launch_k(dur_head2_kernel<1>, grid2, 256, dur_head2_smem(1), st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 2: launch_k(dur_head2_kernel<2>, grid2, 256, dur_head2_smem(2), st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
+      case 4: launch_k(dur_head2_kernel<4>, grid2, 256, dur_head2_smem(4), st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
       case 8: launch_k(dur_head_kernel<8>, grid, 256, 0, st, x, W32(H, "dur.w"), W32(H, "dur.b"), tmask, out_dur, out_presum, BT, c.max_dur); break;
       default: return fail(H, STZ_E_SHAPE, "d_hid %d unsupported", dh);
     }
@@ -1178,20 +1224,34 @@ extern "C" int stz_synthesize_host(stz_handle* H, const float* text_emb, const u
   cudaStream_t st = H->stream;
   RET(order_after_previous_call(H, st));
   const size_t BK = (size_t)B * c.n_style, BT = (size_t)B * T, BP = (size_t)B * P;
-  CK(H, cudaMemcpyAsync(w.st_text, text_emb, BT * c.d_text * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(H, cudaMemcpyAsync(w.st_prompt, prompt_feats, BP * c.d_prompt * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(H, cudaMemcpyAsync(w.st_noise, noise, (size_t)slices * BK * c.d_style * sizeof(float), cudaMemcpyHostToDevice, st));
+  // Main stream: masks + text H2D, then compute.  Copy stream: prompt and noise H2D (consumed after the text-side
+  // prep / at state initialisation: sample_style_impl waits on the events), later the style D2H (overlaps the
+  // duration predictor).  The staging buffers are only ever touched by this entry point, which synchronises both
+  // streams before returning, so the copy stream needs no ordering against earlier calls.
+  cudaStream_t cs = H->copy_stream;
   uint8_t *tm = nullptr, *pm = nullptr;
   if (text_mask) { tm = w.hs_tmask; CK(H, cudaMemcpyAsync(tm, text_mask, BT, cudaMemcpyHostToDevice, st)); }
   if (prompt_mask) { pm = w.hs_pmask; CK(H, cudaMemcpyAsync(pm, prompt_mask, BP, cudaMemcpyHostToDevice, st)); }
-  RET(sample_style_impl(H, w.st_text, tm, w.st_prompt, pm, w.st_noise, B, T, P, steps, cfg_scale, sampler_kind, w.st_style, st));
-  CK(H, cudaMemcpyAsync(out_style, w.st_style, BK * c.d_style * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(H, cudaMemcpyAsync(w.st_text, text_emb, BT * c.d_text * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(H, cudaMemcpyAsync(w.st_prompt, prompt_feats, BP * c.d_prompt * sizeof(float), cudaMemcpyHostToDevice, cs));
+  CK(H, cudaEventRecord(H->ev_prompt, cs));
+  CK(H, cudaMemcpyAsync(w.st_noise, noise, (size_t)slices * BK * c.d_style * sizeof(float), cudaMemcpyHostToDevice, cs));
+  CK(H, cudaEventRecord(H->ev_noise, cs));
+  H->wait_prompt = H->wait_noise = true;
+  int rc = sample_style_impl(H, w.st_text, tm, w.st_prompt, pm, w.st_noise, B, T, P, steps, cfg_scale, sampler_kind, w.st_style, st);
+  H->wait_prompt = H->wait_noise = false;
+  if (rc != 0) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); return rc; }
+  CK(H, cudaEventRecord(H->ev_style, st));
+  CK(H, cudaStreamWaitEvent(cs, H->ev_style, 0));
+  CK(H, cudaMemcpyAsync(out_style, w.st_style, BK * c.d_style * sizeof(float), cudaMemcpyDeviceToHost, cs));
   if (out_dur) {
     int32_t* dur_dev = w.st_dur;
-    RET(predict_duration_impl(H, w.st_text, tm, w.st_style, B, T, dur_dev, nullptr, st));
+    rc = predict_duration_impl(H, w.st_text, tm, w.st_style, B, T, dur_dev, nullptr, st);
+    if (rc != 0) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); return rc; }
     CK(H, cudaMemcpyAsync(out_dur, dur_dev, BT * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   }
   CK(H, cudaStreamSynchronize(st));
+  CK(H, cudaStreamSynchronize(cs));
   return 0;
 }
 
