@@ -51,6 +51,8 @@ struct Workspace {
   int32_t* st_dur;
 };
 
+constexpr int STZ_MAX_CHAINS = 8;
+
 struct stz_handle {
   stz_config cfg;
   int device = 0;
@@ -86,6 +88,10 @@ struct stz_handle {
   bool has_last = false;
   std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
   int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 0;
+  int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
+  cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
+  cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
+  int attn_impl = 0;   // 0 = tcgen05 kernel when the keys fit (else streaming), 1 = mma.sync resident-key kernel, 2 = always streaming
   int ablate = 0;   // tools/ablate.py: bit mask of kernel families skipped inside run_eval (timing attribution only; results are wrong)
   int64_t launches = 0;
   int cur_launches = 0;  // launches issued since the counter was last sampled (capture bookkeeping)
@@ -373,6 +379,8 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<10>())) != cudaSuccess) return e;
@@ -622,6 +630,11 @@ extern "C" void stz_destroy(stz_handle* H) {
   if (H->ev_prompt) cudaEventDestroy(H->ev_prompt);
   if (H->ev_noise) cudaEventDestroy(H->ev_noise);
   if (H->ev_style) cudaEventDestroy(H->ev_style);
+  if (H->fork_ev) cudaEventDestroy(H->fork_ev);
+  for (int i = 1; i < STZ_MAX_CHAINS; ++i) {
+    if (H->join_ev[i]) cudaEventDestroy(H->join_ev[i]);
+    if (H->chain_stream[i]) cudaStreamDestroy(H->chain_stream[i]);
+  }
   if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
   cudaFree(H->kv_null); cudaFree(H->w_in3); cudaFree(H->w_out3); cudaFree(H->whhT); cudaFree(H->whh); cudaFree(H->lstm_b);
   if (H->last_ev) cudaEventDestroy(H->last_ev);
@@ -647,6 +660,11 @@ static int create_impl(stz_handle* H, const float* weights_host) {
   CK(H, cudaEventCreateWithFlags(&H->ev_prompt, cudaEventDisableTiming));
   CK(H, cudaEventCreateWithFlags(&H->ev_noise, cudaEventDisableTiming));
   CK(H, cudaEventCreateWithFlags(&H->ev_style, cudaEventDisableTiming));
+  CK(H, cudaEventCreateWithFlags(&H->fork_ev, cudaEventDisableTiming));
+  for (int i = 1; i < STZ_MAX_CHAINS; ++i) {
+    CK(H, cudaStreamCreateWithFlags(&H->chain_stream[i], cudaStreamNonBlocking));
+    CK(H, cudaEventCreateWithFlags(&H->join_ev[i], cudaEventDisableTiming));
+  }
   CK(H, init_kernel_attrs());
   cudaStream_t st = H->stream;
   CK(H, cudaMalloc(&H->w32, H->n_floats * sizeof(float)));
@@ -781,10 +799,11 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
-  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate")) {
+  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains")) {
     for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
     H->graphs.clear();
-    if (!strcmp(key, "ablate")) H->ablate = value; else H->fuse_ln = value;
+    if (!strcmp(key, "chains")) H->chains = value;
+    else if (!strcmp(key, "ablate")) H->ablate = value; else if (!strcmp(key, "attn_impl")) H->attn_impl = value; else H->fuse_ln = value;
   }
   else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // process-wide knobs baked into captured graphs
     for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
@@ -852,54 +871,72 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
   int n_keys = 0;
   for (int i = 0; i < ap.nseg; ++i) n_keys += ap.seg[i].n;
   ProfScope ps(H, st, PC_ATTN, 4.0 * B * H->cfg.n_heads * ap.n_q * (double)n_keys * ATT_DH);
-  launch_k(attention_kernel, grid, 2 * cdiv(ap.n_q / 2, 16) * 32, ATT_SMEM_BYTES, st, ap);   // ceil(K / 16) warps per CFG branch
+  if (n_keys <= 128 && ap.n_q <= 128 && H->attn_impl == 0) {   // tcgen05: both contractions on the tensor core, thread-per-row softmax
+    const int units = B * H->cfg.n_heads;
+    launch_k(attention_tc_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 128, ATC_SMEM_BYTES, st, ap, H->cfg.n_heads, units);
+  } else if (n_keys <= ATT3_ROWS && ap.n_q <= ATT3_ROWS && H->attn_impl == 1) {   // whole key sequence resident: persistent, prefetching kernel
+    const int units = B * H->cfg.n_heads;
+    launch_k(attention3_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATT3_SMEM_BYTES, st, ap, H->cfg.n_heads, units);
+  } else {
+    launch_k(attention_kernel, grid, 2 * cdiv(ap.n_q / 2, 16) * 32, ATT_SMEM_BYTES, st, ap);   // ceil(K / 16) warps per CFG branch
+  }
   KCHECK(H);
   return 0;
 }
 
-// One denoiser evaluation + fused guidance/sampler update (a-4, a-5, a-6).
-static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, const uint8_t* tmask, const uint8_t* pmask) {
+// One denoiser evaluation + fused guidance/sampler update (a-4, a-5, a-6) for utterances [b0, b0 + nb) of a batch of
+// Btot.  Utterances never interact, so the evaluation loop of a batch may run as several independent chains
+// (sub-ranges) on parallel graph branches: one chain's launch gaps, prologues and tails are filled by the others.
+static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int nb, int T, int P, const uint8_t* tmask,
+                    const uint8_t* pmask) {
   const stz_config& c = H->cfg;
-  Workspace& w = H->ws;
+  const Workspace& w = H->ws;
   const int d = c.d_model, L = c.n_layers, K = c.n_style, Ds = c.d_style, n_mod = (9 * L + 2) * d;
-  const int R = 2 * B * K, NS = 2 * B, impl = H->gemm_impl;
+  const int R = 2 * nb * K, NS = 2 * nb, impl = H->gemm_impl;
+  const size_t r0 = (size_t)2 * b0 * K, s0 = (size_t)2 * b0;     // first activation row / first sequence of this chain
+  float* mod = w.mod + s0 * n_mod;
+  float* h = w.h + r0 * d;
+  bf16 *u = w.u + r0 * d, *u3 = w.u3 + r0 * 3 * d, *qkv = w.qkv + r0 * 3 * d, *att = w.att + r0 * d, *ffh = w.ffh + r0 * c.d_ff;
+  bf16* xin = w.xin + r0 * 3 * Ds;
+  if (tmask) tmask += (size_t)b0 * T;
+  if (pmask) pmask += (size_t)b0 * P;
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)(d / c.n_heads));
   GemmParams base{};
-  base.mod = w.mod; base.n_mod = n_mod; base.rows_per_utt = 2 * K; base.n_style = K;
+  base.mod = mod; base.n_mod = n_mod; base.rows_per_utt = 2 * K; base.n_style = K;
   // ablation bits: 1 self-attn, 2 cross-attn, 4 ln_mod, 8 qkv, 16 attention out-projections, 32 q2, 64 ff1, 128 ff2, 256 mod
   const int ab = H->ablate;
 
   if (!(ab & 256)) {  // AdaLN modulations of this eval: mod[NS, n_mod] = c[e] · Wmod^T + b
     GemmParams p = base;
-    p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * NS; p.bias = W32(H, "mod.b"); p.out = w.mod; p.ldo = n_mod;
+    p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * 2 * Btot + (int)s0; p.bias = W32(H, "mod.b"); p.out = mod; p.ldo = n_mod;
     RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
   }
   const bool fused = H->fuse_ln && impl == 0 && d == GLN_N;   // GEMM + residual + AdaLN in one kernel (gemm_ln.cuh)
   GemmLnParams lb{};
-  lb.M = R; lb.h = w.h; lb.mod = w.mod; lb.n_mod = n_mod; lb.rows_per_utt = 2 * K; lb.pos = W32(H, "pos"); lb.n_style = K;
+  lb.M = R; lb.h = h; lb.mod = mod; lb.n_mod = n_mod; lb.rows_per_utt = 2 * K; lb.pos = W32(H, "pos"); lb.n_style = K;
   // residual GEMM of a sub-layer followed by the AdaLN of the next one: (gate, shift, scale) offsets into mod
   auto res_ln = [&](const bf16* A, int Kc, const bf16* Wt, const float* bias, int gate_off, int ln_off, bool last) -> int {
     if (fused) {
       GemmLnParams p = lb;
       p.K = Kc; p.bias = bias; p.gate_off = gate_off; p.shift_off = ln_off; p.scale_off = ln_off + d; p.split3 = last ? 1 : 0;
-      return launch_gemmln<GLN_RES>(H, st, A, Kc, R, Wt, last ? w.u3 : w.u, p);
+      return launch_gemmln<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
     }
     GemmParams p = base;
-    p.M = R; p.N = d; p.K = Kc; p.bias = bias; p.out = w.h; p.ldo = d; p.gate_off = gate_off;
+    p.M = R; p.N = d; p.K = Kc; p.bias = bias; p.out = h; p.ldo = d; p.gate_off = gate_off;
     if (!(ab & (Kc == d ? 16 : 128))) RET(gemm<EPI_GATE_RES>(H, st, impl, A, Kc, R, Wt, p));
     if (ab & 4) return 0;
-    return ln_mod(H, st, w.h, R, d, w.mod, n_mod, ln_off, ln_off + d, 2 * K, last ? w.u3 : w.u, last ? 1 : 0);
+    return ln_mod(H, st, h, R, d, mod, n_mod, ln_off, ln_off + d, 2 * K, last ? u3 : u, last ? 1 : 0);
   };
   {  // h = x_in · Win^T + b + pos, u = AdaLN_1 of layer 0
     if (fused) {
       GemmLnParams p = lb;
       p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.shift_off = 0; p.scale_off = d; p.split3 = 0;
-      RET(launch_gemmln<GLN_POS>(H, st, w.xin, 3 * Ds, R, H->w_in3, w.u, p));
+      RET(launch_gemmln<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
     } else {
       GemmParams p = base;
-      p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = w.h; p.ldo = d; p.pos = W32(H, "pos");
-      RET(gemm<EPI_F32_POS>(H, st, impl, w.xin, 3 * Ds, R, H->w_in3, p));
-      RET(ln_mod(H, st, w.h, R, d, w.mod, n_mod, 0, d, 2 * K, w.u));
+      p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = h; p.ldo = d; p.pos = W32(H, "pos");
+      RET(gemm<EPI_F32_POS>(H, st, impl, xin, 3 * Ds, R, H->w_in3, p));
+      RET(ln_mod(H, st, h, R, d, mod, n_mod, 0, d, 2 * K, u));
     }
   }
   for (int l = 0; l < L; ++l) {
@@ -908,51 +945,53 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int B, int T, int P, 
     // --- self-attention (u holds AdaLN_1(h))
     if (!(ab & 8)) {
       GemmParams p = base;
-      p.M = R; p.N = 3 * d; p.K = d; p.bias = W32(H, pf + "qkv.b"); p.out = w.qkv; p.ldo = 3 * d;
-      RET(gemm<EPI_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "qkv.w"), p));
+      p.M = R; p.N = 3 * d; p.K = d; p.bias = W32(H, pf + "qkv.b"); p.out = qkv; p.ldo = 3 * d;
+      RET(gemm<EPI_BF16>(H, st, impl, u, d, R, WBF(H, pf + "qkv.w"), p));
     }
     if (!(ab & 1)) {
       AttnParams ap{};
-      ap.q = w.qkv; ap.ldq = 3 * d; ap.out = w.att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 1; ap.scale_log2 = scale_log2;
-      ap.seg[0] = AttnSeg{w.qkv + d, w.qkv + 2 * d, 3 * d, 2 * K, 2 * K, nullptr, KEY_SAME_BRANCH};
-      RET(attention(H, st, ap, B));
+      ap.q = qkv; ap.ldq = 3 * d; ap.out = att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 1; ap.scale_log2 = scale_log2;
+      ap.seg[0] = AttnSeg{qkv + d, qkv + 2 * d, 3 * d, 2 * K, 2 * K, nullptr, KEY_SAME_BRANCH};
+      RET(attention(H, st, ap, nb));
     }
-    RET(res_ln(w.att, d, WBF(H, pf + "o.w"), W32(H, pf + "o.b"), mo + 2 * d, mo + 3 * d, false));
-    RET(tap(H, st, e, l, 0, R));
+    RET(res_ln(att, d, WBF(H, pf + "o.w"), W32(H, pf + "o.b"), mo + 2 * d, mo + 3 * d, false));
+    if (nb == Btot) RET(tap(H, st, e, l, 0, R));
     // --- cross-attention over [text ; prompt | null]  (u holds AdaLN_2(h))
     if (!(ab & 32)) {
       GemmParams p = base;
-      p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "q2.b"); p.out = w.qkv; p.ldo = d;
-      RET(gemm<EPI_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "q2.w"), p));
+      p.M = R; p.N = d; p.K = d; p.bias = W32(H, pf + "q2.b"); p.out = qkv; p.ldo = d;
+      RET(gemm<EPI_BF16>(H, st, impl, u, d, R, WBF(H, pf + "q2.w"), p));
     }
     if (!(ab & 2)) {
       AttnParams ap{};
       const int ldkv = L * 2 * d;
-      ap.q = w.qkv; ap.ldq = d; ap.out = w.att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 3; ap.scale_log2 = scale_log2;
-      ap.seg[0] = AttnSeg{w.kv_text + l * 2 * d, w.kv_text + l * 2 * d + d, ldkv, T, T, tmask, KEY_ALL};
-      ap.seg[1] = AttnSeg{w.kv_prompt + l * 2 * d, w.kv_prompt + l * 2 * d + d, ldkv, P, P, pmask, KEY_COND};
+      const bf16* kt = w.kv_text + ((size_t)b0 * T * L + l) * 2 * d;
+      const bf16* kp = w.kv_prompt + ((size_t)b0 * P * L + l) * 2 * d;
+      ap.q = qkv; ap.ldq = d; ap.out = att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 3; ap.scale_log2 = scale_log2;
+      ap.seg[0] = AttnSeg{kt, kt + d, ldkv, T, T, tmask, KEY_ALL};
+      ap.seg[1] = AttnSeg{kp, kp + d, ldkv, P, P, pmask, KEY_COND};
       ap.seg[2] = AttnSeg{H->kv_null + l * 2 * d, H->kv_null + l * 2 * d + d, ldkv, 1, 0, nullptr, KEY_UNCOND};
-      RET(attention(H, st, ap, B));
+      RET(attention(H, st, ap, nb));
     }
-    RET(res_ln(w.att, d, WBF(H, pf + "o2.w"), W32(H, pf + "o2.b"), mo + 5 * d, mo + 6 * d, false));
-    RET(tap(H, st, e, l, 1, R));
+    RET(res_ln(att, d, WBF(H, pf + "o2.w"), W32(H, pf + "o2.b"), mo + 5 * d, mo + 6 * d, false));
+    if (nb == Btot) RET(tap(H, st, e, l, 1, R));
     // --- FFN  (u holds AdaLN_3(h)); its residual GEMM also produces AdaLN_1 of the next layer / the final AdaLN
     if (!(ab & 64)) {
       GemmParams p = base;
-      p.M = R; p.N = c.d_ff; p.K = d; p.bias = W32(H, pf + "ff1.b"); p.out = w.ffh; p.ldo = c.d_ff;
-      RET(gemm<EPI_GELU_BF16>(H, st, impl, w.u, d, R, WBF(H, pf + "ff1.w"), p));
+      p.M = R; p.N = c.d_ff; p.K = d; p.bias = W32(H, pf + "ff1.b"); p.out = ffh; p.ldo = c.d_ff;
+      RET(gemm<EPI_GELU_BF16>(H, st, impl, u, d, R, WBF(H, pf + "ff1.w"), p));
     }
-    RET(res_ln(w.ffh, c.d_ff, WBF(H, pf + "ff2.w"), W32(H, pf + "ff2.b"), mo + 8 * d, 9 * (l + 1) * d, l == L - 1));
-    RET(tap(H, st, e, l, 2, R));
+    RET(res_ln(ffh, c.d_ff, WBF(H, pf + "ff2.w"), W32(H, pf + "ff2.b"), mo + 8 * d, 9 * (l + 1) * d, l == L - 1));
+    if (nb == Btot) RET(tap(H, st, e, l, 2, R));
   }
   {  // F = u · Wout^T + b, then CFG combine + sampler update + next input in the epilogue
     GemmParams p = base;
     p.M = R; p.N = Ds; p.K = 3 * d; p.bias = W32(H, "out.b"); p.ldo = Ds;
-    p.x = w.x; p.xmid = w.xmid; p.xin = w.xin; p.coef = w.coef + (size_t)e * 8;
+    p.x = w.x + (size_t)b0 * K * Ds; p.xmid = w.xmid + (size_t)b0 * K * Ds; p.xin = xin; p.coef = w.coef + (size_t)e * 8;
     // teacher: eval 2i+1 adds sigma_up * noise slice i+1 (slice 0 seeded the state)
-    p.noise = w.noise + (size_t)((e >> 1) + 1) * B * K * Ds;
-    p.tap = (H->tap_buf && !H->capturing && H->tap_eval == e && H->tap_layer == L) ? H->tap_buf : nullptr;
-    RET(gemm<EPI_SAMPLER>(H, st, impl, w.u3, 3 * d, R, H->w_out3, p));
+    p.noise = w.noise + ((size_t)((e >> 1) + 1) * Btot + b0) * K * Ds;
+    p.tap = (H->tap_buf && !H->capturing && H->tap_eval == e && H->tap_layer == L && nb == Btot) ? H->tap_buf : nullptr;
+    RET(gemm<EPI_SAMPLER>(H, st, impl, u3, 3 * d, R, H->w_out3, p));
   }
   return 0;
 }
@@ -1033,7 +1072,22 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
       CK(H, cudaStreamBeginCapture(H->stream, cudaStreamCaptureModeThreadLocal));
       H->capturing = true;
       int rc = 0;
-      for (int e = 0; e < E && rc == 0; ++e) rc = run_eval(H, H->stream, e, B, T, P, tm, pm);
+      // independent utterance chains on parallel graph branches (fork / join with events inside the capture)
+      int nch = H->chains < 1 ? 1 : (H->chains > STZ_MAX_CHAINS ? STZ_MAX_CHAINS : H->chains);
+      if (nch > B) nch = B;
+      for (int ch = 1; ch < nch && rc == 0; ++ch) {
+        if (cudaEventRecord(H->fork_ev, H->stream) != cudaSuccess || cudaStreamWaitEvent(H->chain_stream[ch], H->fork_ev, 0) != cudaSuccess)
+          rc = fail(H, STZ_E_CUDA, "graph fork failed");
+      }
+      for (int e = 0; e < E && rc == 0; ++e)
+        for (int ch = 0; ch < nch && rc == 0; ++ch) {
+          const int b0 = (int)((long long)B * ch / nch), b1 = (int)((long long)B * (ch + 1) / nch);
+          rc = run_eval(H, ch == 0 ? H->stream : H->chain_stream[ch], e, B, b0, b1 - b0, T, P, tm, pm);
+        }
+      for (int ch = 1; ch < nch && rc == 0; ++ch) {
+        if (cudaEventRecord(H->join_ev[ch], H->chain_stream[ch]) != cudaSuccess || cudaStreamWaitEvent(H->stream, H->join_ev[ch], 0) != cudaSuccess)
+          rc = fail(H, STZ_E_CUDA, "graph join failed");
+      }
       H->capturing = false;
       cudaError_t ce = cudaStreamEndCapture(H->stream, &graph);
       if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1047,7 +1101,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     CK(H, cudaGraphLaunch(it->second.first, st));
     H->launches += it->second.second;
   } else {
-    for (int e = 0; e < E; ++e) RET(run_eval(H, st, e, B, T, P, tmask, pmask));
+    for (int e = 0; e < E; ++e) RET(run_eval(H, st, e, B, 0, B, T, P, tmask, pmask));
     H->launches += H->cur_launches;
     H->cur_launches = 0;
   }

@@ -182,11 +182,11 @@ def test_cfg2_full_size_properties(path):
     z0b = run(steps=1, w=0.0, prompt=inp["prompt_feats"].flip(0) * 1.3)
     assert rel(z0b, z0) < 1e-5
     assert rel(run(steps=1, w=1.0, prompt=inp["prompt_feats"].flip(0) * 1.3), z1) > 1e-2
-    # padding invariance: extend T with masked garbage.  T2 = 128 keeps the 64-key block partition of the fused
-    # attention (one extra, fully masked block), so the result must be (nearly) bit-identical; T2 = 96 shifts the
-    # prompt keys into different blocks, which changes the running max at which P is rounded to bf16 for the PV MMA
-    # -> differences of the size of the bf16 noise itself (well inside the 1e-2 budget), not a masking error.
-    for T2, tol in ((128, 1e-5), (96, 5e-3)):
+    # padding invariance: extend T with masked garbage.  The result changes only by bf16 rounding noise (well inside
+    # the 1e-2 budget), not by a masking error: T2 = 96 moves the prompt keys to other columns of the tcgen05
+    # attention tile, T2 = 128 exceeds its 128 resident keys and runs the streaming mma.sync kernel instead, which
+    # rounds P to bf16 at a different running max.
+    for T2, tol in ((128, 5e-3), (96, 5e-3)):
         te = torch.cat([inp["text_emb"], 50.0 * torch.randn(B, T2 - T, CFG.d_text)], 1)
         tm = torch.cat([torch.ones(B, T, dtype=torch.bool), torch.zeros(B, T2 - T, dtype=torch.bool)], 1)
         assert rel(run(text=te, mask=tm), z) < tol, T2

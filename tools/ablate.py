@@ -29,6 +29,12 @@ def timeit(fn, n=20):
 samp = lambda: path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=dev["noise"])
 z = samp()
 pred = lambda: path.predict_duration(dev["text_emb"], z)
+for ch in (1, 2, 3, 4, 6, 8):
+    path.set_option("chains", ch)
+    print(f"chains {ch}: sample_style {timeit(samp):.3f} ms", flush=True)
+path.set_option("chains", int(os.environ.get("CHAINS", 1)))
+if os.environ.get("SWEEP_ONLY"):
+    sys.exit(0)
 full = timeit(samp)
 print(f"full sample_style {full:.3f} ms   predict_duration {timeit(pred):.3f} ms", flush=True)
 names = {1: "self-attn", 2: "cross-attn", 4: "ln_mod", 8: "qkv gemm", 16: "attn out-proj gemms (2/layer)", 32: "q2 gemm",
