@@ -122,6 +122,10 @@ int stz_profile_read(stz_handle* h, int kernel_class, double* ms, double* work, 
  * tap_dev = NULL disables. */
 int stz_debug_set_tap(stz_handle* h, int eval, int layer, int stage, float* tap_dev);
 
+/* Debug timeline of the tcgen05 attention kernel: trace_dev = int64 [CTAs][16] device buffer (NULL disables); thread 0
+ * of every CTA stores clock64() at its phase boundaries (tools/att_trace.py). */
+int stz_debug_set_att_trace(stz_handle* h, long long* trace_dev);
+
 /* Roofline measurement hook (bench.py): `iters` back-to-back launches of the product GEMM kernel for one shape
  * (C[M,N] = A[M,K] W[N,K]^T, epi 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual reduce-add) on the handle's
  * internal stream, timed with a CUDA-event pair; *avg_us = mean microseconds per launch.  Zero-filled operands. */

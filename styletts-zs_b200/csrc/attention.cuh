@@ -9,6 +9,7 @@
 // legacy warp-level tensor path (mma.sync m16n8k16 bf16 -> fp32).  This is ~4 % of the
 // denoiser's flops; the tcgen05 budget goes to the GEMMs (gemm.cuh).
 #pragma once
+#include <cuda.h>
 #include "ptx.cuh"
 
 namespace stz {
@@ -529,6 +530,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   return d;
 }
 
+// Debug timeline (tools/att_trace.py): when set, thread 0 of every CTA records clock64() at the phase boundaries of
+// its first two units into g_att_trace[cta][16].
+__device__ long long* g_att_trace = nullptr;
+
 __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p, int n_heads, int n_units) {
   extern __shared__ uint8_t atc_smem_raw[];
   __shared__ __align__(8) uint64_t bar_s, bar_o;
@@ -537,6 +542,10 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
   __shared__ uint32_t colmask[2][2][4];     // [buffer][branch][32-column chunk]
   const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* tr = (g_att_trace != nullptr && tid == 0) ? g_att_trace + blockIdx.x * 16 : nullptr;
+  int tri = 0;
+#define ATC_TR() do { if (tr != nullptr && tri < 16) tr[tri++] = clock64(); } while (0)
+  ATC_TR();
   const int n_tok = p.n_q >> 1;
   const int br = warp >> 1;                            // rows 0..63 conditional, 64..127 unconditional
   const int tok = tid & 63;
@@ -554,7 +563,9 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
+  ATC_TR();
   pdl_sync();
+  ATC_TR();
 
   // thread -> one operand row (Q row tid, K/V key row tid), eight 16-byte chunks each, written 128B-swizzled
   auto issue = [&](int unit, int buf) {
@@ -609,9 +620,11 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
     const int next = unit + gridDim.x;
     if (next < n_units) issue(next, buf ^ 1);
     cp_async_commit();
+    ATC_TR();
     cp_async_wait<1>();
     fence_proxy_async();          // cp.async wrote through the generic proxy; the tensor core reads through the async proxy
     __syncthreads();
+    ATC_TR();
     {  // per-branch visibility of each 32-key chunk
       const uint8_t v = visb[buf][warp * 32 + lane];
       const uint32_t m0 = __ballot_sync(0xffffffffu, (v & 1) != 0), m1 = __ballot_sync(0xffffffffu, (v & 2) != 0);
@@ -628,6 +641,7 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
     __syncthreads();              // colmask visible
     mbar_wait(&bar_s, phase);
     tc_fence_after();
+    ATC_TR();
 
     // ---- softmax of row `tid` ----
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
@@ -673,6 +687,7 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    ATC_TR();
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -685,6 +700,7 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
     }
     mbar_wait(&bar_o, phase);
     tc_fence_after();
+    ATC_TR();
     {  // out row = O / rowsum
       const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
       const int b = unit / n_heads, head = unit - b * n_heads;
@@ -709,6 +725,255 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
     }
     tc_fence_before();
     __syncthreads();     // TMEM and this buffer are free again
+    ATC_TR();
+    buf ^= 1;
+    phase ^= 1u;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem_slot);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// attention_tc2_kernel — attention_tc_kernel with (a) TMA operand staging and (b) 8 warps.
+//
+// (a) The timeline of attention_tc_kernel (tools/att_trace.py) showed ~1.5 k cycles of LSU time per unit just
+//     issuing the 3072 16-byte cp.async of one unit.  Here one thread issues 6-8 TMA box copies per unit:
+//       self  : a 3-D view (column, branch, token) of the qkv buffer de-interleaves the CFG branches in the copy:
+//               box (64 cols, 1 branch, 64 tokens) -> tile rows branch * 64 + token, for Q, K and V;
+//       cross : Q as above; text / prompt / null-prompt K and V as 2-D boxes at tile rows 0, T8 and T8 + P8
+//               (segments start on 8-row = 1024-byte swizzle-atom boundaries).
+//     Rows a box does not cover keep old (finite: the tiles are zeroed at kernel start) contents and are masked by
+//     the per-key visibility byte; padded / masked keys are loaded but invisible (their K/V rows are finite because
+//     cast_pool_kernel zeroes masked tokens).
+// (b) Warps w and w + 4 share TMEM lane quadrant w & 3 (= the same 32 query rows) and split the 32-key chunks of
+//     S by parity and the 64 output columns in halves; row max / row sum partials meet in shared memory.
+//     Fully visible chunks skip the per-element visibility select (warp-uniform branch).
+// ------------------------------------------------------------------------------------------------------
+struct AttnTcParams {
+  __nv_bfloat16* out;      // R layout [R, ldo]
+  int ldo, n_q, n_heads, n_units;
+  int self;                // 1: keys = the utterance's own rows (same branch); 0: [text ; prompt | null]
+  int T, P, T8, P8;        // cross: segment lengths and their 8-row padded sizes
+  int col_k, col_v;        // first column of this layer's K / V inside the K/V tensor maps (head 0)
+  const uint8_t* tmask;    // [B, T] or nullptr
+  const uint8_t* pmask;    // [B, P] or nullptr
+  int n_style;             // tokens per branch
+  float scale_log2;
+};
+
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                               const __grid_constant__ CUtensorMap tmT,
+                                                               const __grid_constant__ CUtensorMap tmP,
+                                                               const __grid_constant__ CUtensorMap tmN,
+                                                               const AttnTcParams p) {
+  extern __shared__ uint8_t atc_smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[2], bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint8_t visb[2][128];
+  __shared__ uint32_t colmask[2][4];        // [branch][32-column chunk] of the current unit
+  __shared__ float pmax[2][128], psum[2][128];
+  const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;
+  const int row = q4 * 32 + lane;                      // query row = TMEM lane
+  const int br = row >> 6, tok = row & 63;             // rows 0..63 conditional, 64..127 unconditional
+  const int n_tok = p.n_style;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmT);
+    if (!p.self) { prefetch_tmap(&tmP); prefetch_tmap(&tmN); }
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  for (uint32_t o = tid * 16; o < 2 * ATC_BUF_BYTES; o += 256 * 16) st_shared_v4(smem_base + o, 0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
+  pdl_sync();
+
+  const uint32_t tx_bytes = p.self ? 6u * 8192u : 2u * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
+  auto produce = [&](int unit, int buf) {
+    const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+    if (tid == 0) {
+      const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
+      const uint32_t bar = smem_u32(&bar_full[buf]);
+      mbar_expect_tx(&bar_full[buf], tx_bytes);
+      const int t0 = b * n_tok, hc = head * ATT_DH;
+      tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
+      tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+      if (p.self) {
+        tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
+        tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
+        tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
+        tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
+      } else {
+        const uint32_t o1 = p.T8 * 128, o2 = (p.T8 + p.P8) * 128;
+        tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
+        tma_load_2d_u32(vs, &tmT, bar, p.col_v + hc, b * p.T);
+        tma_load_2d_u32(ks + o1, &tmP, bar, p.col_k + hc, b * p.P);
+        tma_load_2d_u32(vs + o1, &tmP, bar, p.col_v + hc, b * p.P);
+        tma_load_2d_u32(ks + o2, &tmN, bar, p.col_k + hc, 0);
+        tma_load_2d_u32(vs + o2, &tmN, bar, p.col_v + hc, 0);
+      }
+    }
+    if (tid < 128) {   // visibility of key row `tid`: bit 0 = conditional queries, bit 1 = unconditional queries
+      uint8_t vis = 0;
+      if (p.self) {
+        vis = (tid & 63) < n_tok ? static_cast<uint8_t>(1u << (tid >> 6)) : 0;
+      } else if (tid < p.T) {
+        vis = (p.tmask == nullptr || p.tmask[static_cast<size_t>(b) * p.T + tid] != 0) ? 3 : 0;
+      } else if (tid >= p.T8 && tid < p.T8 + p.P) {
+        vis = (p.pmask == nullptr || p.pmask[static_cast<size_t>(b) * p.P + (tid - p.T8)] != 0) ? 1 : 0;
+      } else if (tid == p.T8 + p.P8) {
+        vis = 2;
+      }
+      visb[buf][tid] = vis;
+    }
+  };
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
+  const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+  int buf = 0;
+  uint32_t phase = 0, fph0 = 0, fph1 = 0;
+  if (static_cast<int>(blockIdx.x) < p.n_units) produce(blockIdx.x, 0);
+  for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+    const int next = unit + gridDim.x;
+    if (next < p.n_units) produce(next, buf ^ 1);
+    mbar_wait(&bar_full[buf], buf ? fph1 : fph0);
+    if (buf) fph1 ^= 1u; else fph0 ^= 1u;
+    __syncthreads();              // visb[buf] visible
+    const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(ks);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&bar_s);
+    }
+    if (warp < 4) {  // per-branch visibility of each 32-key chunk
+      const uint8_t v = visb[buf][warp * 32 + lane];
+      const uint32_t m0 = __ballot_sync(0xffffffffu, (v & 1) != 0), m1 = __ballot_sync(0xffffffffu, (v & 2) != 0);
+      if (lane == 0) { colmask[0][warp] = m0; colmask[1][warp] = m1; }
+    }
+    __syncthreads();              // colmask visible
+    const uint32_t cm0 = colmask[br][half], cm1 = colmask[br][half + 2];   // this warp's chunks: half, half + 2
+    mbar_wait(&bar_s, phase);
+    tc_fence_after();
+
+    // ---- pass 1: row max over the visible keys of this warp's chunks
+    float mx = -INFINITY;
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const uint32_t cm = ci ? cm1 : cm0;
+      if (cm == 0) continue;   // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_s + lane_addr + (half + 2 * ci) * 32, r);
+      tmem_ld_wait();
+      if (cm == 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+      } else {   // partially visible chunk: mask, so that the result never depends on a neighbouring utterance's rows
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((cm >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
+      }
+    }
+    pmax[half][row] = mx;
+    __syncthreads();
+    mx = fmaxf(pmax[0][row], pmax[1][row]);
+    const float mb = (mx == -INFINITY ? 0.f : mx) * p.scale_log2;
+
+    // ---- pass 2: P = exp2(S * scale - max), masked, bf16, into the dead Q | K tiles (K-major, swizzled)
+    float lsum = 0.f;
+    const uint32_t prow = qs + row * 128, sw = row & 7;
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const int c = half + 2 * ci;
+      const uint32_t cm = ci ? cm1 : cm0;
+      const uint32_t pb = prow + (c >> 1) * ATC_TILE;
+      if (cm == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), 0u, 0u, 0u, 0u);
+        continue;
+      }
+      uint32_t r[32];
+      tmem_ld32(tmem_s + lane_addr + c * 32, r);
+      tmem_ld_wait();
+      float pv[32];
+      if (cm == 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
+          lsum += pv[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
+          pv[j] = ((cm >> j) & 1u) ? e : 0.f;
+          lsum += pv[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
+                     pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
+    }
+    psum[half][row] = lsum;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
+        const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
+        umma_bf16(tmem_o, da, db, idesc_o, j != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_o);
+    }
+    const float ltot = psum[0][row] + psum[1][row];
+    const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
+    const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+    __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
+    mbar_wait(&bar_o, phase);
+    tc_fence_after();
+    {  // out row = O / rowsum: this warp's 32 of the 64 columns
+      uint32_t r[32];
+      tmem_ld32(tmem_o + lane_addr + half * 32, r);
+      tmem_ld_wait();
+      if (tok < n_tok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + j * 8) = u;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();     // TMEM, this buffer and the row-statistic arrays are free again
     buf ^= 1;
     phase ^= 1u;
   }

@@ -37,10 +37,13 @@ __global__ void __launch_bounds__(256) cast_pool_kernel(const float* __restrict_
   int cnt = 0;
   for (int t = sl; t < T; t += 8) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(xr + static_cast<size_t>(t) * D) + c);
-    uint2 u;
-    u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
+    const bool ok = mask == nullptr || mask[static_cast<size_t>(b) * T + t];
+    // masked tokens are stored as zeros: their context K / V rows stay finite whatever the caller left in the
+    // padding (the attention kernels load masked keys and rely on p = 0 * finite)
+    uint2 u = make_uint2(0u, 0u);
+    if (ok) { u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w); }
     *reinterpret_cast<uint2*>(br + static_cast<size_t>(t) * D + c * 4) = u;
-    if (mask == nullptr || mask[static_cast<size_t>(b) * T + t]) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; ++cnt; }
+    if (ok) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; ++cnt; }
   }
   part[sl][cl] = acc;
   if (cl == 0) cnt_s[sl] = cnt;

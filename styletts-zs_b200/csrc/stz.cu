@@ -91,7 +91,7 @@ struct stz_handle {
   int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
-  int attn_impl = 0;   // 0 = tcgen05 kernel when the keys fit (else streaming), 1 = mma.sync resident-key kernel, 2 = always streaming
+  int attn_impl = 0;   // 0 = tcgen05 + TMA kernel when the keys fit (else streaming), 1 = mma.sync resident-key kernel, 2 = always streaming, 3 = tcgen05 + cp.async
   int ablate = 0;   // tools/ablate.py: bit mask of kernel families skipped inside run_eval (timing attribution only; results are wrong)
   int64_t launches = 0;
   int cur_launches = 0;  // launches issued since the counter was last sampled (capture bookkeeping)
@@ -247,6 +247,16 @@ static int make_tmap_out(CUtensorMap* m, void* base, bool is_bf16, uint64_t rows
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// General tiled map over bf16 data with 128B swizzle: dims / box innermost first, strides (bytes) for dims 1..rank-1.
+static int make_tmap_nd(CUtensorMap* m, const void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes,
+                        const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 // ------------------------------------------------------------------------------------------
 // GEMM launchers
 // ------------------------------------------------------------------------------------------
@@ -381,6 +391,7 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<10>())) != cudaSuccess) return e;
@@ -851,6 +862,13 @@ extern "C" int stz_profile_read(stz_handle* H, int cls, double* ms, double* work
   return 0;
 }
 
+extern "C" int stz_debug_set_att_trace(stz_handle* H, long long* trace_dev) {
+  if (!H) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  CK(H, cudaMemcpyToSymbol(g_att_trace, &trace_dev, sizeof trace_dev));
+  return 0;
+}
+
 extern "C" int stz_debug_set_tap(stz_handle* H, int eval, int layer, int stage, float* tap_dev) {
   if (!H) return STZ_E_ARG;
   H->tap_eval = eval; H->tap_layer = layer; H->tap_stage = stage; H->tap_buf = tap_dev;
@@ -866,12 +884,56 @@ static int tap(stz_handle* H, cudaStream_t st, int e, int l, int s, size_t R) {
   return 0;
 }
 
+__global__ void empty_pdl_kernel(int) { pdl_sync(); }
+
 static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B) {
+  if (H->ablate & 512) {   // timing attribution: what a dependent kernel node costs when it does nothing
+    launch_k(empty_pdl_kernel, 148, 128, 0, st, 0);
+    KCHECK(H);
+    return 0;
+  }
   dim3 grid(H->cfg.n_heads, B);
   int n_keys = 0;
   for (int i = 0; i < ap.nseg; ++i) n_keys += ap.seg[i].n;
   ProfScope ps(H, st, PC_ATTN, 4.0 * B * H->cfg.n_heads * ap.n_q * (double)n_keys * ATT_DH);
-  if (n_keys <= 128 && ap.n_q <= 128 && H->attn_impl == 0) {   // tcgen05: both contractions on the tensor core, thread-per-row softmax
+  const int n_style = ap.n_q / 2, dm = H->cfg.d_model;
+  const bool self = ap.nseg == 1 && ap.seg[0].rule == KEY_SAME_BRANCH;
+  const bool cross3 = ap.nseg == 3 && ap.seg[0].rule == KEY_ALL && ap.seg[1].rule == KEY_COND && ap.seg[2].rule == KEY_UNCOND && ap.seg[2].n == 1;
+  const int T8 = cross3 ? (ap.seg[0].n + 7) / 8 * 8 : 0, P8 = cross3 ? (ap.seg[1].n + 7) / 8 * 8 : 0;
+  if (H->attn_impl == 0 && ap.n_q <= 128 && n_style <= 64 && (self || (cross3 && T8 + P8 + 1 <= 128))) {
+    // tcgen05 attention, TMA-staged operands (attention_tc2_kernel)
+    CUtensorMap tq, tt, tp, tn;
+    memset(&tp, 0, sizeof tp); memset(&tn, 0, sizeof tn);
+    const int qcols = self ? (int)(ap.seg[0].v - ap.q) + dm : dm;
+    {  // Q (and, for self-attention, K / V): (column, branch, token) view of the R-layout buffer
+      const cuuint64_t gd[3] = {(cuuint64_t)qcols, 2, (cuuint64_t)B * n_style};
+      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 4};
+      const cuuint32_t bx[3] = {64, 1, 64};
+      if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
+    }
+    tt = tq;
+    AttnTcParams tp_{};
+    tp_.out = ap.out; tp_.ldo = ap.ldo; tp_.n_q = ap.n_q; tp_.n_heads = H->cfg.n_heads; tp_.n_units = B * H->cfg.n_heads;
+    tp_.self = self ? 1 : 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2;
+    if (self) {
+      tp_.col_k = (int)(ap.seg[0].k - ap.q); tp_.col_v = (int)(ap.seg[0].v - ap.q);
+    } else {
+      const AttnSeg* sg = ap.seg;
+      const CUtensorMap* maps[3] = {&tt, &tp, &tn};
+      for (int i = 0; i < 3; ++i) {   // K | V of this layer = 2 * d_model columns starting at seg.k
+        const cuuint64_t rows = i == 2 ? 1 : (cuuint64_t)B * sg[i].n;
+        const cuuint64_t gd[2] = {(cuuint64_t)2 * dm, rows};
+        const cuuint64_t gs[1] = {(cuuint64_t)sg[i].ld * 2};
+        const cuuint32_t bx[2] = {64, (cuuint32_t)sg[i].n};
+        if ((int)(sg[i].v - sg[i].k) != dm || make_tmap_nd(const_cast<CUtensorMap*>(maps[i]), sg[i].k, 2, gd, gs, bx))
+          return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention K/V segment %d) failed", i);
+      }
+      tp_.T = sg[0].n; tp_.P = sg[1].n; tp_.T8 = T8; tp_.P8 = P8; tp_.col_k = 0; tp_.col_v = dm;
+      tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
+    }
+    const int units = tp_.n_units;
+    launch_k(attention_tc2_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
+  } else if (n_keys <= 128 && ap.n_q <= 128 && H->attn_impl == 3) {   // tcgen05 with cp.async staging (superseded by tc2)
     const int units = B * H->cfg.n_heads;
     launch_k(attention_tc_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 128, ATC_SMEM_BYTES, st, ap, H->cfg.n_heads, units);
   } else if (n_keys <= ATT3_ROWS && ap.n_q <= ATT3_ROWS && H->attn_impl == 1) {   // whole key sequence resident: persistent, prefetching kernel

@@ -37,7 +37,7 @@ if os.environ.get("SWEEP_ONLY"):
     sys.exit(0)
 full = timeit(samp)
 print(f"full sample_style {full:.3f} ms   predict_duration {timeit(pred):.3f} ms", flush=True)
-names = {1: "self-attn", 2: "cross-attn", 4: "ln_mod", 8: "qkv gemm", 16: "attn out-proj gemms (2/layer)", 32: "q2 gemm",
+names = {512: "attention bodies (empty kernels instead)", 1: "self-attn", 2: "cross-attn", 4: "ln_mod", 8: "qkv gemm", 16: "attn out-proj gemms (2/layer)", 32: "q2 gemm",
          64: "ff1 gemm", 128: "ff2 gemm", 256: "mod gemm", 3: "both attentions", 511 - 256: "everything per-layer",
          8 + 16 + 32 + 64 + 128: "all layer gemms"}
 for bits, name in names.items():
