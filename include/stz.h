@@ -126,6 +126,10 @@ int stz_debug_set_tap(stz_handle* h, int eval, int layer, int stage, float* tap_
  * of every CTA stores clock64() at its phase boundaries (tools/att_trace.py). */
 int stz_debug_set_att_trace(stz_handle* h, long long* trace_dev);
 
+/* Debug timeline of the product GEMM kernel: trace_dev = int64 [CTAs][64] device buffer (NULL disables); see gemm2.cuh
+ * for the slot meanings (tools/gemm_trace.py). */
+int stz_debug_set_gemm_trace(stz_handle* h, long long* trace_dev);
+
 /* Roofline measurement hook (bench.py): `iters` back-to-back launches of the product GEMM kernel for one shape
  * (C[M,N] = A[M,K] W[N,K]^T, epi 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual reduce-add) on the handle's
  * internal stream, timed with a CUDA-event pair; *avg_us = mean microseconds per launch.  Zero-filled operands. */

@@ -542,7 +542,11 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p
   __shared__ uint32_t colmask[2][2][4];     // [buffer][branch][32-column chunk]
   const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef STZ_TRACE
   long long* tr = (g_att_trace != nullptr && tid == 0) ? g_att_trace + blockIdx.x * 16 : nullptr;
+#else
+  constexpr long long* tr = nullptr;   // (make TRACE=1 enables the timeline)
+#endif
   int tri = 0;
 #define ATC_TR() do { if (tr != nullptr && tri < 16) tr[tri++] = clock64(); } while (0)
   ATC_TR();

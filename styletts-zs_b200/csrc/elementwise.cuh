@@ -75,10 +75,19 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h
   float4 v[VPL];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i] = hr[i * 32 + lane];
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  for (int i = 0; i < VPL; ++i) v[i] = hr[i * 32 + lane];
+  // the modulation rows do not depend on the statistics: fetch them under the two reductions
+  float4 sc[VPL], sh[VPL];
+  if (mod != nullptr) {
+    const float* mrow = mod + static_cast<size_t>((row / rows_per_utt) * 2 + (row & 1)) * n_mod;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      sc[i] = __ldg(reinterpret_cast<const float4*>(mrow + scale_off) + i * 32 + lane);
+      sh[i] = __ldg(reinterpret_cast<const float4*>(mrow + shift_off) + i * 32 + lane);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
   const float mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll
@@ -87,16 +96,12 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h
     q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
-  const float* mrow = nullptr;
-  if (mod != nullptr) mrow = mod + static_cast<size_t>((row / rows_per_utt) * 2 + (row & 1)) * n_mod;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     float4 y = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);
-    if (mrow != nullptr) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + scale_off) + i * 32 + lane);
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + shift_off) + i * 32 + lane);
-      y.x = y.x * (1.f + sc.x) + sh.x; y.y = y.y * (1.f + sc.y) + sh.y;
-      y.z = y.z * (1.f + sc.z) + sh.z; y.w = y.w * (1.f + sc.w) + sh.w;
+    if (mod != nullptr) {
+      y.x = y.x * (1.f + sc[i].x) + sh[i].x; y.y = y.y * (1.f + sc[i].y) + sh[i].y;
+      y.z = y.z * (1.f + sc[i].z) + sh[i].z; y.w = y.w * (1.f + sc[i].w) + sh[i].w;
     }
     uint2 u;
     u.x = pack_bf16(y.x, y.y); u.y = pack_bf16(y.z, y.w);

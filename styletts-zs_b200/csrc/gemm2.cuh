@@ -12,6 +12,7 @@
 // Tiles are visited n-fastest so CTAs running concurrently share A row-blocks in L2.  Rows past M are
 // zero-filled on load and clipped on store by the tensor maps (no tail code).
 #pragma once
+#include <cuda_fp16.h>
 #include "gemm.cuh"
 
 namespace stz {
@@ -48,10 +49,98 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.0f + tanh_fast(k0 * (x + k1 * x * x * x)));
 }
 
-// Staged epilogues: EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_GATE_RES.  Direct (row-per-thread global
-// access, legacy epilogue_row32): EPI_F32_POS, EPI_SAMPLER — one launch each per denoiser evaluation.
+// GELU-tanh of two values at once in packed fp16 arithmetic -> packed bf16.  The FFN1 epilogue is instruction-issue
+// bound (tools/gemm_trace.py: a 128 x 256 tile's epilogue took longer than its mainloop and slowed it by ~45 %);
+// fp16x2 halves the arithmetic instructions.  fp16 carries 11 significant bits against the 8 of the bf16 result,
+// |x| of the FFN pre-activations is far inside the fp16 range, and tiny |x| only lose absolute accuracy (< 6e-8).
+__device__ __forceinline__ uint32_t gelu_tanh_f16x2_to_bf16x2(float a, float b) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmul2(x, x);
+  const __half2 inner = __hmul2(x, __hfma2(x2, __float2half2_rn(0.7978845608028654f * 0.044715f), __float2half2_rn(0.7978845608028654f)));
+  __half2 t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&t)) : "r"(*reinterpret_cast<const uint32_t*>(&inner)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 y = __hfma2(hx, t, hx);
+  const float2 f = __half22float2(y);
+  return pack_bf16(f.x, f.y);
+}
+
+// Staged epilogues (TMA store / reduce): EPI_F32, EPI_F32_POS, EPI_BF16, EPI_GELU_BF16, EPI_GATE_RES.
+// EPI_SAMPLER: sampler_epilogue32 below (warp-transposed through the staging tile, coalesced global access).
+
+// CFG combine + EDM/sampler affine update + next input for one warp: tile rows m0 .. m0 + 31 (lane = row, R layout:
+// even rows conditional, odd rows unconditional) x 32 columns from n0, accumulators (+ bias) in v[].
+// The guided F of the 16 state rows is transposed through a 2 KB shared-memory tile so that the state update runs
+// with lane = (state row, 16-column half): every global access is a full 32-byte sector run (the row-per-thread
+// form issued 24 scattered 8-byte stores per thread and chunk and was bound by L1 store transactions).
+__device__ __forceinline__ void sampler_epilogue32(const GemmParams& p, int m0, int n0, float (&v)[32], uint32_t stage, int lane) {
+  const float w = __ldg(p.coef + 5);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
+    const float Fc = (lane & 1) ? other : v[j], Fu = (lane & 1) ? v[j] : other;
+    v[j] = Fu + w * (Fc - Fu);
+  }
+  if ((lane & 1) == 0) {
+    const int r = lane >> 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(stage + r * 128 + ((j ^ (r & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                   __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+  }
+  __syncwarp();
+  const int r = lane >> 1, hs = lane & 1;
+  const int srow = (m0 >> 1) + r;                       // state row
+  if (2 * srow < p.M) {
+    const float cx = __ldg(p.coef + 0), cm = __ldg(p.coef + 1), cF = __ldg(p.coef + 2), cn = __ldg(p.coef + 3);
+    const float cin = __ldg(p.coef + 4);
+    const bool to_mid = __ldg(p.coef + 6) != 0.0f;
+    const size_t so = static_cast<size_t>(srow) * p.N + n0 + hs * 16;
+    float* dst = (to_mid ? p.xmid : p.x) + so;
+    __nv_bfloat16* xo = p.xin + static_cast<size_t>(2 * srow) * 3 * p.N + n0 + hs * 16;
+#pragma unroll
+    for (int jj = 0; jj < 4; jj += 2) {
+      float4 o[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float4 F;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(F.x), "=f"(F.y), "=f"(F.z), "=f"(F.w)
+                     : "r"(stage + r * 128 + (((4 * hs + jj + q) ^ (r & 7)) << 4)));
+        const float4 xv = *reinterpret_cast<const float4*>(p.x + so + (jj + q) * 4);
+        o[q] = make_float4(cx * xv.x + cF * F.x, cx * xv.y + cF * F.y, cx * xv.z + cF * F.z, cx * xv.w + cF * F.w);
+        if (cm != 0.0f) {
+          const float4 xm = *reinterpret_cast<const float4*>(p.xmid + so + (jj + q) * 4);
+          o[q].x += cm * xm.x; o[q].y += cm * xm.y; o[q].z += cm * xm.z; o[q].w += cm * xm.w;
+        }
+        if (cn != 0.0f) {
+          const float4 nz = __ldg(reinterpret_cast<const float4*>(p.noise + so + (jj + q) * 4));
+          o[q].x += cn * nz.x; o[q].y += cn * nz.y; o[q].z += cn * nz.z; o[q].w += cn * nz.w;
+        }
+        if (p.tap != nullptr) *reinterpret_cast<float4*>(p.tap + so + (jj + q) * 4) = F;
+      }
+      *reinterpret_cast<float4*>(dst + jj * 4) = o[0];
+      *reinterpret_cast<float4*>(dst + jj * 4 + 4) = o[1];
+      // next eval's input c_in(sigma') x' as the split-bf16 A operand [hi | lo | hi] (row stride 3N), both CFG branches
+      const float4 y0 = make_float4(cin * o[0].x, cin * o[0].y, cin * o[0].z, cin * o[0].w);
+      const float4 y1 = make_float4(cin * o[1].x, cin * o[1].y, cin * o[1].z, cin * o[1].w);
+      uint2 h0, h1;
+      h0.x = pack_bf16(y0.x, y0.y); h0.y = pack_bf16(y0.z, y0.w);
+      h1.x = pack_bf16(y1.x, y1.y); h1.y = pack_bf16(y1.z, y1.w);
+      const uint2 l0 = split_lo4(y0, h0), l1 = split_lo4(y1, h1);
+      const uint4 hi = make_uint4(h0.x, h0.y, h1.x, h1.y), lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        __nv_bfloat16* xr = xo + static_cast<size_t>(b) * 3 * p.N + jj * 4;
+        *reinterpret_cast<uint4*>(xr) = hi;
+        *reinterpret_cast<uint4*>(xr + p.N) = lo;
+        *reinterpret_cast<uint4*>(xr + 2 * p.N) = hi;
+      }
+    }
+  }
+  __syncwarp();   // the staging tile is reused by this warp's next chunk
+}
 template <int EPI>
-constexpr bool g2_staged() { return EPI == EPI_F32 || EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_GATE_RES; }
+constexpr bool g2_staged() { return EPI == EPI_F32 || EPI == EPI_F32_POS || EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_GATE_RES; }
 template <int EPI>
 constexpr bool g2_out_bf16() { return EPI == EPI_BF16 || EPI == EPI_GELU_BF16; }
 
@@ -116,6 +205,13 @@ constexpr int g2_stages_cm() { return CM == 1 ? g2_stages<BN>() : (BN == 128 ? 8
 template <int BN, int CM>
 constexpr int g2_smem_bytes_cm() { return g2_stages_cm<BN, CM>() * g2_stage_bytes<BN, CM>() + G2_STAGE_BYTES_EPI + 1024; }
 
+// Debug timeline (tools/gemm_trace.py): when set, every CTA records clock64() stamps into g_gemm_trace[cta][64]:
+// [0] start, [1] after TMEM alloc / barrier init, [2] after griddepcontrol.wait, [3] producer: first TMA issued,
+// [4] producer: last TMA issued; per tile t < 4: [8+4t] MMA: first stage landed, [9+4t] MMA: tile committed,
+// [10+4t] epilogue warp 2: accumulator ready, [11+4t] epilogue warp 2: tile drained; [5] end.
+__device__ long long* g_gemm_trace = nullptr;
+__device__ int g_gemm_dbg = 0;   // experiment flags (tools/gemm_trace.py): 1 skip TMA store, 2 skip GELU, 4 skip staging stores
+
 template <int BN, int EPI, int CM = 1>
 __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
@@ -135,6 +231,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * (A_BYTES + B_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef STZ_TRACE
+  long long* tr = g_gemm_trace != nullptr ? g_gemm_trace + blockIdx.x * 64 : nullptr;
+  const int dbg = g_gemm_dbg;
+#else
+  constexpr long long* tr = nullptr;   // timeline / experiment hooks compile away (make TRACE=1 enables them)
+  constexpr int dbg = 0;
+#endif
+  if (tr != nullptr && threadIdx.x == 0) tr[0] = clock64();
   const int num_kb = p.K / GEMM_BK;
   const int tiles_n = p.N / BN;
   // work units: (CM * 128) rows x BN columns; unit u -> rows of this CTA: tile_m = CM * (u / tiles_n) + rank
@@ -166,7 +270,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if constexpr (CM > 1) g2_cluster_sync();   // peer barriers are initialised before any remote arrive / commit
+  if (tr != nullptr && threadIdx.x == 0) tr[1] = clock64();
   pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (tr != nullptr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -195,14 +301,16 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
             tma_load_2d_2cta(sa + A_BYTES, &tmB, lead_full, kb * GEMM_BK, tile_n * BN + crank * (BN / CM));
             if (leader) mbar_expect_tx(&full_bar[stage], CM * (A_BYTES + B_BYTES));
           }
+          if (tr != nullptr && tile == unit0 && kb == 0) tr[3] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (tr != nullptr) tr[4] = clock64();
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CM, BN);
-      int stage = 0;
+      int stage = 0, tcount = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -210,6 +318,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (tr != nullptr && kb == 0 && tcount < 4) tr[8 + 4 * tcount] = clock64();
           tc_fence_after();
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
@@ -224,6 +333,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         }
         if constexpr (CM == 1) umma_commit(&tmem_full[acc]);
         else umma_commit_2cta(&tmem_full[acc]);
+        if (tr != nullptr && tcount < 4) tr[9 + 4 * tcount] = clock64();
+        ++tcount;
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -233,6 +344,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t stage_buf = epi_base + (warp - 2) * 4096;   // one 32-row x 128-byte staging tile per warp
     uint32_t acc = 0, acc_phase = 0;
+    int tcount = 0;
     for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
       const int tile_m = CM * (tile / tiles_n) + crank, tile_n = tile % tiles_n;
       const int m0 = tile_m * GEMM_BM + q * 32;
@@ -262,6 +374,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         };
         if (half < NCH) prefetch(half * SUB * 32);
         mbar_wait(&tmem_full[acc], acc_phase);
+        if (tr != nullptr && warp == 2 && lane == 0 && tcount < 4) tr[10 + 4 * tcount] = clock64();
         tc_fence_after();
 #pragma unroll 1
         for (int c = half; c < NCH; c += 2) {
@@ -285,9 +398,24 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
             for (int j = 0; j < 8; ++j) {
               v[4 * j] += bq[j].x; v[4 * j + 1] += bq[j].y; v[4 * j + 2] += bq[j].z; v[4 * j + 3] += bq[j].w;
             }
-            if constexpr (EPI == EPI_GELU_BF16) {
+            if constexpr (EPI == EPI_F32_POS) {   // + pos[(row / 2) % n_style]  (input projection)
+              const int mm = m < p.M ? m : p.M - 1;
+              const float4* pr = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>((mm >> 1) % p.n_style) * p.N + tile_n * BN + col);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+              for (int j = 0; j < 8; ++j) {
+                const float4 pq = __ldg(pr + j);
+                v[4 * j] += pq.x; v[4 * j + 1] += pq.y; v[4 * j + 2] += pq.z; v[4 * j + 3] += pq.w;
+              }
+            }
+            if constexpr (EPI == EPI_GELU_BF16) {
+              if (dbg & 8) {   // FMA-pipe stand-in of similar length (experiment)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  float x = v[j], y = x * x;
+                  y = fmaf(y, 0.044715f, 1.0f); y = y * x; y = fmaf(y, 0.7978845608f, 0.1f); y = fmaf(y, y, 0.3f); y = fmaf(y, x, 0.2f);
+                  v[j] = 0.5f * x * (1.0f + y);
+                }
+              }
             }
             if constexpr (EPI == EPI_GATE_RES) {
 #pragma unroll
@@ -302,7 +430,23 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
               __syncwarp();
             }
             const uint32_t sb = stage_buf + lane * 128;
-            if constexpr (g2_out_bf16<EPI>()) {
+            if (dbg & 4) {
+              if (v[0] == 1234.5f) st_shared_v4(sb, __float_as_uint(v[1]), 0u, 0u, 0u);
+            } else if constexpr (EPI == EPI_GELU_BF16) {
+              if (!(dbg & 10)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  st_shared_v4(sb + (((sub * 4 + j) ^ (lane & 7)) << 4), gelu_tanh_f16x2_to_bf16x2(v[8 * j], v[8 * j + 1]),
+                               gelu_tanh_f16x2_to_bf16x2(v[8 * j + 2], v[8 * j + 3]), gelu_tanh_f16x2_to_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                               gelu_tanh_f16x2_to_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  st_shared_v4(sb + (((sub * 4 + j) ^ (lane & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
+                               pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                               pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+              }
+            } else if constexpr (g2_out_bf16<EPI>()) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 st_shared_v4(sb + (((sub * 4 + j) ^ (lane & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
@@ -319,7 +463,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) {
             const int n0 = tile_n * BN + c * SUB * 32;
-            if (m0 < p.M) {
+            if (m0 < p.M && !(dbg & 1)) {
               if constexpr (EPI == EPI_GATE_RES) tma_reduce_add_2d(&tmC, stage_buf, n0, m0);
               else tma_store_2d(&tmC, stage_buf, n0, m0);
             }
@@ -347,9 +491,23 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_row32<EPI>(p, m, tile_n * BN + c * 32, v);
+          if constexpr (EPI == EPI_SAMPLER) {
+            const int n0 = tile_n * BN + c * 32;
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+            sampler_epilogue32(p, m0, n0, v, stage_buf, lane);
+          } else {
+            epilogue_row32<EPI>(p, m, tile_n * BN + c * 32, v);
+          }
         }
       }
+      if (tr != nullptr && warp == 2 && lane == 0 && tcount < 4) tr[11 + 4 * tcount] = clock64();
+      ++tcount;
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -357,6 +515,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (tr != nullptr && threadIdx.x == 0) tr[5] = clock64();
   if constexpr (CM > 1) g2_cluster_sync();   // the peer may still arrive on this CTA's barriers / read its operand stages
   if (warp == 1) {
     if constexpr (CM == 1) tmem_dealloc<TMEM_COLS>(tmem_base);

@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "gemm_ln.cuh"
+#include "gemm_ln2.cuh"
 #include "predictor.cuh"
 #include "stz_layout.h"
 
@@ -350,6 +351,22 @@ static int launch_gemmln(stz_handle* H, cudaStream_t st, const bf16* A, int lda,
   return 0;
 }
 
+// cluster-of-two variant (gemm_ln2.cuh): two CTAs per 128-row block, 256 columns each
+template <int MODE>
+static int launch_gemmln2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
+                          const GemmLnParams& p) {
+  CUtensorMap ta, tb, tu, th;
+  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
+      make_tmap(&tb, W, (uint64_t)GLN_N, (uint64_t)p.K, (uint64_t)p.K, GLN2_BN) ||
+      make_tmap_out(&th, p.h, false, (uint64_t)p.M, (uint64_t)GLN_N, (uint64_t)GLN_N) ||
+      make_tmap_out(&tu, u, true, (uint64_t)p.M, (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N)))
+    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (gemmln2 M=%d K=%d)", p.M, p.K);
+  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * GLN_N * p.K);
+  launch_kc(2, gemmln2_kernel<MODE>, 2 * cdiv(p.M, GEMM_BM), GLN_THREADS, GLN2_SMEM_BYTES, st, ta, tb, tu, th, p);
+  KCHECK(H);
+  return 0;
+}
+
 template <int BN, int EPI>
 static cudaError_t set_gemm2_attr() {
   cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
@@ -388,6 +405,8 @@ static cudaError_t init_kernel_attrs() {
   if ((e = set_gemm2_attrs<EPI_SAMPLER>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemmln2_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN2_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemmln2_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN2_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
@@ -862,6 +881,20 @@ extern "C" int stz_profile_read(stz_handle* H, int cls, double* ms, double* work
   return 0;
 }
 
+extern "C" int stz_debug_set_gemm_trace(stz_handle* H, long long* trace_dev) {
+  if (!H) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  CK(H, cudaMemcpyToSymbol(g_gemm_trace, &trace_dev, sizeof trace_dev));
+  return 0;
+}
+
+extern "C" int stz_debug_set_gemm_dbg(stz_handle* H, int flags) {
+  if (!H) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  CK(H, cudaMemcpyToSymbol(g_gemm_dbg, &flags, sizeof flags));
+  return 0;
+}
+
 extern "C" int stz_debug_set_att_trace(stz_handle* H, long long* trace_dev) {
   if (!H) return STZ_E_ARG;
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
@@ -981,6 +1014,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = Kc; p.bias = bias; p.gate_off = gate_off; p.shift_off = ln_off; p.scale_off = ln_off + d; p.split3 = last ? 1 : 0;
+      if (H->fuse_ln == 2) return launch_gemmln2<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
       return launch_gemmln<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
     }
     GemmParams p = base;
@@ -993,7 +1027,8 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.shift_off = 0; p.scale_off = d; p.split3 = 0;
-      RET(launch_gemmln<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
+      if (H->fuse_ln == 2) RET(launch_gemmln2<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
+      else RET(launch_gemmln<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
     } else {
       GemmParams p = base;
       p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = h; p.ldo = d; p.pos = W32(H, "pos");
