@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   } else {
     // 8 epilogue warps: warp w reads TMEM lane quadrant (w & 3) and every second column chunk, starting at `half`.
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const uint32_t stage_buf = epi_base + (warp - 2) * 4096;   // one 32-row x 128-byte staging tile per warp
+    const uint32_t stage_buf = epi_base + (warp - 2) * 4096;   // two 32-row x 64-byte staging tiles per warp
+    uint32_t tsel = 0;
     uint32_t acc = 0, acc_phase = 0;
     int tcount = 0;
     for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
@@ -361,18 +362,23 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         }
         // bias / gate of the NEXT sub-chunk are fetched while the current one is processed (and, for the first,
         // while the accumulator is still being produced): no dependent global latency inside the loop
-        float4 bq[8], gq[EPI == EPI_GATE_RES ? 8 : 1];
+        // The gate rows are per sequence (L2 latency, measured ~1.5 k cycles under load): they are fetched a whole
+        // chunk ahead into a second register set (gqn) at the top of the previous chunk.
+        float4 bq[8], gq[EPI == EPI_GATE_RES ? 8 : 1], gqn[EPI == EPI_GATE_RES ? 8 : 1];
         auto prefetch = [&](int col) {
           const int n0 = tile_n * BN + col;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             bq[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto prefetch_gate = [&](int col, float4 (&dst)[EPI == EPI_GATE_RES ? 8 : 1]) {
           if constexpr (EPI == EPI_GATE_RES) {
+            const int n0 = tile_n * BN + col;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gq[j] = __ldg(reinterpret_cast<const float4*>(gate + n0) + j);
+            for (int j = 0; j < 8; ++j) dst[j] = __ldg(reinterpret_cast<const float4*>(gate + n0) + j);
           }
         };
-        if (half < NCH) prefetch(half * SUB * 32);
+        if (half < NCH) { prefetch(half * SUB * 32); prefetch_gate(half * SUB * 32, gq); }
         mbar_wait(&tmem_full[acc], acc_phase);
         if (tr != nullptr && warp == 2 && lane == 0 && tcount < 4) tr[10 + 4 * tcount] = clock64();
         tc_fence_after();
@@ -381,6 +387,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
 #pragma unroll
           for (int sub = 0; sub < SUB; ++sub) {
             const int col = (c * SUB + sub) * 32;
+            if (EPI == EPI_GATE_RES && c + 2 < NCH) prefetch_gate((c + 2) * SUB * 32, gqn);
+            const bool trc = tr != nullptr && warp == 2 && lane == 0 && tcount == 0 && c < 4 && sub == 0;
+            long long* te = tr + 32 + (c >> 1) * 8;
+            if (trc) te[0] = clock64();
             float v[32];
             {
               uint32_t r[32];
@@ -389,6 +399,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             }
+            if (trc) te[1] = clock64();
             if (c + 2 >= NCH && sub == SUB - 1) {  // this warp's last read of the accumulator: hand it back
               tc_fence_before();
               __syncwarp();
@@ -407,16 +418,6 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
                 v[4 * j] += pq.x; v[4 * j + 1] += pq.y; v[4 * j + 2] += pq.z; v[4 * j + 3] += pq.w;
               }
             }
-            if constexpr (EPI == EPI_GELU_BF16) {
-              if (dbg & 8) {   // FMA-pipe stand-in of similar length (experiment)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  float x = v[j], y = x * x;
-                  y = fmaf(y, 0.044715f, 1.0f); y = y * x; y = fmaf(y, 0.7978845608f, 0.1f); y = fmaf(y, y, 0.3f); y = fmaf(y, x, 0.2f);
-                  v[j] = 0.5f * x * (1.0f + y);
-                }
-              }
-            }
             if constexpr (EPI == EPI_GATE_RES) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -425,49 +426,57 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
             }
             if (sub + 1 < SUB) prefetch(col + 32);
             else if (c + 2 < NCH) prefetch((c + 2) * SUB * 32);
-            if (sub == 0) {  // the staging tile must have been drained by this warp's previous TMA store
-              if (lane == 0) bulk_wait_read<0>();
+            // Two 2 KB staging tiles per warp (32 rows x 64 bytes, 64B-swizzled: 32 bf16 or 16 fp32 columns), used
+            // alternately: before a tile is rewritten only the store issued two pieces ago has to have been read out,
+            // so the TMA store of one piece overlaps the arithmetic of the next (a single tile serialised every
+            // chunk on the ~0.5 us read-out of its predecessor).
+            constexpr int PIECES = g2_out_bf16<EPI>() ? 1 : 2;
+#pragma unroll
+            for (int pc = 0; pc < PIECES; ++pc) {
+              if (trc && pc == 0) te[2] = clock64();
+              if (lane == 0) bulk_wait_read<1>();
               __syncwarp();
-            }
-            const uint32_t sb = stage_buf + lane * 128;
-            if (dbg & 4) {
-              if (v[0] == 1234.5f) st_shared_v4(sb, __float_as_uint(v[1]), 0u, 0u, 0u);
-            } else if constexpr (EPI == EPI_GELU_BF16) {
-              if (!(dbg & 10)) {
+              if (trc && pc == 0) te[3] = clock64();
+              const uint32_t tile = stage_buf + tsel * 2048;
+              const uint32_t sb = tile + lane * 64, sw = (lane >> 1) & 3;
+              if (dbg & 4) {
+                if (v[0] == 1234.5f) st_shared_v4(sb, __float_as_uint(v[1]), 0u, 0u, 0u);
+              } else if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  st_shared_v4(sb + (((sub * 4 + j) ^ (lane & 7)) << 4), gelu_tanh_f16x2_to_bf16x2(v[8 * j], v[8 * j + 1]),
+                  st_shared_v4(sb + ((j ^ sw) << 4), gelu_tanh_f16x2_to_bf16x2(v[8 * j], v[8 * j + 1]),
                                gelu_tanh_f16x2_to_bf16x2(v[8 * j + 2], v[8 * j + 3]), gelu_tanh_f16x2_to_bf16x2(v[8 * j + 4], v[8 * j + 5]),
                                gelu_tanh_f16x2_to_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              } else if constexpr (g2_out_bf16<EPI>()) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  st_shared_v4(sb + ((j ^ sw) << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  st_shared_v4(sb + (((sub * 4 + j) ^ (lane & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
-                               pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                               pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                  st_shared_v4(sb + ((j ^ sw) << 4), __float_as_uint(v[pc * 16 + 4 * j]), __float_as_uint(v[pc * 16 + 4 * j + 1]),
+                               __float_as_uint(v[pc * 16 + 4 * j + 2]), __float_as_uint(v[pc * 16 + 4 * j + 3]));
               }
-            } else if constexpr (g2_out_bf16<EPI>()) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                st_shared_v4(sb + (((sub * 4 + j) ^ (lane & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
-                             pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                             pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                st_shared_v4(sb + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                             __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+              if (trc && pc == 0) te[4] = clock64();
+              fence_proxy_async();
+              __syncwarp();
+              if (trc && pc == 0) te[5] = clock64();
+              if (lane == 0) {
+                const int n0 = tile_n * BN + col + pc * 16;
+                if (m0 < p.M && !(dbg & 1)) {
+                  if constexpr (EPI == EPI_GATE_RES) tma_reduce_add_2d(&tmC, tile, n0, m0);
+                  else tma_store_2d(&tmC, tile, n0, m0);
+                }
+                bulk_commit();
+              }
+              if (trc && pc == 0) te[6] = clock64();
+              tsel ^= 1u;
             }
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            const int n0 = tile_n * BN + c * SUB * 32;
-            if (m0 < p.M && !(dbg & 1)) {
-              if constexpr (EPI == EPI_GATE_RES) tma_reduce_add_2d(&tmC, stage_buf, n0, m0);
-              else tma_store_2d(&tmC, stage_buf, n0, m0);
-            }
-            bulk_commit();
+          if constexpr (EPI == EPI_GATE_RES) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gq[j] = gqn[j];
           }
         }
         if (half >= NCH) {  // (never with NCH >= 2; keeps the barrier count right for any tile shape)

@@ -234,16 +234,17 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t c
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-// Output map of the staged epilogues: row-major [rows, cols], row stride ld (elements), box = 32 rows x 128 bytes
-// (32 fp32 or 64 bf16 columns), 128B swizzle.  Rows >= `rows` are clipped by the TMA unit.
-static int make_tmap_out(CUtensorMap* m, void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld) {
+// Output map of the staged epilogues: row-major [rows, cols], row stride ld (elements), box = 32 rows x row_bytes
+// (128 B, 128B swizzle: gemm_ln kernels; 64 B, 64B swizzle: gemm2's double-buffered staging).  Rows >= `rows` are
+// clipped by the TMA unit.
+static int make_tmap_out(CUtensorMap* m, void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, int row_bytes = 128) {
   const uint64_t es = is_bf16 ? 2 : 4;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {ld * es};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / es), 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
@@ -309,7 +310,7 @@ static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int ld
   if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
       make_tmap(&tb, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, pair ? BN / 2 : BN))
     return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", p.M, p.N, p.K);
-  if (g2_staged<EPI>() && make_tmap_out(&tc, p.out, g2_out_bf16<EPI>(), (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo))
+  if (g2_staged<EPI>() && make_tmap_out(&tc, p.out, g2_out_bf16<EPI>(), (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 64))
     return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (output) failed (M=%d N=%d ldo=%d)", p.M, p.N, p.ldo);
   ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * p.N * p.K);
   if (pair) {

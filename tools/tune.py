@@ -44,3 +44,11 @@ for name, N, K, epi in [("qkv", 1536, 512, 2), ("attn_out", 512, 512, 4), ("q_cr
         out[cl] = (round(us, 2), round(2.0 * R * N * K / us * 1e-6, 1))
     path.set_option("gemm_cluster", 0)
     print(name, "M", R, "N", N, "K", K, "cluster:", out[1], "no cluster:", out[0], "(us, TFLOP/s)", flush=True)
+for bn in (128, 256):
+    path.set_option("gemm_bn", bn)
+    for name, N, K, epi in [("attn_out", 512, 512, 4), ("q_cross", 512, 512, 2), ("ffn2", 512, 2048, 4)]:
+        R = 2 * B * cfg.n_style
+        us = path.bench_gemm(R, N, K, epi, 50)
+        print("gemm_bn", bn, name, round(us, 2), "us", flush=True)
+    print("gemm_bn", bn, "sample_style ms", round(timeit(samp), 3), flush=True)
+path.set_option("gemm_bn", 0)
