@@ -142,6 +142,15 @@ int stz_debug_max_lstm_clusters(void);
 int stz_op_gemm_bf16(const void* A_bf16_dev, const void* W_bf16_dev, const float* bias_dev,
                      float* C_dev, int M, int N, int K, int impl, int device, void* cuda_stream);
 
+/* Unit-test entry for the fused attention kernels (bf16 device buffers).  Self-attention when kv_text == NULL:
+ * qkv [2*B*K, 3*d_model] in the denoiser's row layout (row = (b*K + k)*2 + branch), ldq = 3*d_model.  Otherwise
+ * cross-attention: queries = first d_model columns of qkv (row stride ldq); keys [text ; prompt (conditional rows only)
+ * | null prompt (unconditional rows only)], each K/V buffer holding K | V (2*d_model columns) per row.
+ * out [2*B*K, d_model].  impl: 0 tcgen05 + TMA, 1 mma.sync resident keys, 2 mma.sync streaming, 3 tcgen05 + cp.async. */
+int stz_op_attention(stz_handle* h, const void* qkv_dev, int ldq, const void* kv_text_dev, const void* kv_prompt_dev,
+                     const void* kv_null_dev, const uint8_t* text_mask_dev, const uint8_t* prompt_mask_dev, int B,
+                     int T, int P, void* out_dev, int impl, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

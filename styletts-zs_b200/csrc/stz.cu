@@ -1427,6 +1427,40 @@ extern "C" int stz_op_gemm_bf16(const void* A, const void* W, const float* bias,
   return rc;
 }
 
+// Unit-test entry for the fused attention kernels.  Self-attention (kv_text == NULL): qkv [2*B*K, 3d] bf16 in R layout.
+// Cross-attention: q = first d columns of `qkv` with row stride ldq, keys = [text ; prompt | null] with one layer's
+// K | V per row: kv_text [B*T, 2d], kv_prompt [B*P, 2d], kv_null [1, 2d].  out [2*B*K, d] bf16.
+// impl: 0 tcgen05 + TMA, 1 mma.sync resident keys, 2 mma.sync streaming, 3 tcgen05 + cp.async.
+extern "C" int stz_op_attention(stz_handle* H, const void* qkv, int ldq, const void* kv_text, const void* kv_prompt,
+                                const void* kv_null, const uint8_t* tmask, const uint8_t* pmask, int B, int T, int P,
+                                void* out, int impl, void* cuda_stream) {
+  if (!H || !qkv || !out || B < 1) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  const stz_config& c = H->cfg;
+  const int d = c.d_model, K = c.n_style;
+  const bf16* q = (const bf16*)qkv;
+  AttnParams ap{};
+  ap.q = q; ap.ldq = ldq; ap.out = (bf16*)out; ap.ldo = d; ap.n_q = 2 * K;
+  ap.scale_log2 = 1.4426950408889634f / sqrtf((float)(d / c.n_heads));
+  if (!kv_text) {
+    ap.nseg = 1;
+    ap.seg[0] = AttnSeg{q + d, q + 2 * d, ldq, 2 * K, 2 * K, nullptr, KEY_SAME_BRANCH};
+  } else {
+    if (!kv_prompt || !kv_null || T < 1 || P < 1) return fail(H, STZ_E_ARG, "cross-attention needs text, prompt and null K/V");
+    const bf16 *kt = (const bf16*)kv_text, *kp = (const bf16*)kv_prompt, *kn = (const bf16*)kv_null;
+    ap.nseg = 3;
+    ap.seg[0] = AttnSeg{kt, kt + d, 2 * d, T, T, tmask, KEY_ALL};
+    ap.seg[1] = AttnSeg{kp, kp + d, 2 * d, P, P, pmask, KEY_COND};
+    ap.seg[2] = AttnSeg{kn, kn + d, 2 * d, 1, 0, nullptr, KEY_UNCOND};
+  }
+  const int saved = H->attn_impl;
+  H->attn_impl = impl;
+  const int rc = attention(H, (cudaStream_t)cuda_stream, ap, B);
+  H->attn_impl = saved;
+  H->cur_launches = 0;
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------------
 // bench.py roofline leg: one GEMM shape of the denoiser, `iters` back-to-back launches on the handle's
 // stream between two CUDA events (PDL-chained exactly like the evaluation loop), average microseconds.

@@ -84,6 +84,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_debug_set_gemm_trace.argtypes = [vp, vp]
     lib.stz_debug_set_att_trace.restype = i32
     lib.stz_debug_set_att_trace.argtypes = [vp, vp]
+    lib.stz_op_attention.restype = i32
+    lib.stz_op_attention.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]
     lib.stz_op_gemm_bf16.restype = i32
     lib.stz_op_gemm_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     if lib.stz_abi_version() != ABI_VERSION:
@@ -97,7 +99,7 @@ EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
                     "stz_synthesize_host", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
-                    "stz_op_gemm_bf16")
+                    "stz_op_gemm_bf16", "stz_op_attention")
 
 
 def _kind(sampler) -> int:
@@ -176,6 +178,25 @@ class StyleTTSZSPath:
         us = C.c_double()
         self._check(self.lib.stz_bench_gemm(self._h, M, N, K, epi, iters, C.byref(us)), "stz_bench_gemm")
         return us.value
+
+    def op_attention(self, qkv: torch.Tensor, kv_text=None, kv_prompt=None, kv_null=None, text_mask=None,
+                     prompt_mask=None, impl: int = 0) -> torch.Tensor:
+        """Unit-test entry: the fused attention kernels on bf16 CUDA buffers (see include/stz.h: stz_op_attention)."""
+        d, K = self.cfg.d_model, self.cfg.n_style
+        R, ldq = qkv.shape
+        B = R // (2 * K)
+        T = 0 if kv_text is None else kv_text.shape[0] // B
+        P = 0 if kv_prompt is None else kv_prompt.shape[0] // B
+        out = torch.empty(R, d, dtype=torch.bfloat16, device=qkv.device)
+        tm, pm = self._mask(text_mask), self._mask(prompt_mask)     # kept alive until the launch is enqueued
+        st = torch.cuda.current_stream().cuda_stream
+        self._check(self.lib.stz_op_attention(self._h, _ptr(qkv), ldq, _ptr(kv_text), _ptr(kv_prompt), _ptr(kv_null),
+                                              _ptr(tm), _ptr(pm), B, T, P, _ptr(out), impl, C.c_void_p(st)),
+                    "stz_op_attention")
+        for t in (tm, pm):
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream())
+        return out
 
     def set_tap(self, ev: int, layer: int, stage: int, buf: Optional[torch.Tensor]):
         self._check(self.lib.stz_debug_set_tap(self._h, ev, layer, stage, _ptr(buf)), "set_tap")

@@ -149,6 +149,56 @@ def test_variable_length_masks_vs_oracle(path, oracle):
 
 
 # ---------------------------------------------------------------------------------------------
+# fused attention kernels vs a plain PyTorch fp32 reference of the same op (bf16 inputs, bf16 output rounding)
+# ---------------------------------------------------------------------------------------------
+def _attention_reference(q, k, v, vis):
+    """q [Rq, H, 64], k/v [Rk, H, 64] fp32, vis [Rq, Rk] bool -> [Rq, H*64]"""
+    s = torch.einsum("qhd,khd->hqk", q, k) / 8.0
+    s = s.masked_fill(~vis[None], float("-inf"))
+    return torch.einsum("hqk,khd->qhd", torch.softmax(s, -1), v).reshape(q.shape[0], -1)
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["tcgen05_tma", "mma_resident", "mma_streaming", "tcgen05_cpasync"])
+@pytest.mark.parametrize("B", [1, 5])
+def test_self_attention_vs_torch_fp32(path, impl, B):
+    d, K, H = CFG.d_model, CFG.n_style, CFG.n_heads
+    g = torch.Generator().manual_seed(10 + B)
+    qkv = torch.randn(2 * B * K, 3 * d, generator=g).bfloat16().cuda()
+    out = path.op_attention(qkv, impl=impl).float().cpu()
+    x = qkv.float().cpu().view(B, K, 2, 3, H, 64)
+    for b in range(B):
+        for br in range(2):
+            q, k, v = (x[b, :, br, i] for i in range(3))
+            ref = _attention_reference(q, k, v, torch.ones(K, K, dtype=torch.bool))
+            got = out.view(B, K, 2, d)[b, :, br]
+            assert rel(got, ref) < 2e-2, (b, br)     # bf16 P and bf16 output rounding
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["tcgen05_tma", "mma_resident", "mma_streaming", "tcgen05_cpasync"])
+@pytest.mark.parametrize("T,P", [(64, 50), (13, 50), (40, 7)])
+def test_cross_attention_vs_torch_fp32(path, impl, T, P):
+    d, K, H, B = CFG.d_model, CFG.n_style, CFG.n_heads, 3
+    g = torch.Generator().manual_seed(100 + T)
+    q = torch.randn(2 * B * K, d, generator=g).bfloat16().cuda()
+    kt = torch.randn(B * T, 2 * d, generator=g).bfloat16().cuda()
+    kp = torch.randn(B * P, 2 * d, generator=g).bfloat16().cuda()
+    kn = torch.randn(1, 2 * d, generator=g).bfloat16().cuda()
+    tlen = torch.tensor([T, max(1, T // 2), max(1, T - 3)])
+    tm = torch.arange(T)[None] < tlen[:, None]
+    pm = torch.ones(B, P, dtype=torch.bool)
+    pm[1, P // 2:] = False
+    out = path.op_attention(q, kt, kp, kn, text_mask=tm, prompt_mask=pm, impl=impl).float().cpu()
+    qf = q.float().cpu().view(B, K, 2, H, 64)
+    for b in range(B):
+        kv = lambda t, n: t.float().cpu().view(-1, n, 2, H, 64)
+        keys = torch.cat([kv(kt, T)[b], kv(kp, P)[b], kn.float().cpu().view(1, 2, H, 64)], 0)     # [T+P+1, 2, H, 64]
+        for br in range(2):
+            vis = torch.cat([tm[b], pm[b] & (br == 0), torch.tensor([br == 1])])
+            ref = _attention_reference(qf[b, :, br], keys[:, 0], keys[:, 1], vis[None].expand(K, -1))
+            assert rel(out.view(B, K, 2, d)[b, :, br], ref) < 2e-2, (b, br)
+
+
+# ---------------------------------------------------------------------------------------------
 # full-size properties (BASELINE configs[1] = cfg2 and configs[3] = cfg4 shapes)
 # ---------------------------------------------------------------------------------------------
 def test_cfg2_full_size_properties(path):
