@@ -103,7 +103,7 @@ int stz_synthesize_host(stz_handle* h, const float* text_emb, const uint8_t* tex
 int64_t stz_launch_count(const stz_handle* h);
 
 /* Knobs: "use_graph" (0/1, default 1), "gemm_impl" (0 = tcgen05 persistent v2, 1 = SIMT cross-check kernel, 2 = tcgen05 v1),
- * "lstm_impl" (0 = cluster kernel, 1 = generic), "pred_gemm_impl" (0 = split-bf16 tcgen05,
+ * "lstm_impl" (0 = tcgen05 cluster kernel, 1 = generic, 2 = fp32 FFMA cluster kernel), "pred_gemm_impl" (0 = split-bf16 tcgen05,
  * 1 = fp32 CUDA cores), "use_pdl" (0/1 programmatic dependent launch, process-wide), "profile" (0/1, see stz_profile_read).  Returns STZ_E_ARG for
  * unknown keys. */
 int stz_set_option(stz_handle* h, const char* key, int value);
@@ -121,6 +121,9 @@ int stz_profile_read(stz_handle* h, int kernel_class, double* ms, double* work, 
  * self-attention / cross-attention / FFN sub-layer, layer == n_layers -> the guided F.
  * tap_dev = NULL disables. */
 int stz_debug_set_tap(stz_handle* h, int eval, int layer, int stage, float* tap_dev);
+
+/* Debug timeline of the tcgen05 BiLSTM recurrence kernel: int64 [64 steps][8] (see predictor_tc.cuh; tools/lstm_trace.py). */
+int stz_debug_set_lstm_trace(stz_handle* h, long long* trace_dev);
 
 /* Debug timeline of the tcgen05 attention kernel: trace_dev = int64 [CTAs][16] device buffer (NULL disables); thread 0
  * of every CTA stores clock64() at its phase boundaries (tools/att_trace.py). */

@@ -22,6 +22,7 @@
 #include "gemm_ln.cuh"
 #include "gemm_ln2.cuh"
 #include "predictor.cuh"
+#include "predictor_tc.cuh"
 #include "stz_layout.h"
 
 using namespace stz;
@@ -412,6 +413,7 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<10>())) != cudaSuccess) return e;
@@ -896,6 +898,13 @@ extern "C" int stz_debug_set_gemm_dbg(stz_handle* H, int flags) {
   return 0;
 }
 
+extern "C" int stz_debug_set_lstm_trace(stz_handle* H, long long* trace_dev) {
+  if (!H) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  CK(H, cudaMemcpyToSymbol(g_lstm_trace, &trace_dev, sizeof trace_dev));
+  return 0;
+}
+
 extern "C" int stz_debug_set_att_trace(stz_handle* H, long long* trace_dev) {
   if (!H) return STZ_E_ARG;
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
@@ -1291,7 +1300,10 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     float* xo = bufs[l & 1];
     {
       ProfScope ps(H, st, PC_LSTM, 2.0 * BT * 2.0 * h * 4.0 * h);
-      if (h == LC_H && H->lstm_impl == 0) {  // product path: register-resident W_hh, cluster of 8 CTAs, DSMEM exchange
+      if (h == LC_H && H->lstm_impl == 0) {  // product path: recurrent product on tcgen05 (split-bf16), cluster of 8 CTAs, DSMEM exchange
+        const float* whh = H->whh + (size_t)l * 2 * 4 * h * h;
+        launch_k(lstm_tc_kernel, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, w.G, whh, w.lens, w.perm, xo, B, T);
+      } else if (h == LC_H && H->lstm_impl == 2) {  // fp32 FFMA form: register-resident W_hh, cluster of 8 CTAs, DSMEM exchange
         // sequences per cluster: fewest waves of co-resident clusters, then least work per step
         int best = 8;
         double best_cost = 1e30;

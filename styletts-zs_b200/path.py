@@ -80,6 +80,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_debug_max_lstm_clusters.argtypes = []
     lib.stz_debug_set_tap.restype = i32
     lib.stz_debug_set_tap.argtypes = [vp, i32, i32, i32, vp]
+    lib.stz_debug_set_lstm_trace.restype = i32
+    lib.stz_debug_set_lstm_trace.argtypes = [vp, vp]
     lib.stz_debug_set_gemm_trace.restype = i32
     lib.stz_debug_set_gemm_trace.argtypes = [vp, vp]
     lib.stz_debug_set_att_trace.restype = i32
@@ -98,7 +100,7 @@ def load_library(path: Optional[str] = None):
 EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
                     "stz_synthesize_host", "stz_launch_count", "stz_set_option", "stz_profile_read",
-                    "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
+                    "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16", "stz_op_attention")
 
 
