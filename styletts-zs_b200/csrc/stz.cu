@@ -34,7 +34,8 @@ static std::string g_create_error;
 // handle
 // ------------------------------------------------------------------------------------------
 struct Workspace {
-  int B = 0, T = 0, P = 0, E = 0, noise_slices = 0;
+  int B = 0, T = 0, P = 0, E = 0, noise_slices = 0, mod_evals = 0;
+  bool mod_hoisted = false;   // this call's AdaLN modulations of ALL evaluations live in `mod` ([E][2B][n_mod])
   char* base = nullptr;
   size_t bytes = 0;
   // conditioning
@@ -54,6 +55,10 @@ struct Workspace {
 };
 
 constexpr int STZ_MAX_CHAINS = 8;
+// The sigma schedule is known before the loop, so the AdaLN modulations c[e] · Wmod^T of every evaluation can be one GEMM
+// (M = E * 2B) instead of E small ones at the head of each evaluation's dependency chain.  E * 2B * n_mod floats: 78 MB at
+// cfg2 (E = 4); the 64-evaluation teacher keeps the per-evaluation GEMM.
+constexpr int STZ_HOIST_MOD_MAX_EVALS = 8;
 
 struct stz_handle {
   stz_config cfg;
@@ -292,7 +297,9 @@ static int pick_bn(int M, int N) {
   for (int bn : {256, 192, 128}) {
     if (N % bn) continue;
     const long tiles = (long)(N / bn) * cdiv(M, GEMM_BM);
-    const long cost = (long)cdiv(tiles, g_num_sms) * bn;
+    // rounds of tiles x (columns per tile + a per-tile overhead worth ~64 columns: prologue / exposed epilogue; measured
+    // on the context K/V GEMM, M 7296 x N 8192: BN 256 52 us vs BN 128 75 us although BN 128 needs fewer column-rounds)
+    const long cost = (long)cdiv(tiles, g_num_sms) * (bn + 64);
     if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
   }
   return best;
@@ -503,13 +510,15 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise_slices) {
   Workspace& w = H->ws;
-  if (w.base && B <= w.B && T <= w.T && P <= w.P && E <= w.E && noise_slices <= w.noise_slices) return 0;
+  const int mod_evals_req = E <= STZ_HOIST_MOD_MAX_EVALS ? E : 1;
+  if (w.base && B <= w.B && T <= w.T && P <= w.P && E <= w.E && noise_slices <= w.noise_slices && mod_evals_req <= w.mod_evals) return 0;
   // grow monotonically; all cached graphs point into the old arena
   for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
   H->graphs.clear();
   if (w.base) { CK(H, cudaDeviceSynchronize()); CK(H, cudaFree(w.base)); w.base = nullptr; }
   B = B > w.B ? B : w.B; T = T > w.T ? T : w.T; P = P > w.P ? P : w.P; E = E > w.E ? E : w.E;
   noise_slices = noise_slices > w.noise_slices ? noise_slices : w.noise_slices;
+  const int mod_evals = mod_evals_req > w.mod_evals ? mod_evals_req : w.mod_evals;
   const stz_config& c = H->cfg;
   const size_t d = c.d_model, Ds = c.d_style, L = c.n_layers, K = c.n_style, n_mod = (9 * L + 2) * d;
   const size_t BT = (size_t)B * T, BP = (size_t)B * P, BK = (size_t)B * K, R = 2 * BK, NS = 2 * (size_t)B;
@@ -529,7 +538,8 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   WANT(ctx_pre, (BT + BP) * d, float);
   WANT(tfeat, (size_t)E * c.d_time, float); WANT(t1, (size_t)E * d, float); WANT(temb, (size_t)E * d, float);
   WANT(coef, (size_t)E * 8, float);
-  WANT(mod, NS * n_mod, float); WANT(x, BK * Ds, float); WANT(xmid, BK * Ds, float); WANT(h, R * d, float);
+  WANT(mod, (size_t)mod_evals * NS * n_mod, float);   // few-step samplers: every evaluation's modulations at once
+  WANT(x, BK * Ds, float); WANT(xmid, BK * Ds, float); WANT(h, R * d, float);
   WANT(noise, (size_t)noise_slices * BK * Ds, float);
   WANT(xin, R * 3 * Ds, bf16); WANT(u, R * d, bf16); WANT(u3, R * 3 * d, bf16); WANT(qkv, R * 3 * d, bf16); WANT(att, R * d, bf16);
   WANT(ffh, R * c.d_ff, bf16);
@@ -550,7 +560,7 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
     return fail(H, STZ_E_NOMEM, "workspace of %zu bytes: %s", off, cudaGetErrorString(e));
   }
   for (auto& pr : plan) *pr.first = w.base + pr.second;
-  w.bytes = off; w.B = B; w.T = T; w.P = P; w.E = E; w.noise_slices = noise_slices;
+  w.bytes = off; w.B = B; w.T = T; w.P = P; w.E = E; w.noise_slices = noise_slices; w.mod_evals = mod_evals;
   CK(H, cudaMemsetAsync(w.cvec, 0, ((size_t)E * NS * d + 128 * d) * sizeof(bf16), H->stream));
   CK(H, cudaStreamSynchronize(H->stream));
   return 0;
@@ -1011,7 +1021,10 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   // ablation bits: 1 self-attn, 2 cross-attn, 4 ln_mod, 8 qkv, 16 attention out-projections, 32 q2, 64 ff1, 128 ff2, 256 mod
   const int ab = H->ablate;
 
-  if (!(ab & 256)) {  // AdaLN modulations of this eval: mod[NS, n_mod] = c[e] · Wmod^T + b
+  if (w.mod_hoisted) {   // all evaluations' modulations were computed by one GEMM before the loop (sample_style_impl)
+    mod = w.mod + ((size_t)e * 2 * Btot + s0) * n_mod;
+    base.mod = mod;
+  } else if (!(ab & 256)) {  // AdaLN modulations of this eval: mod[NS, n_mod] = c[e] · Wmod^T + b
     GemmParams p = base;
     p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * 2 * Btot + (int)s0; p.bias = W32(H, "mod.b"); p.out = mod; p.ldo = n_mod;
     RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
@@ -1143,6 +1156,13 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
   launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
+  w.mod_hoisted = E <= STZ_HOIST_MOD_MAX_EVALS && !(H->ablate & 256);
+  if (w.mod_hoisted) {   // AdaLN modulations of every evaluation: mod[E * NS, n_mod] = c · Wmod^T + b
+    const int n_mod = (9 * L + 2) * d;
+    GemmParams p{};
+    p.M = E * NS; p.N = n_mod; p.K = d; p.bias = W32(H, "mod.b"); p.out = w.mod; p.ldo = n_mod;
+    RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
+  }
   {
     GemmParams p{};
     p.M = B * P; p.N = d; p.K = c.d_prompt; p.bias = H->ctx_prompt_b; p.out = w.ctx_pre + (size_t)B * T * d; p.ldo = d;
