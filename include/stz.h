@@ -89,6 +89,15 @@ int stz_predict_duration(stz_handle* h, const float* text_emb_dev, const uint8_t
                          const float* style_dev, int B, int T, int32_t* out_dur_dev,
                          float* out_presum_dev, void* cuda_stream);
 
+/* Length regulator — the step right after predict_duration: expands per-token features by the
+ * integer durations, on device (the prefix sum of the durations never leaves the GPU).
+ *   feats_dev [B,T,C] fp32 (C % 4 == 0, T <= 1024), dur_dev [B,T] int32 (entries <= 0 contribute no frame),
+ *   out_frames_dev [B,F_max,C]: frame f of utterance b = feats[b, tok(f)], tok(f) = first token whose cumulative duration
+ *   exceeds f; frames past the utterance's total are zeros; totals beyond F_max are truncated;
+ *   out_frame_lens_dev [B] = min(sum of durations, F_max); out_frame_tok_dev [B,F_max] (optional, may be NULL) = tok(f) or -1. */
+int stz_regulate_length(stz_handle* h, const float* feats_dev, const int32_t* dur_dev, int B, int T, int C, int F_max,
+                        float* out_frames_dev, int32_t* out_frame_lens_dev, int32_t* out_frame_tok_dev, void* cuda_stream);
+
 /* Host-buffer form of the whole path (what a non-CUDA caller binds): copies the inputs H2D,
  * runs sample_style and (if out_dur_host != NULL) predict_duration on the sampled codes, copies
  * the results D2H and synchronises.  All pointers are host pointers. */

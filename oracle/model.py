@@ -213,6 +213,23 @@ class OraclePath:
         return self._lstm
 
     @torch.no_grad()
+    def regulate_length(self, feats, durations, *, max_frames=None, return_tokens=False):
+        """Length regulator: torch.repeat_interleave per utterance, zero-padded to max_frames
+        (default max_dur * T), totals truncated at max_frames.  -> (frames [B,F,C], frame_lens [B] int32[, frame_tok])."""
+        feats, durations = feats.float(), durations.to(torch.int64).clamp(min=0)
+        B, T, Cc = feats.shape
+        F_max = int(max_frames) if max_frames is not None else self.cfg.max_dur * T
+        frames = torch.zeros(B, F_max, Cc)
+        tok = torch.full((B, F_max), -1, dtype=torch.int32)
+        lens = torch.zeros(B, dtype=torch.int32)
+        for b in range(B):
+            idx = torch.repeat_interleave(torch.arange(T), durations[b])[:F_max]
+            frames[b, :idx.numel()] = feats[b, idx]
+            tok[b, :idx.numel()] = idx.to(torch.int32)
+            lens[b] = idx.numel()
+        return (frames, lens, tok) if return_tokens else (frames, lens)
+
+    @torch.no_grad()
     def style_per_token(self, text_emb, style_codes):
         """a-8: s_tok = MHA(q = text, kv = style codes), n_sp_heads heads."""
         W, cfg = self.W, self.cfg

@@ -23,6 +23,7 @@
 #include "gemm_ln2.cuh"
 #include "predictor.cuh"
 #include "predictor_tc.cuh"
+#include "regulator.cuh"
 #include "stz_layout.h"
 
 using namespace stz;
@@ -1388,6 +1389,27 @@ extern "C" int stz_predict_duration(stz_handle* H, const float* text_emb_dev, co
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   return predict_duration_impl(H, text_emb_dev, text_mask_dev, style_dev, B, T, out_dur_dev, out_presum_dev,
                                (cudaStream_t)cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// length regulator: the step right after predict_duration
+// ------------------------------------------------------------------------------------------
+extern "C" int stz_regulate_length(stz_handle* H, const float* feats_dev, const int32_t* dur_dev, int B, int T, int C, int F_max,
+                                   float* out_frames_dev, int32_t* out_frame_lens_dev, int32_t* out_frame_tok_dev,
+                                   void* cuda_stream) {
+  if (!H) return STZ_E_ARG;
+  if (!feats_dev || !dur_dev || !out_frames_dev || !out_frame_lens_dev) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (B < 1 || T < 1 || F_max < 1) return fail(H, STZ_E_ARG, "bad sizes B=%d T=%d F_max=%d", B, T, F_max);
+  if (T > LR_MAX_T || C < 4 || C % 4) return fail(H, STZ_E_SHAPE, "length regulator supports T <= %d, C %% 4 == 0", LR_MAX_T);
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  H->cur_launches = 0;
+  launch_k(length_regulate_kernel, dim3(cdiv(F_max, LR_FRAMES), B), LR_THREADS, 0, st, feats_dev, dur_dev, out_frames_dev,
+           out_frame_lens_dev, out_frame_tok_dev, T, C, F_max);
+  KCHECK(H);
+  H->launches += H->cur_launches;
+  H->cur_launches = 0;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------

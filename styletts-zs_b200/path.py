@@ -66,6 +66,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_sample_style.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
     lib.stz_predict_duration.restype = i32
     lib.stz_predict_duration.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    lib.stz_regulate_length.restype = i32
+    lib.stz_regulate_length.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.stz_synthesize_host.restype = i32
     lib.stz_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
     lib.stz_launch_count.restype = i64
@@ -99,7 +101,7 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
-                    "stz_synthesize_host", "stz_launch_count", "stz_set_option", "stz_profile_read",
+                    "stz_synthesize_host", "stz_regulate_length", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16", "stz_op_attention")
 
@@ -253,6 +255,24 @@ class StyleTTSZSPath:
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream())
         return (out, pre) if return_presum else out
+
+    def regulate_length(self, feats, durations, *, max_frames: Optional[int] = None, return_tokens: bool = False):
+        """Length regulator: frames[b, f] = feats[b, token of frame f] for the integer durations of predict_duration.
+        -> (frames [B,F,C] fp32, frame_lens [B] int32[, frame_tok [B,F] int32]); F = max_frames or max_dur * T."""
+        B, T, Cc = feats.shape
+        F_max = int(max_frames) if max_frames is not None else self.cfg.max_dur * T
+        with torch.cuda.device(self.device):
+            ft, du = self._dev(feats, torch.float32), self._dev(durations, torch.int32)
+            frames = torch.empty(B, F_max, Cc, dtype=torch.float32, device=self.device)
+            lens = torch.empty(B, dtype=torch.int32, device=self.device)
+            tok = torch.empty(B, F_max, dtype=torch.int32, device=self.device) if return_tokens else None
+            st = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.stz_regulate_length(self._h, _ptr(ft), _ptr(du), B, T, Cc, F_max, _ptr(frames), _ptr(lens),
+                                              _ptr(tok), C.c_void_p(st))
+            self._check(rc, "stz_regulate_length")
+            for t in (ft, du):
+                t.record_stream(torch.cuda.current_stream())
+        return (frames, lens, tok) if return_tokens else (frames, lens)
 
     def synthesize_host(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
                         prompt_mask=None, noise=None, sampler="student", out_style=None, out_dur=None,

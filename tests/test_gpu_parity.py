@@ -199,6 +199,47 @@ def test_cross_attention_vs_torch_fp32(path, impl, T, P):
 
 
 # ---------------------------------------------------------------------------------------------
+# length regulator: integer / copy work -> bit-exact against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,C,F", [(1, 1, 4, 7), (3, 17, 640, 200), (4, 64, 640, None), (2, 1024, 128, 4096)])
+def test_length_regulator_bit_exact(path, oracle, B, T, C, F):
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    feats = torch.randn(B, T, C, generator=g)
+    dur = torch.randint(0, 6, (B, T), generator=g, dtype=torch.int32)
+    dur[0, 0] = 0                                   # zero-length tokens contribute no frame
+    if B > 1:
+        dur[1] = 0                                  # an utterance with no frames at all
+        dur[-1, T // 2:] = 0                        # padded tail
+    fr, ln, tk = path.regulate_length(feats, dur, max_frames=F, return_tokens=True)
+    fr_ref, ln_ref, tk_ref = oracle.regulate_length(feats, dur, max_frames=F, return_tokens=True)
+    assert torch.equal(ln.cpu(), ln_ref) and torch.equal(tk.cpu(), tk_ref)
+    assert torch.equal(fr.cpu(), fr_ref)            # copies: bit-exact
+
+
+def test_length_regulator_full_size_properties(path):
+    """cfg4-sized: B = 256, T = 512, durations from the predictor itself; properties that need no oracle run."""
+    B, T, C = 256, 512, 640
+    inp = stz.synthetic_inputs(CFG, B, T, steps=1, seed=4321, var_len=(16, 512))
+    style = 0.7 * torch.randn(B, CFG.n_style, CFG.d_style, generator=torch.Generator().manual_seed(5))
+    m = inp["text_mask"]
+    dur = path.predict_duration(inp["text_emb"], style, text_mask=m)
+    feats = torch.randn(B, T, C, generator=torch.Generator().manual_seed(6)).cuda()
+    F = 4096
+    fr, ln, tk = path.regulate_length(feats, dur, max_frames=F, return_tokens=True)
+    total = dur.sum(1).clamp(max=F)
+    assert torch.equal(ln, total.to(torch.int32))
+    valid = torch.arange(F, device="cuda")[None] < ln[:, None]
+    assert bool((tk[~valid] == -1).all()) and bool((fr[~valid] == 0).all())
+    # every valid frame is a verbatim copy of its token's row, tokens are non-decreasing, and token t owns dur[t] frames
+    gathered = torch.gather(feats, 1, tk.clamp(min=0).long()[..., None].expand(-1, -1, C))
+    assert torch.equal(fr[valid], gathered[valid])
+    assert bool((tk[:, 1:][valid[:, 1:]] >= tk[:, :-1][valid[:, 1:]]).all())
+    counts = torch.zeros(B, T, dtype=torch.int64, device="cuda").scatter_add_(1, tk.clamp(min=0).long(), valid.long())
+    untruncated = dur.sum(1) <= F
+    assert torch.equal(counts[untruncated], dur[untruncated].long())
+
+
+# ---------------------------------------------------------------------------------------------
 # full-size properties (BASELINE configs[1] = cfg2 and configs[3] = cfg4 shapes)
 # ---------------------------------------------------------------------------------------------
 def test_cfg2_full_size_properties(path):

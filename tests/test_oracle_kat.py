@@ -223,3 +223,14 @@ def test_random_init_is_non_degenerate(default_weights):
     assert float((z - zc).abs().max()) > 1e-2            # guidance does something
     d = o.predict_duration(inp["text_emb"], z)
     assert int(d.min()) >= 1 and int(d.max()) > int(d.min()) and int(d.max()) <= cfg.max_dur
+
+
+def test_length_regulator_known_answer(tiny_weights):
+    """repeat_interleave semantics, zero-duration tokens, truncation at max_frames, zero padding."""
+    o = OraclePath(stz.TINY, tiny_weights)
+    f = torch.arange(2 * 4 * 4, dtype=torch.float32).view(2, 4, 4)
+    d = torch.tensor([[2, 0, 1, 3], [1, 1, 0, 0]], dtype=torch.int32)
+    fr, ln, tk = o.regulate_length(f, d, max_frames=5, return_tokens=True)
+    assert ln.tolist() == [5, 2]                                  # 6 frames truncated to 5
+    assert tk.tolist() == [[0, 0, 2, 3, 3], [0, 1, -1, -1, -1]]
+    assert torch.equal(fr[0, 2], f[0, 2]) and torch.equal(fr[1, 2:], torch.zeros(3, 4))
