@@ -986,4 +986,483 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   if (warp == 0) tmem_dealloc<256>(tmem_slot);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// attention_tcs_kernel — streaming form of attention_tc2_kernel for cross-attention over long text
+// (T8 + P8 + 1 > 128 keys, e.g. BASELINE cfg4: 512 text tokens + 50 prompt tokens + null).
+//
+// The key sequence is visited in blocks of 128 rows: ceil(T / 128) text blocks, then one block holding the prompt
+// keys (rows 0..P-1) and the null-prompt key (row P8).  Per block: S = Q K_j^T (tcgen05), thread-per-row masked
+// softmax with a running row max / row sum, P_j -> shared memory (the first 64 keys over the dead K_j tile),
+// O (+)= P_j V_j (tcgen05, V MN-major).  When a block raises a row's running max the O accumulator of that row is
+// rescaled in TMEM (tcgen05.ld -> x alpha -> tcgen05.st); warps skip the rescale when no row of theirs moved.
+// K_j / V_j are double-buffered (block j + 1 is fetched while block j is processed, and S_{j+1} is issued right behind
+// P_j V_j); Q stays resident for the unit.
+// Same work split as attention_tc2_kernel: warps w and w + 4 share 32 query rows and split the four 32-key chunks
+// of a block by parity and the 64 output columns in halves.
+// ------------------------------------------------------------------------------------------------------
+constexpr int ATS_SMEM_BYTES = ATC_TILE /*Q*/ + 2 * 2 * ATC_TILE /*2 x (K, V)*/ + ATC_TILE /*P keys 64..127*/ + 1024;
+
+__global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                               const __grid_constant__ CUtensorMap tmT,
+                                                               const __grid_constant__ CUtensorMap tmP,
+                                                               const __grid_constant__ CUtensorMap tmN,
+                                                               const AttnTcParams p) {
+  extern __shared__ uint8_t atc_smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_kv[2], bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t colmask[2][4];
+  __shared__ float pmax[2][128], psum[2][128];
+  const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
+  const uint32_t qs = smem_base, kv0 = smem_base + ATC_TILE, p1s = smem_base + 5 * ATC_TILE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, half = warp >> 2;
+  const int row = q4 * 32 + lane;
+  const int br = row >> 6, tok = row & 63;
+  const int n_tok = p.n_style;
+  const int nbt = (p.T + 127) >> 7, nblk = nbt + 1;       // text blocks, then the prompt + null block
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmT); prefetch_tmap(&tmP); prefetch_tmap(&tmN);
+    mbar_init(&bar_q, 1);
+    mbar_init(&bar_kv[0], 1);
+    mbar_init(&bar_kv[1], 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  for (uint32_t o = tid * 16; o < 6 * ATC_TILE; o += 256 * 16) st_shared_v4(smem_base + o, 0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
+  pdl_sync();
+
+  auto load_block = [&](int b, int head, int j) {     // tid == 0
+    const int buf = j & 1;
+    const uint32_t ks = kv0 + buf * 2 * ATC_TILE, vs = ks + ATC_TILE, bar = smem_u32(&bar_kv[buf]);
+    const int hc = head * ATT_DH;
+    if (j < nbt) {
+      mbar_expect_tx(&bar_kv[buf], 2u * ATC_TILE);
+      tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T + j * 128);
+      tma_load_2d_u32(vs, &tmT, bar, p.col_v + hc, b * p.T + j * 128);
+    } else {
+      mbar_expect_tx(&bar_kv[buf], 2u * 128u * static_cast<uint32_t>(p.P + 1));
+      tma_load_2d_u32(ks, &tmP, bar, p.col_k + hc, b * p.P);
+      tma_load_2d_u32(vs, &tmP, bar, p.col_v + hc, b * p.P);
+      tma_load_2d_u32(ks + p.P8 * 128, &tmN, bar, p.col_k + hc, 0);
+      tma_load_2d_u32(vs + p.P8 * 128, &tmN, bar, p.col_v + hc, 0);
+    }
+  };
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);
+  const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+  uint32_t ph_q = 0, ph_kv0 = 0, ph_kv1 = 0, ph_s = 0, ph_o = 0;
+
+  // tid 0 only: S_j = Q K_j^T as soon as block j has landed (issued right behind the previous block's P V, so its latency
+  // hides under that block's tail instead of heading the next block's dependency chain)
+  auto issue_s = [&](int j) {
+    const int buf = j & 1;
+    if (j == 0) { mbar_wait(&bar_q, ph_q); ph_q ^= 1u; }
+    if (buf == 0) { mbar_wait(&bar_kv[0], ph_kv0); ph_kv0 ^= 1u; } else { mbar_wait(&bar_kv[1], ph_kv1); ph_kv1 ^= 1u; }
+    tc_fence_after();
+    const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(kv0 + buf * 2 * ATC_TILE);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+    umma_commit(&bar_s);
+  };
+
+  for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+    const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+    if (tid == 0) {
+      mbar_expect_tx(&bar_q, 2u * 8192u);
+      tma_load_3d_u32(qs, &tmQ, smem_u32(&bar_q), head * ATT_DH, 0, b * n_tok);
+      tma_load_3d_u32(qs + 8192, &tmQ, smem_u32(&bar_q), head * ATT_DH, 1, b * n_tok);
+      load_block(b, head, 0);
+      load_block(b, head, 1);       // nblk >= 2 always
+      issue_s(0);
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int buf = j & 1;
+      const uint32_t ks = kv0 + buf * 2 * ATC_TILE, vs = ks + ATC_TILE;
+      if (warp < 4) {   // visibility of key row warp * 32 + lane of this block -> per-branch 32-key chunk masks
+        const int kr = warp * 32 + lane;
+        uint32_t vis = 0;
+        if (j < nbt) {
+          const int kt = j * 128 + kr;
+          vis = (kt < p.T && (p.tmask == nullptr || p.tmask[static_cast<size_t>(b) * p.T + kt] != 0)) ? 3 : 0;
+        } else if (kr < p.P) {
+          vis = (p.pmask == nullptr || p.pmask[static_cast<size_t>(b) * p.P + kr] != 0) ? 1 : 0;
+        } else if (kr == p.P8) {
+          vis = 2;
+        }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, (vis & 1) != 0), m1 = __ballot_sync(0xffffffffu, (vis & 2) != 0);
+        if (lane == 0) { colmask[0][warp] = m0; colmask[1][warp] = m1; }
+      }
+      __syncthreads();            // colmask visible
+      const uint32_t cm0 = colmask[br][half], cm1 = colmask[br][half + 2];
+      mbar_wait(&bar_s, ph_s); ph_s ^= 1u;
+      // the previous block's P V has completed: its P tiles may be overwritten, O may be rescaled, and its K / V buffer
+      // may be refilled with block j + 1
+      if (j > 0) {
+        mbar_wait(&bar_o, ph_o); ph_o ^= 1u;
+        if (tid == 0 && j + 1 < nblk) load_block(b, head, j + 1);
+      }
+      tc_fence_after();
+
+      // ---- pass 1: block row max over the visible keys of this warp's chunks
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const uint32_t cm = ci ? cm1 : cm0;
+        if (cm == 0) continue;
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_addr + (half + 2 * ci) * 32, r);
+        tmem_ld_wait();
+        if (cm == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((cm >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
+        }
+      }
+      pmax[half][row] = mx;
+      __syncthreads();
+      const float m_new = fmaxf(m_run, fmaxf(pmax[0][row], pmax[1][row]));
+      const float mb = (m_new == -INFINITY ? 0.f : m_new) * p.scale_log2;
+      const float alpha = (m_run == -INFINITY) ? (m_new == -INFINITY ? 1.f : 0.f) : ex2_approx((m_run - m_new) * p.scale_log2);
+      m_run = m_new;
+
+      // ---- pass 2: P_j = exp2(S * scale - max), masked, bf16 (keys 0..63 over the dead K_j tile, keys 64..127 in p1s)
+      float lsum = 0.f;
+      const uint32_t sw = row & 7;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = half + 2 * ci;
+        const uint32_t cm = ci ? cm1 : cm0;
+        const uint32_t pb = ((c >> 1) ? p1s : ks) + row * 128;
+        if (cm == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) st_shared_v4(pb + ((((c & 1) * 4 + i) ^ sw) << 4), 0u, 0u, 0u, 0u);
+          continue;
+        }
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+        if (cm == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb)); lsum += pv[i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+            pv[i] = ((cm >> i) & 1u) ? e : 0.f;
+            lsum += pv[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(pb + ((((c & 1) * 4 + i) ^ sw) << 4), pack_bf16(pv[8 * i], pv[8 * i + 1]), pack_bf16(pv[8 * i + 2], pv[8 * i + 3]),
+                       pack_bf16(pv[8 * i + 4], pv[8 * i + 5]), pack_bf16(pv[8 * i + 6], pv[8 * i + 7]));
+      }
+      psum[half][row] = lsum;
+      // ---- rescale this warp's 32 columns of O where the running max moved
+      if (j > 0) {
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+          uint32_t r[32];
+          tmem_ld32(tmem_o + lane_addr + half * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st32(tmem_o + lane_addr + half * 32, r);
+          tmem_st_wait();
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      l_run = l_run * alpha + (psum[0][row] + psum[1][row]);
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint64_t da = umma_desc_sw128((i >> 2) ? p1s : ks) + 2 * (i & 3);
+          const uint64_t db = umma_desc_sw128_mn(vs + i * 2048);
+          umma_bf16(tmem_o, da, db, idesc_o, (j | i) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_o);
+        if (j + 1 < nblk) issue_s(j + 1);      // S is free: every warp finished reading S_j before the barrier above
+      }
+    }
+    // ---- out row = O / rowsum
+    mbar_wait(&bar_o, ph_o); ph_o ^= 1u;
+    tc_fence_after();
+    {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_o + lane_addr + half * 32, r);
+      tmem_ld_wait();
+      if (tok < n_tok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + i * 8) = u;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();     // TMEM, Q tile and statistics are free for the next unit
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem_slot);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// attention_tc3_kernel — attention_tc2_kernel with a dedicated issuing warp.
+//
+// In tc2 thread 0 is both a softmax thread and the only issuer of the unit's 6-8 TMA copies and 12 tcgen05.mma
+// (~170 and ~50 cycles of issue each): ~1.5-2 k cycles of serial work per unit that the other 255 threads wait for at
+// the next __syncthreads.  Here warp 8 (one lane) does nothing but issue, runs AHEAD of the softmax warps (operands of
+// the unit after next in flight, S of the next unit computed while this unit's softmax runs), and meets them only on
+// mbarriers: bar_s (S ready), bar_p (P written by all 8 softmax warps), bar_o (O ready), bar_done (O drained).
+// The softmax warps synchronise among themselves with a named barrier.
+// ------------------------------------------------------------------------------------------------------
+constexpr int ATC3_THREADS = 288;
+__device__ __forceinline__ void att_named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                       const __grid_constant__ CUtensorMap tmT,
+                                                                       const __grid_constant__ CUtensorMap tmP,
+                                                                       const __grid_constant__ CUtensorMap tmN,
+                                                                       const AttnTcParams p) {
+  extern __shared__ uint8_t atc_smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[2], bar_s, bar_o, bar_p, bar_done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t colmask[2][2][4];     // [unit parity][branch][32-column chunk]
+  __shared__ float pmax[2][128], psum[2][128];
+  const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tok = p.n_style;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmT);
+    if (!p.self) { prefetch_tmap(&tmP); prefetch_tmap(&tmN); }
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    mbar_init(&bar_p, 8);        // one arrival per softmax warp
+    mbar_init(&bar_done, 8);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<256>(&tmem_slot);
+  for (uint32_t o = tid * 16; o < 2 * ATC_BUF_BYTES; o += ATC3_THREADS * 16) st_shared_v4(smem_base + o, 0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
+  pdl_sync();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = p.self ? 6u * 8192u : 2u * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
+      auto produce = [&](int unit, int buf) {
+        const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+        const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
+        const uint32_t bar = smem_u32(&bar_full[buf]);
+        mbar_expect_tx(&bar_full[buf], tx_bytes);
+        const int t0 = b * n_tok, hc = head * ATT_DH;
+        tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
+        tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+        if (p.self) {
+          tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
+          tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
+          tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
+          tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
+        } else {
+          const uint32_t o1 = p.T8 * 128, o2 = (p.T8 + p.P8) * 128;
+          tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
+          tma_load_2d_u32(vs, &tmT, bar, p.col_v + hc, b * p.T);
+          tma_load_2d_u32(ks + o1, &tmP, bar, p.col_k + hc, b * p.P);
+          tma_load_2d_u32(vs + o1, &tmP, bar, p.col_v + hc, b * p.P);
+          tma_load_2d_u32(ks + o2, &tmN, bar, p.col_k + hc, 0);
+          tma_load_2d_u32(vs + o2, &tmN, bar, p.col_v + hc, 0);
+        }
+      };
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
+      auto issue_s = [&](int it) {     // S of the it-th unit of this CTA: waits for its operands
+        const int buf = it & 1;
+        mbar_wait(&bar_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qs = smem_base + buf * ATC_BUF_BYTES;
+        const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(qs + ATC_TILE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&bar_s);
+      };
+      const int stride = gridDim.x;
+      int unit = blockIdx.x;
+      if (unit < p.n_units) {
+        produce(unit, 0);
+        if (unit + stride < p.n_units) produce(unit + stride, 1);
+        issue_s(0);
+      }
+      for (int it = 0; unit < p.n_units; unit += stride, ++it) {
+        const int buf = it & 1;
+        const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, vs = qs + 2 * ATC_TILE;
+        mbar_wait(&bar_p, it & 1);                        // P of this unit is in shared memory, S has been consumed
+        if (it > 0) mbar_wait(&bar_done, (it - 1) & 1);   // the previous unit's O has been drained
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
+          const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
+          umma_bf16(tmem_o, da, db, idesc_o, j != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_o);
+        if (unit + stride < p.n_units) issue_s(it + 1);   // runs right behind P V: ready before the softmax warps get there
+        if (unit + 2 * stride < p.n_units) {              // this unit's buffer is free once its P V has completed
+          mbar_wait(&bar_o, it & 1);
+          produce(unit + 2 * stride, buf);
+        }
+      }
+    }
+  } else {
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;                      // query row = TMEM lane
+    const int br = row >> 6, tok = row & 63;             // rows 0..63 conditional, 64..127 unconditional
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
+      const int buf = it & 1, par = it & 1;
+      const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+      const uint32_t qs = smem_base + buf * ATC_BUF_BYTES;
+      if (warp < 4) {   // visibility of key row warp * 32 + lane -> per-branch 32-key chunk masks
+        const int kr = warp * 32 + lane;
+        uint32_t vis = 0;
+        if (p.self) {
+          vis = (kr & 63) < n_tok ? (1u << (kr >> 6)) : 0u;
+        } else if (kr < p.T) {
+          vis = (p.tmask == nullptr || p.tmask[static_cast<size_t>(b) * p.T + kr] != 0) ? 3 : 0;
+        } else if (kr >= p.T8 && kr < p.T8 + p.P) {
+          vis = (p.pmask == nullptr || p.pmask[static_cast<size_t>(b) * p.P + (kr - p.T8)] != 0) ? 1 : 0;
+        } else if (kr == p.T8 + p.P8) {
+          vis = 2;
+        }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, (vis & 1) != 0), m1 = __ballot_sync(0xffffffffu, (vis & 2) != 0);
+        if (lane == 0) { colmask[par][0][warp] = m0; colmask[par][1][warp] = m1; }
+      }
+      att_named_bar_sync(1, 256);
+      const uint32_t cm0 = colmask[par][br][half], cm1 = colmask[par][br][half + 2];
+      mbar_wait(&bar_s, par);
+      tc_fence_after();
+
+      // ---- pass 1: row max over the visible keys of this warp's chunks
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const uint32_t cm = ci ? cm1 : cm0;
+        if (cm == 0) continue;   // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_addr + (half + 2 * ci) * 32, r);
+        tmem_ld_wait();
+        if (cm == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((cm >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
+        }
+      }
+      pmax[half][row] = mx;
+      att_named_bar_sync(1, 256);
+      mx = fmaxf(pmax[0][row], pmax[1][row]);
+      const float mb = (mx == -INFINITY ? 0.f : mx) * p.scale_log2;
+
+      // ---- pass 2: P = exp2(S * scale - max), masked, bf16, into the dead Q | K tiles (K-major, swizzled)
+      float lsum = 0.f;
+      const uint32_t prow = qs + row * 128, sw = row & 7;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = half + 2 * ci;
+        const uint32_t cm = ci ? cm1 : cm0;
+        const uint32_t pb = prow + (c >> 1) * ATC_TILE;
+        if (cm == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), 0u, 0u, 0u, 0u);
+          continue;
+        }
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+        if (cm == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb)); lsum += pv[j]; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
+            pv[j] = ((cm >> j) & 1u) ? e : 0.f;
+            lsum += pv[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
+                       pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
+      }
+      psum[half][row] = lsum;
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p);
+      // ---- out row = O / rowsum: this warp's 32 of the 64 columns
+      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
+      mbar_wait(&bar_o, par);
+      tc_fence_after();
+      {
+        const float ltot = psum[0][row] + psum[1][row];
+        const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
+        uint32_t r[32];
+        tmem_ld32(tmem_o + lane_addr + half * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_done);       // O (and this unit's statistics) are in registers
+        if (tok < n_tok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + j * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<256>(tmem_slot);
+}
+
 }  // namespace stz

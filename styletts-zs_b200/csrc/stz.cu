@@ -99,6 +99,7 @@ struct stz_handle {
   int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
+  int attn_tc3 = 0;    // resident-key tcgen05 attention with a dedicated issuing warp (0: attention_tc2_kernel)
   int attn_impl = 0;   // 0 = tcgen05 + TMA kernel when the keys fit (else streaming), 1 = mma.sync resident-key kernel, 2 = always streaming, 3 = tcgen05 + cp.async
   int ablate = 0;   // tools/ablate.py: bit mask of kernel families skipped inside run_eval (timing attribution only; results are wrong)
   int64_t launches = 0;
@@ -421,6 +422,8 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
@@ -843,10 +846,11 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
-  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains")) {
+  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") || !strcmp(key, "attn_tc3")) {
     for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
     H->graphs.clear();
     if (!strcmp(key, "chains")) H->chains = value;
+    else if (!strcmp(key, "attn_tc3")) H->attn_tc3 = value;
     else if (!strcmp(key, "ablate")) H->ablate = value; else if (!strcmp(key, "attn_impl")) H->attn_impl = value; else H->fuse_ln = value;
   }
   else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // process-wide knobs baked into captured graphs
@@ -986,7 +990,36 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
       tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
     }
     const int units = tp_.n_units;
-    launch_k(attention_tc2_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
+    if (H->attn_tc3)
+      launch_k(attention_tc3_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, ATC3_THREADS, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
+    else
+      launch_k(attention_tc2_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
+  } else if (H->attn_impl == 0 && cross3 && ap.n_q <= 128 && n_style <= 64 && P8 + 1 <= 128) {
+    // long text: streaming tcgen05 attention over 128-key blocks (attention_tcs_kernel)
+    CUtensorMap tq, tt, tp, tn;
+    {
+      const cuuint64_t gd[3] = {(cuuint64_t)dm, 2, (cuuint64_t)B * n_style};
+      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 4};
+      const cuuint32_t bx[3] = {64, 1, 64};
+      if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
+    }
+    const AttnSeg* sg = ap.seg;
+    CUtensorMap* maps[3] = {&tt, &tp, &tn};
+    for (int i = 0; i < 3; ++i) {
+      const cuuint64_t rows = i == 2 ? 1 : (cuuint64_t)B * sg[i].n;
+      const cuuint64_t gd[2] = {(cuuint64_t)2 * dm, rows};
+      const cuuint64_t gs[1] = {(cuuint64_t)sg[i].ld * 2};
+      const cuuint32_t bx[2] = {64, (cuuint32_t)(i == 0 ? 128 : sg[i].n)};     // text: fixed 128-row blocks
+      if ((int)(sg[i].v - sg[i].k) != dm || make_tmap_nd(maps[i], sg[i].k, 2, gd, gs, bx))
+        return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention K/V segment %d) failed", i);
+    }
+    AttnTcParams tp_{};
+    tp_.out = ap.out; tp_.ldo = ap.ldo; tp_.n_q = ap.n_q; tp_.n_heads = H->cfg.n_heads; tp_.n_units = B * H->cfg.n_heads;
+    tp_.self = 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2;
+    tp_.T = sg[0].n; tp_.P = sg[1].n; tp_.T8 = T8; tp_.P8 = P8; tp_.col_k = 0; tp_.col_v = dm;
+    tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
+    const int units = tp_.n_units;
+    launch_k(attention_tcs_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATS_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
   } else if (n_keys <= 128 && ap.n_q <= 128 && H->attn_impl == 3) {   // tcgen05 with cp.async staging (superseded by tc2)
     const int units = B * H->cfg.n_heads;
     launch_k(attention_tc_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 128, ATC_SMEM_BYTES, st, ap, H->cfg.n_heads, units);
