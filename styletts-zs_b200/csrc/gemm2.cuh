@@ -271,7 +271,25 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   const uint32_t tmem_base = tmem_slot;
   if constexpr (CM > 1) g2_cluster_sync();   // peer barriers are initialised before any remote arrive / commit
   if (tr != nullptr && threadIdx.x == 0) tr[1] = clock64();
-  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // The W operand is constant (weights): the first ring of W tiles is requested BEFORE waiting for the previous kernel,
+  // so only the A tiles (its output) are fetched on the critical path after the dependency resolves.
+  constexpr int kPre = STAGES;
+  int n_pre = 0;
+  if constexpr (CM == 1) {
+    if (warp == 0 && lane == 0 && unit0 < n_tiles) {
+      n_pre = num_kb < kPre ? num_kb : kPre;
+      const int tile_n0 = unit0 % tiles_n;
+      for (int s = 0; s < n_pre; ++s) {
+        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(smem_base + s * (A_BYTES + B_BYTES) + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[s])),
+            "r"(s * GEMM_BK), "r"(tile_n0 * BN)
+            : "memory");
+      }
+    }
+  }
+  pdl_sync();   // everything above overlapped the previous kernel's tail; activations are touched only below
   if (tr != nullptr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
@@ -284,17 +302,19 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
           if constexpr (CM == 1) {
-            mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+            const bool pre = tile == unit0 && kb < n_pre;   // this stage's W tile (and its expect_tx) went out before the wait
+            if (!pre) mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                 ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK),
                 "r"(p.a_row0 + tile_m * GEMM_BM)
                 : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])),
-                "r"(kb * GEMM_BK), "r"(tile_n * BN)
-                : "memory");
+            if (!pre)
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                  ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])),
+                  "r"(kb * GEMM_BK), "r"(tile_n * BN)
+                  : "memory");
           } else {
             const uint32_t lead_full = g2_mapa(smem_u32(&full_bar[stage]), 0);
             tma_load_2d_2cta(sa, &tmA, lead_full, kb * GEMM_BK, p.a_row0 + tile_m * GEMM_BM);
