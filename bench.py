@@ -295,7 +295,9 @@ def main_native(args, rank, world, local_rank):
                    "sample": f"one full cfg2 batch ({B} utterances) through the fp32 PyTorch oracle, {r['wall_s']:.1f} s wall"}
     line = {"metric": METRIC, "value": total_utt / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core operands, fp32 accumulate/state; predictor fp32",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "dtype_note": "bf16 tensor-core operands (split-bf16 = fp32-grade where noted in DESIGN.md), fp32 accumulate / residual / "
+                          "sampler state / LSTM gates / duration head",
             "data": "synthetic (seeded N(0,1) inputs, random-init weights)", "config": workload_config(world),
             "e2e": {"value": total_utt / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
