@@ -111,10 +111,21 @@ int stz_synthesize_host(stz_handle* h, const float* text_emb, const uint8_t* tex
 /* Number of kernels launched by this handle since creation (graph nodes count per replay). */
 int64_t stz_launch_count(const stz_handle* h);
 
-/* Knobs: "use_graph" (0/1, default 1), "gemm_impl" (0 = tcgen05 persistent v2, 1 = SIMT cross-check kernel, 2 = tcgen05 v1),
- * "lstm_impl" (0 = tcgen05 cluster kernel, 1 = generic, 2 = fp32 FFMA cluster kernel), "pred_gemm_impl" (0 = split-bf16 tcgen05,
- * 1 = fp32 CUDA cores), "use_pdl" (0/1 programmatic dependent launch, process-wide), "profile" (0/1, see stz_profile_read).  Returns STZ_E_ARG for
- * unknown keys. */
+/* Knobs (product defaults first; the alternatives are measured A/B variants kept for cross-checks and tuning):
+ *   "use_graph"      1 | 0        evaluation loop as one CUDA graph per shape bucket | eager launches
+ *   "use_pdl"        1 | 0        programmatic dependent launch (process-wide)
+ *   "gemm_impl"      0 | 1 | 2    persistent tcgen05 GEMM | SIMT cross-check kernel | first tcgen05 kernel
+ *   "gemm_bn"        0 | 128/192/256   tile width heuristic | forced (process-wide)
+ *   "gemm_cluster"   0 | 1        single-CTA tiles | cta_group::2 CTA pairs (process-wide)
+ *   "fuse_ln"        0 | 1 | 2    GEMM + ln_mod kernels | one-CTA fused GEMM+LayerNorm | cluster-of-two fused GEMM+LayerNorm
+ *   "attn_impl"      0 | 1 | 2 | 3   tcgen05 + TMA (resident keys, streaming for long text) | mma.sync resident keys |
+ *                                 mma.sync streaming | tcgen05 + cp.async
+ *   "attn_tc3"       0 | 1        resident-key tcgen05 attention without | with a dedicated issuing warp
+ *   "chains"         1 | 2..8     utterance chains on parallel graph branches
+ *   "lstm_impl"      0 | 1 | 2    tcgen05 cluster recurrence | generic kernel | fp32 FFMA cluster recurrence
+ *   "pred_gemm_impl" 0 | 1        split-bf16 tcgen05 predictor GEMMs | fp32 CUDA-core GEMMs
+ *   "profile"        0 | 1        see stz_profile_read;   "ablate" (bit mask): tools/ablate.py timing attribution only
+ * Returns STZ_E_ARG for unknown keys. */
 int stz_set_option(stz_handle* h, const char* key, int value);
 
 /* Profile mode (set_option "profile" = 1; setting it also clears the records): sample_style /
