@@ -134,6 +134,24 @@ def test_teacher_adpm2_vs_oracle(path, oracle):
     assert rel(z, z_ref) < TOL_STYLE
 
 
+@pytest.mark.parametrize("B,T,P,tlen", [(3, 29, 33, (5, 29)), (2, 77, 50, (40, 77)), (2, 130, 17, (100, 130)), (1, 257, 50, (257, 257))])
+def test_odd_shapes_and_prompt_masks_vs_oracle(path, oracle, B, T, P, tlen):
+    """Shapes off every tile boundary (T, P not multiples of 8 / 64 / 128; resident and streaming attention; masked
+    prompt tokens), full path: 2-step CFG student + duration predictor against the fp32 oracle."""
+    inp = stz.synthetic_inputs(CFG, B, T, P=P, steps=2, seed=900 + T, var_len=tlen)
+    pm = inp["prompt_mask"].clone()
+    pm[0, P // 3:] = False                       # a short prompt
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 2, 1.7, text_mask=inp["text_mask"], prompt_mask=pm,
+                          noise=inp["noise"])
+    z_ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], 2, 1.7, text_mask=inp["text_mask"], prompt_mask=pm,
+                                noise=inp["noise"])
+    assert rel(z, z_ref) < TOL_STYLE
+    d = path.predict_duration(inp["text_emb"], z_ref, text_mask=inp["text_mask"]).cpu()
+    d_ref = oracle.predict_duration(inp["text_emb"], z_ref, text_mask=inp["text_mask"])
+    m = inp["text_mask"]
+    assert float((d[m] == d_ref[m]).float().mean()) >= TOL_DUR_AGREE and bool((d[~m] == 0).all())
+
+
 def test_cfg3_teacher_32_steps_vs_oracle(path, oracle):
     """BASELINE configs[2] schedule (32 ADPM2 steps = 64 chained denoiser evaluations, ancestral noise) at a batch the
     oracle finishes in seconds: error accumulation over the whole teacher trajectory stays inside the 1e-2 budget.
