@@ -117,7 +117,8 @@ int64_t stz_launch_count(const stz_handle* h);
  *   "gemm_impl"      0 | 1 | 2    persistent tcgen05 GEMM | SIMT cross-check kernel | first tcgen05 kernel
  *   "gemm_bn"        0 | 128/192/256   tile width heuristic | forced (process-wide)
  *   "gemm_cluster"   0 | 1        single-CTA tiles | cta_group::2 CTA pairs (process-wide)
- *   "fuse_ln"        0 | 1 | 2    GEMM + ln_mod kernels | one-CTA fused GEMM+LayerNorm | cluster-of-two fused GEMM+LayerNorm
+ *   "fuse_ln"        3 | 0 | 1 | 2   cluster-of-two GEMM + residual + LayerNorm with the residual tile staged in the operand
+ *                                 ring | GEMM + ln_mod kernels | one-CTA fused kernel | first cluster-of-two fused kernel
  *   "attn_impl"      0 | 1 | 2 | 3   tcgen05 + TMA (resident keys, streaming for long text) | mma.sync resident keys |
  *                                 mma.sync streaming | tcgen05 + cp.async
  *   "attn_tc3"       0 | 1        resident-key tcgen05 attention without | with a dedicated issuing warp

@@ -21,6 +21,7 @@
 #include "gemm2.cuh"
 #include "gemm_ln.cuh"
 #include "gemm_ln2.cuh"
+#include "gemm_ln3.cuh"
 #include "predictor.cuh"
 #include "predictor_tc.cuh"
 #include "regulator.cuh"
@@ -95,7 +96,7 @@ struct stz_handle {
   cudaEvent_t last_ev = nullptr;
   bool has_last = false;
   std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
-  int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 0;
+  int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 3;
   int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
@@ -245,11 +246,12 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t c
 // Output map of the staged epilogues: row-major [rows, cols], row stride ld (elements), box = 32 rows x row_bytes
 // (128 B, 128B swizzle: gemm_ln kernels; 64 B, 64B swizzle: gemm2's double-buffered staging).  Rows >= `rows` are
 // clipped by the TMA unit.
-static int make_tmap_out(CUtensorMap* m, void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, int row_bytes = 128) {
+static int make_tmap_out(CUtensorMap* m, void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, int row_bytes = 128,
+                         int box_rows = 32) {
   const uint64_t es = is_bf16 ? 2 : 4;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {ld * es};
-  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / es), 32};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -378,6 +380,25 @@ static int launch_gemmln2(stz_handle* H, cudaStream_t st, const bf16* A, int lda
   return 0;
 }
 
+// residual tile staged in the operand ring (gemm_ln3.cuh)
+template <int MODE>
+static int launch_gemmln3(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
+                          const GemmLnParams& p) {
+  if (p.K % (GEMM_BK * GLN3_STAGES)) return fail(H, STZ_E_SHAPE, "gemmln3 needs K %% %d == 0", GEMM_BK * GLN3_STAGES);
+  if (2 * ((GEMM_BM - 1 + p.rows_per_utt - 1) / p.rows_per_utt + 1) > GLN3_MAX_SEQ)
+    return fail(H, STZ_E_SHAPE, "gemmln3: a 128-row tile spans too many sequences (rows_per_utt %d)", p.rows_per_utt);
+  CUtensorMap ta, tb, tu, th;
+  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
+      make_tmap(&tb, W, (uint64_t)GLN_N, (uint64_t)p.K, (uint64_t)p.K, GLN3_BN) ||
+      make_tmap_out(&th, p.h, false, (uint64_t)p.M, (uint64_t)GLN_N, (uint64_t)GLN_N, 128, 128) ||
+      make_tmap_out(&tu, u, true, (uint64_t)p.M, (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), 128, 128))
+    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (gemmln3 M=%d K=%d)", p.M, p.K);
+  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * GLN_N * p.K);
+  launch_kc(2, gemmln3_kernel<MODE>, 2 * cdiv(p.M, GEMM_BM), GLN_THREADS, GLN3_SMEM_BYTES, st, ta, tb, tu, th, p);
+  KCHECK(H);
+  return 0;
+}
+
 template <int BN, int EPI>
 static cudaError_t set_gemm2_attr() {
   cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
@@ -416,6 +437,8 @@ static cudaError_t init_kernel_attrs() {
   if ((e = set_gemm2_attrs<EPI_SAMPLER>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemmln3_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN3_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemmln3_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN3_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln2_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN2_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln2_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN2_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
@@ -1063,7 +1086,12 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * 2 * Btot + (int)s0; p.bias = W32(H, "mod.b"); p.out = mod; p.ldo = n_mod;
     RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
   }
-  const bool fused = H->fuse_ln && impl == 0 && d == GLN_N;   // GEMM + residual + AdaLN in one kernel (gemm_ln.cuh)
+  // GEMM + residual + AdaLN in one kernel.  Product: gemmln3_kernel (fuse_ln = 3) whenever its shape constraints hold
+  // (d_model 512, every contraction length a multiple of 256, a 128-row tile spanning <= 8 sequences); otherwise, and for
+  // fuse_ln = 0, the GEMM + ln_mod_kernel pair.  1 / 2 select the earlier fused kernels (A/B only).
+  int fuse_mode = (impl == 0 && d == GLN_N) ? H->fuse_ln : 0;
+  if (fuse_mode == 3 && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || 2 * ((GEMM_BM - 1 + 2 * K - 1) / (2 * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
+  const bool fused = fuse_mode != 0;
   GemmLnParams lb{};
   lb.M = R; lb.h = h; lb.mod = mod; lb.n_mod = n_mod; lb.rows_per_utt = 2 * K; lb.pos = W32(H, "pos"); lb.n_style = K;
   // residual GEMM of a sub-layer followed by the AdaLN of the next one: (gate, shift, scale) offsets into mod
@@ -1071,7 +1099,8 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = Kc; p.bias = bias; p.gate_off = gate_off; p.shift_off = ln_off; p.scale_off = ln_off + d; p.split3 = last ? 1 : 0;
-      if (H->fuse_ln == 2) return launch_gemmln2<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
+      if (fuse_mode == 3) return launch_gemmln3<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
+      if (fuse_mode == 2) return launch_gemmln2<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
       return launch_gemmln<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
     }
     GemmParams p = base;
@@ -1084,7 +1113,8 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.shift_off = 0; p.scale_off = d; p.split3 = 0;
-      if (H->fuse_ln == 2) RET(launch_gemmln2<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
+      if (fuse_mode == 3) RET(launch_gemmln3<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
+      else if (fuse_mode == 2) RET(launch_gemmln2<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
       else RET(launch_gemmln<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
     } else {
       GemmParams p = base;

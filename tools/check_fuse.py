@@ -26,7 +26,7 @@ def timeit(fn, n=20):
 
 
 ref = None
-for mode in [int(x) for x in os.environ.get("MODES", "0,2,1").split(",")]:
+for mode in [int(x) for x in os.environ.get("MODES", "0,3").split(",")]:
     path.set_option("fuse_ln", mode)
     z = samp()
     torch.cuda.synchronize()
