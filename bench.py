@@ -264,8 +264,10 @@ def main_native(args, rank, world, local_rank):
             pass
         # the denoiser's GEMM mix of one evaluation (x layers), M = 2*B*K rows: (name, N, K, epilogue, count)
         R, L, d, dff = 2 * B * cfg.n_style, cfg.n_layers, cfg.d_model, cfg.d_ff
-        mix = [("qkv", 3 * d, d, 2, L), ("attn_out", d, d, 4, L), ("q_cross", d, d, 2, L), ("cross_out", d, d, 4, L),
-               ("ffn1_gelu", dff, d, 3, L), ("ffn2", d, dff, 4, L)]
+        # epilogue 6 = the product form of the residual GEMMs (GEMM + gated residual + AdaLN in one kernel); only the
+        # GEMM's 2MNK flops are credited to it
+        mix = [("qkv", 3 * d, d, 2, L), ("attn_out+ln", d, d, 6, L), ("q_cross", d, d, 2, L), ("cross_out+ln", d, d, 6, L),
+               ("ffn1_gelu", dff, d, 3, L), ("ffn2+ln", d, dff, 6, L)]
         per_shape, tot_flops, tot_us = {}, 0.0, 0.0
         for name, N, K, epi, cnt in mix:
             us = path.bench_gemm(R, N, K, epi, 50)
@@ -277,7 +279,7 @@ def main_native(args, rank, world, local_rank):
         ach_situ = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         tot_ms = sum(v[0] for v in prof.values())
         n_mix = sum(c for *_, c in mix)
-        roofline = {"kernel": "gemm2_kernel (persistent tcgen05/TMEM/TMA bf16 GEMM family of the denoiser)", "bound": "tensor",
+        roofline = {"kernel": "gemm2_kernel / gemmln3_kernel (persistent tcgen05/TMEM/TMA bf16 GEMM family of the denoiser)", "bound": "tensor",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "avg_launch_us": tot_us / n_mix, "flops_per_launch": tot_flops / n_mix,
                     "how": "per shape of one denoiser evaluation's GEMM mix (M = 2*B*K rows): 50 back-to-back launches of the "

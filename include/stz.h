@@ -117,8 +117,9 @@ int64_t stz_launch_count(const stz_handle* h);
  *   "gemm_impl"      0 | 1 | 2    persistent tcgen05 GEMM | SIMT cross-check kernel | first tcgen05 kernel
  *   "gemm_bn"        0 | 128/192/256   tile width heuristic | forced (process-wide)
  *   "gemm_cluster"   0 | 1        single-CTA tiles | cta_group::2 CTA pairs (process-wide)
- *   "fuse_ln"        3 | 0 | 1 | 2   cluster-of-two GEMM + residual + LayerNorm with the residual tile staged in the operand
- *                                 ring | GEMM + ln_mod kernels | one-CTA fused kernel | first cluster-of-two fused kernel
+ *   "fuse_ln"        3 | 0 | 1 | 2 | 4   cluster-of-two GEMM + residual + LayerNorm with the residual tile staged in the operand
+ *                                 ring (from 36 row tiles up, GEMM + ln_mod kernels below) | GEMM + ln_mod kernels | one-CTA fused
+ *                                 kernel | first cluster-of-two fused kernel | 3 at any size
  *   "attn_impl"      0 | 1 | 2 | 3   tcgen05 + TMA (resident keys, streaming for long text) | mma.sync resident keys |
  *                                 mma.sync streaming | tcgen05 + cp.async
  *   "attn_tc3"       0 | 1        resident-key tcgen05 attention without | with a dedicated issuing warp
@@ -155,7 +156,8 @@ int stz_debug_set_att_trace(stz_handle* h, long long* trace_dev);
 int stz_debug_set_gemm_trace(stz_handle* h, long long* trace_dev);
 
 /* Roofline measurement hook (bench.py): `iters` back-to-back launches of the product GEMM kernel for one shape
- * (C[M,N] = A[M,K] W[N,K]^T, epi 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual reduce-add) on the handle's
+ * (C[M,N] = A[M,K] W[N,K]^T, epi 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual reduce-add, 6 = the fused gated residual + AdaLN kernel,
+ * N = d_model) on the handle's
  * internal stream, timed with a CUDA-event pair; *avg_us = mean microseconds per launch.  Zero-filled operands. */
 int stz_bench_gemm(stz_handle* h, int M, int N, int K, int epi, int iters, double* avg_us);
 

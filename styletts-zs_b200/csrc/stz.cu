@@ -1090,7 +1090,11 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   // (d_model 512, every contraction length a multiple of 256, a 128-row tile spanning <= 8 sequences); otherwise, and for
   // fuse_ln = 0, the GEMM + ln_mod_kernel pair.  1 / 2 select the earlier fused kernels (A/B only).
   int fuse_mode = (impl == 0 && d == GLN_N) ? H->fuse_ln : 0;
-  if (fuse_mode == 3 && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || 2 * ((GEMM_BM - 1 + 2 * K - 1) / (2 * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
+  if ((fuse_mode == 3 || fuse_mode == 4) && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || 2 * ((GEMM_BM - 1 + 2 * K - 1) / (2 * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
+  // below ~36 row tiles (B < ~46 at K = 50) the separate LayerNorm kernel is cheap and the fused kernel's long serial
+  // epilogue loses (measured: -2 .. -4 % at B = 16 / 32, +5 % at B >= 64); fuse_ln = 4 forces the fused kernel at any size
+  if (fuse_mode == 3 && cdiv(R, GEMM_BM) < 36) fuse_mode = 0;
+  if (fuse_mode == 4) fuse_mode = 3;
   const bool fused = fuse_mode != 0;
   GemmLnParams lb{};
   lb.M = R; lb.h = h; lb.mod = mod; lb.n_mod = n_mod; lb.rows_per_utt = 2 * K; lb.pos = W32(H, "pos"); lb.n_style = K;
@@ -1596,12 +1600,12 @@ extern "C" int stz_bench_gemm(stz_handle* H, int M, int N, int K, int epi, int i
   CK(H, cudaMalloc(&Cb, (size_t)M * N * sizeof(bf16)));
   CK(H, cudaMalloc(&Cf, (size_t)M * N * sizeof(float)));
   CK(H, cudaMalloc(&bias, (size_t)N * sizeof(float)));
-  CK(H, cudaMalloc(&mod, (size_t)n_seq * N * sizeof(float)));
+  CK(H, cudaMalloc(&mod, (size_t)n_seq * 3 * N * sizeof(float)));
   CK(H, cudaMemsetAsync(A, 0, (size_t)(M + 128) * K * sizeof(bf16), st));
   CK(H, cudaMemsetAsync(W, 0, (size_t)N * K * sizeof(bf16), st));
   CK(H, cudaMemsetAsync(Cf, 0, (size_t)M * N * sizeof(float), st));
   CK(H, cudaMemsetAsync(bias, 0, (size_t)N * sizeof(float), st));
-  CK(H, cudaMemsetAsync(mod, 0, (size_t)n_seq * N * sizeof(float), st));
+  CK(H, cudaMemsetAsync(mod, 0, (size_t)n_seq * 3 * N * sizeof(float), st));
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.ldo = N; p.mod = mod; p.n_mod = N; p.gate_off = 0; p.rows_per_utt = rpu;
   p.n_style = H->cfg.n_style;
@@ -1610,6 +1614,13 @@ extern "C" int stz_bench_gemm(stz_handle* H, int M, int N, int K, int epi, int i
       case 2: p.out = Cb; return gemm<EPI_BF16>(H, st, 0, A, K, M, W, p);
       case 3: p.out = Cb; return gemm<EPI_GELU_BF16>(H, st, 0, A, K, M, W, p);
       case 4: p.out = Cf; return gemm<EPI_GATE_RES>(H, st, 0, A, K, M, W, p);
+      case 6: {   // the product form of the residual GEMMs: GEMM + gated residual + AdaLN (gemmln3_kernel), N = d_model
+        if (N != GLN_N) return fail(H, STZ_E_SHAPE, "fused residual GEMM needs N = %d", GLN_N);
+        GemmLnParams q{};
+        q.M = M; q.K = K; q.bias = bias; q.h = Cf; q.mod = mod; q.n_mod = 3 * N; q.gate_off = 0; q.shift_off = N; q.scale_off = 2 * N;
+        q.rows_per_utt = rpu; q.pos = nullptr; q.n_style = H->cfg.n_style; q.split3 = 0;
+        return launch_gemmln3<GLN_RES>(H, st, A, K, M, W, Cb, q);
+      }
       default: return fail(H, STZ_E_ARG, "epi %d not benchable", epi);
     }
   };

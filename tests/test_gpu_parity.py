@@ -292,7 +292,14 @@ def test_cfg2_full_size_properties(path):
     for i in (0, 17, 63):
         zi = path.sample_style(inp["text_emb"][i:i + 1], inp["prompt_feats"][i:i + 1], steps, 2.0,
                                noise=inp["noise"][:, i:i + 1])
-        assert rel(zi[0], z[i]) < 1e-3
+        assert rel(zi[0], z[i]) < 5e-3      # B = 1 runs GEMM + LayerNorm kernels, the batch the fused kernel: bf16-noise level
+    path.set_option("fuse_ln", 4)           # same kernels at every size -> invariance to ~fp32 reduction order
+    z4 = run()
+    for i in (0, 17, 63):
+        zi = path.sample_style(inp["text_emb"][i:i + 1], inp["prompt_feats"][i:i + 1], steps, 2.0,
+                               noise=inp["noise"][:, i:i + 1])
+        assert rel(zi[0], z4[i]) < 1e-3
+    path.set_option("fuse_ln", 3)
     # permutation equivariance
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
     zp = run(text=inp["text_emb"][perm], prompt=inp["prompt_feats"][perm], noise=inp["noise"][:, perm])

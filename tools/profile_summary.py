@@ -33,10 +33,10 @@ def summarise(rep, dst):
 H, U, rows = summarise(f"gpurun_out/prof_{tag}_layer.ncu-rep", "profiles/r01_ncu_full_layer_final.json")
 num = lambda x: float(x.replace(',', ''))
 mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-g = [r for r in rows if 'gemm2_kernel' in r[H.index('Kernel Name')]]
+g = [r for r in rows if 'gemm2_kernel' in r[H.index('Kernel Name')] or 'gemmln3_kernel' in r[H.index('Kernel Name')]]
 ir, iw = H.index('dram__bytes_read.sum'), H.index('dram__bytes_write.sum')
 tr = [num(r[ir]) * mult[U[ir]] + num(r[iw]) * mult[U[iw]] for r in g]
-json.dump({"kernel": "gemm2_kernel family (one denoiser layer of cfg2, cold-cache ncu --set full replay)", "launches": len(g),
+json.dump({"kernel": "gemm2_kernel / gemmln3_kernel family (one denoiser layer of cfg2, cold-cache ncu --set full replay)", "launches": len(g),
            "dram_bytes_per_launch": sum(tr) / len(tr),
            "per_launch": [{"kernel": re.sub(r'\(.*', '', r[H.index('Kernel Name')]).replace('void ', ''), "dram_bytes": t} for r, t in zip(g, tr)],
            "source": "profiles/r01_ncu_full_layer_final.json (ncu --set full --clock-control none)"},
