@@ -804,7 +804,15 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<256>(&tmem_slot);
-  for (uint32_t o = tid * 16; o < 2 * ATC_BUF_BYTES; o += 256 * 16) st_shared_v4(smem_base + o, 0u, 0u, 0u, 0u);
+  // Only V rows that no TMA box covers must be finite (p = 0 times NaN would poison O); K rows the boxes do not cover only
+  // produce S columns that the visibility select discards, and Q / P rows are always fully written.  Self-attention boxes
+  // cover every row, so nothing is cleared there; cross-attention clears the two V tiles.
+  if (!p.self) {
+    for (uint32_t o = tid * 16; o < 2 * ATC_TILE; o += 256 * 16) {
+      const uint32_t buf = o / ATC_TILE, off = o % ATC_TILE;
+      st_shared_v4(smem_base + buf * ATC_BUF_BYTES + 2 * ATC_TILE + off, 0u, 0u, 0u, 0u);
+    }
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
