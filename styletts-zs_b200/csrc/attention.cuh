@@ -792,6 +792,14 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   const int row = q4 * 32 + lane;                      // query row = TMEM lane
   const int br = row >> 6, tok = row & 63;             // rows 0..63 conditional, 64..127 unconditional
   const int n_tok = p.n_style;
+#ifdef STZ_TRACE
+  long long* tr = (g_att_trace != nullptr && tid == 0) ? g_att_trace + blockIdx.x * 32 : nullptr;
+#else
+  constexpr long long* tr = nullptr;
+#endif
+  int tri = 0;
+#define ATC2_TR() do { if (tr != nullptr && tri < 32) tr[tri++] = clock64(); } while (0)
+  ATC2_TR();
 
   if (tid == 0) {
     prefetch_tmap(&tmQ);
@@ -818,7 +826,9 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
+  ATC2_TR();
   pdl_sync();
+  ATC2_TR();
 
   const uint32_t tx_bytes = p.self ? 6u * 8192u : 2u * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
   auto produce = [&](int unit, int buf) {
@@ -869,9 +879,11 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
     const int next = unit + gridDim.x;
     if (next < p.n_units) produce(next, buf ^ 1);
+    ATC2_TR();
     mbar_wait(&bar_full[buf], buf ? fph1 : fph0);
     if (buf) fph1 ^= 1u; else fph0 ^= 1u;
     __syncthreads();              // visb[buf] visible
+    ATC2_TR();
     const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
     if (tid == 0) {
       tc_fence_after();
@@ -889,6 +901,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     const uint32_t cm0 = colmask[br][half], cm1 = colmask[br][half + 2];   // this warp's chunks: half, half + 2
     mbar_wait(&bar_s, phase);
     tc_fence_after();
+    ATC2_TR();
 
     // ---- pass 1: row max over the visible keys of this warp's chunks
     float mx = -INFINITY;
@@ -909,6 +922,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     }
     pmax[half][row] = mx;
     __syncthreads();
+    ATC2_TR();
     mx = fmaxf(pmax[0][row], pmax[1][row]);
     const float mb = (mx == -INFINITY ? 0.f : mx) * p.scale_log2;
 
@@ -949,9 +963,11 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
                      pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
     }
     psum[half][row] = lsum;
+    ATC2_TR();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    ATC2_TR();
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -966,8 +982,10 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
     const int b = unit / p.n_heads, head = unit - b * p.n_heads;
     __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
+    ATC2_TR();
     mbar_wait(&bar_o, phase);
     tc_fence_after();
+    ATC2_TR();
     {  // out row = O / rowsum: this warp's 32 of the 64 columns
       uint32_t r[32];
       tmem_ld32(tmem_o + lane_addr + half * 32, r);
@@ -986,6 +1004,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();     // TMEM, this buffer and the row-statistic arrays are free again
+    ATC2_TR();
     buf ^= 1;
     phase ^= 1u;
   }

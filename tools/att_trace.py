@@ -10,9 +10,9 @@ path = stz.StyleTTSZSPath(cfg, stz.init_weights(cfg, 0))
 B, T, steps = 64, 64, 1
 inp = stz.synthetic_inputs(cfg, B, T, steps=steps, seed=1234)
 dev = {k: inp[k].cuda() for k in ("text_emb", "prompt_feats", "noise")}
-tr = torch.zeros(296 * 16, dtype=torch.int64, device="cuda")
-names = ["start", "alloc", "pdl", "issued", "landed", "S done", "softmax", "PV done", "epi+sync",
-         "issued2", "landed2", "S2", "softmax2", "PV2", "epi2", "-"]
+tr = torch.zeros(296 * 32, dtype=torch.int64, device="cuda")
+names = ["start", "alloc", "pdl", "produce", "landed+sync", "S done", "pass1+sync", "pass2", "fence+sync", "PV issued", "O done", "epi+sync",
+         "produce2", "landed2", "S2", "pass1", "pass2", "sync", "PVi", "O2", "epi2"]
 for which, bits in (("cross-attention", 0), ("self-attention", 2)):
     path.set_option("ablate", bits)
     for _ in range(3):
@@ -22,13 +22,13 @@ for which, bits in (("cross-attention", 0), ("self-attention", 2)):
     path.sample_style(dev["text_emb"], dev["prompt_feats"], steps, 2.0, noise=dev["noise"])
     torch.cuda.synchronize()
     path.lib.stz_debug_set_att_trace(path._h, None)
-    t = tr.view(296, 16).cpu()
+    t = tr.view(296, 32).cpu()
     print(which)
     for cta in (0, 1, 100, 200, 250, 295):
         row = t[cta]
-        d = [int(row[i] - row[0]) for i in range(16)]
+        d = [int(row[i] - row[0]) for i in range(21)]
         print(f"  cta {cta:3d}: " + "  ".join(f"{n}={v}" for n, v in zip(names, d) if v > 0))
     two = t[:216]
-    dd = (two[:, 1:15] - two[:, 0:14]).float().mean(0)
-    print("  mean phase cycles (CTAs with 2 units):", {names[i + 1]: int(dd[i]) for i in range(14)})
-    print("  mean total:", float((two[:, 14] - two[:, 0]).float().mean()))
+    dd = (two[:, 1:21] - two[:, 0:20]).float().mean(0)
+    print("  mean phase cycles (CTAs with 2 units):", {names[i + 1]: int(dd[i]) for i in range(20)})
+    print("  mean total:", float((two[:, 20] - two[:, 0]).float().mean()))
