@@ -1262,7 +1262,9 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
 // (~170 and ~50 cycles of issue each): ~1.5-2 k cycles of serial work per unit that the other 255 threads wait for at
 // the next __syncthreads.  Here warp 8 (one lane) does nothing but issue, runs AHEAD of the softmax warps (operands of
 // the unit after next in flight, S of the next unit computed while this unit's softmax runs), and meets them only on
-// mbarriers: bar_s (S ready), bar_p (P written by all 8 softmax warps), bar_o (O ready), bar_done (O drained).
+// mbarriers: bar_s (S ready), bar_p (P written by all 8 softmax warps), bar_o[2] (O ready), bar_done[2] (O drained).
+// O is double-buffered in TMEM and the epilogue of a unit is deferred until the NEXT unit's softmax has been computed,
+// so the P V round trip (issue + execution + commit) hides under that softmax.
 // The softmax warps synchronise among themselves with a named barrier.
 // ------------------------------------------------------------------------------------------------------
 constexpr int ATC3_THREADS = 288;
@@ -1276,7 +1278,7 @@ __global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __
                                                                        const __grid_constant__ CUtensorMap tmN,
                                                                        const AttnTcParams p) {
   extern __shared__ uint8_t atc_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[2], bar_s, bar_o, bar_p, bar_done;
+  __shared__ __align__(8) uint64_t bar_full[2], bar_s, bar_o[2], bar_p, bar_done[2];   // bar_o / bar_done: one per O accumulator
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t colmask[2][2][4];     // [unit parity][branch][32-column chunk]
   __shared__ float pmax[2][128], psum[2][128];
@@ -1291,9 +1293,11 @@ __global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __
     mbar_init(&bar_full[0], 1);
     mbar_init(&bar_full[1], 1);
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_o, 1);
+    mbar_init(&bar_o[0], 1);
+    mbar_init(&bar_o[1], 1);
     mbar_init(&bar_p, 8);        // one arrival per softmax warp
-    mbar_init(&bar_done, 8);
+    mbar_init(&bar_done[0], 8);
+    mbar_init(&bar_done[1], 8);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<256>(&tmem_slot);
@@ -1302,7 +1306,7 @@ __global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
+  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;     // O is double-buffered: columns 128..191 and 192..255
   pdl_sync();
 
   if (warp == 8) {
@@ -1353,19 +1357,19 @@ __global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __
       for (int it = 0; unit < p.n_units; unit += stride, ++it) {
         const int buf = it & 1;
         const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, vs = qs + 2 * ATC_TILE;
-        mbar_wait(&bar_p, it & 1);                        // P of this unit is in shared memory, S has been consumed
-        if (it > 0) mbar_wait(&bar_done, (it - 1) & 1);   // the previous unit's O has been drained
+        mbar_wait(&bar_p, it & 1);                              // P of this unit is in shared memory, S has been consumed
+        if (it > 1) mbar_wait(&bar_done[buf], ((it - 2) >> 1) & 1);   // the unit that last used this O accumulator has drained it
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
           const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
-          umma_bf16(tmem_o, da, db, idesc_o, j != 0 ? 1u : 0u);
+          umma_bf16(tmem_o + buf * 64, da, db, idesc_o, j != 0 ? 1u : 0u);
         }
-        umma_commit(&bar_o);
+        umma_commit(&bar_o[buf]);
         if (unit + stride < p.n_units) issue_s(it + 1);   // runs right behind P V: ready before the softmax warps get there
         if (unit + 2 * stride < p.n_units) {              // this unit's buffer is free once its P V has completed
-          mbar_wait(&bar_o, it & 1);
+          mbar_wait(&bar_o[buf], (it >> 1) & 1);
           produce(unit + 2 * stride, buf);
         }
       }
@@ -1375,7 +1379,34 @@ __global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __
     const int row = q4 * 32 + lane;                      // query row = TMEM lane
     const int br = row >> 6, tok = row & 63;             // rows 0..63 conditional, 64..127 unconditional
     const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
-    int it = 0;
+    // out row = O / rowsum (this warp's 32 of the 64 columns) of the `e`-th unit of this CTA
+    auto epilogue = [&](int unit, int e, float ltot) {
+      const int ob = e & 1;
+      const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
+      mbar_wait(&bar_o[ob], (e >> 1) & 1);
+      tc_fence_after();
+      const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
+      uint32_t r[32];
+      tmem_ld32(tmem_o + ob * 64 + lane_addr + half * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_done[ob]);       // this O accumulator is in registers
+      if (tok < n_tok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + j * 8) = u;
+        }
+      }
+    };
+    int it = 0, prev_unit = 0;
+    float prev_ltot = 0.f;
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
       const int buf = it & 1, par = it & 1;
       const int b = unit / p.n_heads, head = unit - b * p.n_heads;
@@ -1460,32 +1491,15 @@ __global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p);
-      // ---- out row = O / rowsum: this warp's 32 of the 64 columns
-      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
-      mbar_wait(&bar_o, par);
-      tc_fence_after();
-      {
-        const float ltot = psum[0][row] + psum[1][row];
-        const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
-        uint32_t r[32];
-        tmem_ld32(tmem_o + lane_addr + half * 32, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_done);       // O (and this unit's statistics) are in registers
-        if (tok < n_tok) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-            u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-            u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-            u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + j * 8) = u;
-          }
-        }
-      }
+      // The row sums travel to the deferred epilogue in registers (psum is rewritten by the next unit's pass 2).
+      att_named_bar_sync(1, 256);                          // both column halves' psum are visible
+      const float ltot = psum[0][row] + psum[1][row];
+      // ---- epilogue of the PREVIOUS unit: its P V ran while this unit's softmax was computed
+      if (it > 0) epilogue(prev_unit, it - 1, prev_ltot);
+      prev_unit = unit;
+      prev_ltot = ltot;
     }
+    if (it > 0) epilogue(prev_unit, it - 1, prev_ltot);
   }
   tc_fence_before();
   __syncthreads();
