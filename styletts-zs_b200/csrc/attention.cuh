@@ -1046,7 +1046,7 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
   const int row = q4 * 32 + lane;
   const int br = row >> 6, tok = row & 63;
   const int n_tok = p.n_style;
-  const int nbt = (p.T + 127) >> 7, nblk = nbt + 1;       // text blocks, then the prompt + null block
+  const int nbt = (p.T + 127) >> 7;                        // text blocks; block id nbt = the prompt + null block
 
   if (tid == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmT); prefetch_tmap(&tmP); prefetch_tmap(&tmN);
@@ -1066,8 +1066,9 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
   const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
   pdl_sync();
 
-  auto load_block = [&](int b, int head, int j) {     // tid == 0
-    const int buf = j & 1;
+  // jj = position in this unit's block sequence (selects the buffer), j = block id (text block, or nbt = prompt + null)
+  auto load_block = [&](int b, int head, int jj, int j) {     // tid == 0
+    const int buf = jj & 1;
     const uint32_t ks = kv0 + buf * 2 * ATC_TILE, vs = ks + ATC_TILE, bar = smem_u32(&bar_kv[buf]);
     const int hc = head * ATT_DH;
     if (j < nbt) {
@@ -1090,9 +1091,9 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
 
   // tid 0 only: S_j = Q K_j^T as soon as block j has landed (issued right behind the previous block's P V, so its latency
   // hides under that block's tail instead of heading the next block's dependency chain)
-  auto issue_s = [&](int j) {
-    const int buf = j & 1;
-    if (j == 0) { mbar_wait(&bar_q, ph_q); ph_q ^= 1u; }
+  auto issue_s = [&](int jj) {
+    const int buf = jj & 1;
+    if (jj == 0) { mbar_wait(&bar_q, ph_q); ph_q ^= 1u; }
     if (buf == 0) { mbar_wait(&bar_kv[0], ph_kv0); ph_kv0 ^= 1u; } else { mbar_wait(&bar_kv[1], ph_kv1); ph_kv1 ^= 1u; }
     tc_fence_after();
     const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(kv0 + buf * 2 * ATC_TILE);
@@ -1103,17 +1104,25 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
 
   for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
     const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+    // text masks are prefix masks: a text block whose first key is padding is padding throughout and is skipped
+    int nbv = nbt;
+    if (p.tmask != nullptr) {
+      nbv = 1;
+      for (int j = 1; j < nbt; ++j) nbv += p.tmask[static_cast<size_t>(b) * p.T + j * 128] != 0 ? 1 : 0;
+    }
+    const int nblk = nbv + 1;                  // valid text blocks, then the prompt + null block (id nbt)
     if (tid == 0) {
       mbar_expect_tx(&bar_q, 2u * 8192u);
       tma_load_3d_u32(qs, &tmQ, smem_u32(&bar_q), head * ATT_DH, 0, b * n_tok);
       tma_load_3d_u32(qs + 8192, &tmQ, smem_u32(&bar_q), head * ATT_DH, 1, b * n_tok);
-      load_block(b, head, 0);
-      load_block(b, head, 1);       // nblk >= 2 always
+      load_block(b, head, 0, 0);
+      load_block(b, head, 1, nblk > 2 ? 1 : nbt);       // nblk >= 2 always
       issue_s(0);
     }
     float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      const int buf = j & 1;
+    for (int jj = 0; jj < nblk; ++jj) {
+      const int j = jj < nbv ? jj : nbt;         // block id
+      const int buf = jj & 1;
       const uint32_t ks = kv0 + buf * 2 * ATC_TILE, vs = ks + ATC_TILE;
       if (warp < 4) {   // visibility of key row warp * 32 + lane of this block -> per-branch 32-key chunk masks
         const int kr = warp * 32 + lane;
@@ -1134,9 +1143,9 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
       mbar_wait(&bar_s, ph_s); ph_s ^= 1u;
       // the previous block's P V has completed: its P tiles may be overwritten, O may be rescaled, and its K / V buffer
       // may be refilled with block j + 1
-      if (j > 0) {
+      if (jj > 0) {
         mbar_wait(&bar_o, ph_o); ph_o ^= 1u;
-        if (tid == 0 && j + 1 < nblk) load_block(b, head, j + 1);
+        if (tid == 0 && jj + 1 < nblk) load_block(b, head, jj + 1, jj + 1 < nbv ? jj + 1 : nbt);
       }
       tc_fence_after();
 
@@ -1199,7 +1208,7 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
       }
       psum[half][row] = lsum;
       // ---- rescale this warp's 32 columns of O where the running max moved
-      if (j > 0) {
+      if (jj > 0) {
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
           uint32_t r[32];
           tmem_ld32(tmem_o + lane_addr + half * 32, r);
@@ -1220,10 +1229,10 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
         for (int i = 0; i < 8; ++i) {
           const uint64_t da = umma_desc_sw128((i >> 2) ? p1s : ks) + 2 * (i & 3);
           const uint64_t db = umma_desc_sw128_mn(vs + i * 2048);
-          umma_bf16(tmem_o, da, db, idesc_o, (j | i) != 0 ? 1u : 0u);
+          umma_bf16(tmem_o, da, db, idesc_o, (jj | i) != 0 ? 1u : 0u);
         }
         umma_commit(&bar_o);
-        if (j + 1 < nblk) issue_s(j + 1);      // S is free: every warp finished reading S_j before the barrier above
+        if (jj + 1 < nblk) issue_s(jj + 1);      // S is free: every warp finished reading S_j before the barrier above
       }
     }
     // ---- out row = O / rowsum
