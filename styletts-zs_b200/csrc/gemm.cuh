@@ -44,6 +44,9 @@ struct GemmParams {
   __nv_bfloat16* xin;
   const float* coef;    // device: {cx, cm, cF, cn, cin_next, cfg_scale, dest(0 = x, 1 = xmid), 0}
   float* tap;           // optional [B*K, N] copy of the guided F
+  // optional [ceil(M / 128)] flags: 0 = every row of that 128-row tile is padding, the tile is skipped (its output rows
+  // keep whatever they held; only legal when nothing downstream reads them: the duration predictor with text masks)
+  const uint8_t* tile_needed;
 };
 
 constexpr int GEMM_BM = 128;

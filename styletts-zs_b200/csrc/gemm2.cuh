@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   constexpr int kPre = STAGES;
   int n_pre = 0;
   if constexpr (CM == 1) {
-    if (warp == 0 && lane == 0 && unit0 < n_tiles) {
+    if (warp == 0 && lane == 0 && unit0 < n_tiles && p.tile_needed == nullptr) {   // (the skip list is produced upstream: not readable yet)
       n_pre = num_kb < kPre ? num_kb : kPre;
       const int tile_n0 = unit0 % tiles_n;
       for (int s = 0; s < n_pre; ++s) {
@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       uint32_t phase = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
         const int tile_m = CM * (tile / tiles_n) + crank, tile_n = tile % tiles_n;
+        if (CM == 1 && p.tile_needed != nullptr && p.tile_needed[tile_m] == 0) continue;   // all-padding rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       int stage = 0, tcount = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
+        if (CM == 1 && p.tile_needed != nullptr && p.tile_needed[tile / tiles_n] == 0) continue;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     int tcount = 0;
     for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
       const int tile_m = CM * (tile / tiles_n) + crank, tile_n = tile % tiles_n;
+      if (CM == 1 && p.tile_needed != nullptr && p.tile_needed[tile_m] == 0) continue;
       const int m0 = tile_m * GEMM_BM + q * 32;
       const int m = m0 + lane;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;

@@ -45,6 +45,23 @@ __global__ void __launch_bounds__(256) style_pool_attn_kernel(const float* __res
   }
 }
 
+// needed[t] = 1 iff any of the rows 128 t .. 128 t + 127 of a [rows] mask is valid: the predictor's GEMMs skip 128-row
+// tiles that hold nothing but padding (variable-length batches: about half of cfg4's B x T rows).
+__global__ void __launch_bounds__(256) tile_needed_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ needed, int rows) {
+  pdl_sync();
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int r0 = warp * 128;
+  if (r0 >= rows) return;
+  int any = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + i * 32 + lane;
+    any |= (r < rows && mask[r] != 0) ? 1 : 0;
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) needed[warp] = static_cast<uint8_t>(any);
+}
+
 // a-8, product kernel: one CTA = SP_TOK consecutive tokens of one utterance; the utterance's projected K / V
 // (K x ds fp32 each) are staged in shared memory once, then a warp handles one token at a time:
 //   scores  : lane = key (keys j and j + 32), q broadcast by shuffle, K rows padded to ds + 1 (conflict-free);

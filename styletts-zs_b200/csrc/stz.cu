@@ -50,6 +50,7 @@ struct Workspace {
   float *sq, *sk, *sv, *sa, *stok, *G, *xa, *xb, *gb, *skv;
   bf16 *pa, *ps3, *pq, *pstyle3, *psa3;
   int *lens, *perm;
+  uint8_t* tile_needed;   // predictor: per 128-row tile of [B*T], 1 = holds a valid token
   // host-call staging (stz_synthesize_host)
   float *st_text, *st_prompt, *st_noise, *st_style;
   uint8_t *st_tmask, *st_pmask, *hs_tmask, *hs_pmask;
@@ -572,7 +573,7 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   WANT(ffh, R * c.d_ff, bf16);
   WANT(sq, BT * ds, float); WANT(sk, BK * ds, float); WANT(sv, BK * ds, float); WANT(sa, BT * ds, float);
   WANT(stok, BT * ds, float); WANT(G, BT * h8, float); WANT(xa, BT * dh, float); WANT(xb, BT * dh, float);
-  WANT(gb, BT * 2 * dh, float); WANT(lens, B, int); WANT(perm, B, int);
+  WANT(gb, BT * 2 * dh, float); WANT(lens, B, int); WANT(perm, B, int); WANT(tile_needed, BT / 128 + 2, uint8_t);
   WANT(skv, BK * 2 * ds, float);
   WANT(pa, (BT + 128) * 3 * (dh + ds), bf16); WANT(ps3, (BT + 128) * 3 * ds, bf16); WANT(pq, (BT + 128) * 3 * c.d_text, bf16);
   WANT(pstyle3, (BK + 128) * 3 * Ds, bf16); WANT(psa3, (BT + 128) * 3 * ds, bf16);
@@ -1337,9 +1338,17 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     KCHECK(H);
     return 0;
   };
-  auto gemm3 = [&](const bf16* A, int K3, int rows, const bf16* W3, const float* bias, float* out, int N) -> int {
+  // with text masks, 128-row tiles of [B*T] that are padding throughout are skipped by the token-row GEMMs (their rows feed
+  // nothing: the recurrence, AdaLN and the duration head all honour the mask)
+  const uint8_t* needed = nullptr;
+  if (tmask != nullptr && tc && impl == 0) {
+    launch_k(tile_needed_kernel, cdiv(cdiv(BT, 128), 8), 256, 0, st, tmask, w.tile_needed, BT); KCHECK(H);
+    needed = w.tile_needed;
+  }
+  auto gemm3 = [&](const bf16* A, int K3, int rows, const bf16* W3, const float* bias, float* out, int N, bool token_rows = true) -> int {
     GemmParams p{};
     p.M = rows; p.N = N; p.K = K3; p.bias = bias; p.out = out; p.ldo = N;
+    p.tile_needed = token_rows ? needed : nullptr;
     return gemm<EPI_F32>(H, st, impl, A, K3, rows, W3, p);
   };
   // a-8: per-token style summary
@@ -1357,7 +1366,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     RET(split_rows(text, c.d_text, c.d_text, w.pa, 3 * kin, kin, 0, BT));          // x part of layer 0's [x | s_tok]
     RET(split_rows(style, Ds, Ds, w.pstyle3, 3 * Ds, Ds, 0, BK));
     RET(gemm3(w.pq, 3 * c.d_text, BT, H->wq3, W32(H, "sp.q.b"), w.sq, ds));
-    RET(gemm3(w.pstyle3, 3 * Ds, BK, H->wkv3, H->b_kv, w.skv, 2 * ds));
+    RET(gemm3(w.pstyle3, 3 * Ds, BK, H->wkv3, H->b_kv, w.skv, 2 * ds, false));   // style-code rows, not token rows
     RET(style_pool(w.skv, w.skv + ds, 2 * ds));
     RET(split_rows(w.sa, ds, ds, w.psa3, 3 * ds, ds, 0, BT));
     RET(gemm3(w.psa3, 3 * ds, BT, H->wo3, W32(H, "sp.o.b"), w.stok, ds));
