@@ -51,6 +51,7 @@ struct Workspace {
   bf16 *pa, *ps3, *pq, *pstyle3, *psa3;
   int *lens, *perm;
   uint8_t* tile_needed;   // predictor: per 128-row tile of [B*T], 1 = holds a valid token
+  uint8_t* tile_needed_ctx;   // sampler: the same for the context rows [B*T text ; B*P prompt] (prompt tiles always 1)
   // host-call staging (stz_synthesize_host)
   float *st_text, *st_prompt, *st_noise, *st_style;
   uint8_t *st_tmask, *st_pmask, *hs_tmask, *hs_pmask;
@@ -573,7 +574,7 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   WANT(ffh, R * c.d_ff, bf16);
   WANT(sq, BT * ds, float); WANT(sk, BK * ds, float); WANT(sv, BK * ds, float); WANT(sa, BT * ds, float);
   WANT(stok, BT * ds, float); WANT(G, BT * h8, float); WANT(xa, BT * dh, float); WANT(xb, BT * dh, float);
-  WANT(gb, BT * 2 * dh, float); WANT(lens, B, int); WANT(perm, B, int); WANT(tile_needed, BT / 128 + 2, uint8_t);
+  WANT(gb, BT * 2 * dh, float); WANT(lens, B, int); WANT(perm, B, int); WANT(tile_needed, BT / 128 + 2, uint8_t); WANT(tile_needed_ctx, (BT + BP) / 128 + 4, uint8_t);
   WANT(skv, BK * 2 * ds, float);
   WANT(pa, (BT + 128) * 3 * (dh + ds), bf16); WANT(ps3, (BT + 128) * 3 * ds, bf16); WANT(pq, (BT + 128) * 3 * c.d_text, bf16);
   WANT(pstyle3, (BK + 128) * 3 * Ds, bf16); WANT(psa3, (BT + 128) * 3 * ds, bf16);
@@ -1216,9 +1217,17 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   RET(linear_f32(H, st, ACT_NONE, w.pool_text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "ptext.w"), W32(H, "ptext.b"), w.pt, d, B, d));
   RET(linear_f32(H, st, ACT_SILU, w.tfeat, c.d_time, c.d_time, nullptr, 0, 0, W32(H, "time.w1"), W32(H, "time.b1"), w.t1, d, E, d));
   RET(linear_f32(H, st, ACT_NONE, w.t1, d, d, nullptr, 0, 0, W32(H, "time.w2"), W32(H, "time.b2"), w.temb, d, E, d));
+  // Long padded text (T a multiple of 128, so GEMM row tiles coincide with the streaming attention's key blocks): row
+  // tiles that are padding throughout are skipped by the context GEMMs — the attention never visits those key blocks.
+  const uint8_t* ctx_needed = nullptr;
+  if (tmask != nullptr && impl == 0 && T % 128 == 0 && T > 128) {
+    launch_k(tile_needed_kernel, cdiv(cdiv(B * T, 128), 8), 256, 0, st, tmask, w.tile_needed_ctx, B * T); KCHECK(H);
+    CK(H, cudaMemsetAsync(w.tile_needed_ctx + B * T / 128, 1, cdiv(B * P, 128) + 1, st));
+    ctx_needed = w.tile_needed_ctx;
+  }
   {
     GemmParams p{};
-    p.M = B * T; p.N = d; p.K = c.d_text; p.bias = H->ctx_text_b; p.out = w.ctx_pre; p.ldo = d;
+    p.M = B * T; p.N = d; p.K = c.d_text; p.bias = H->ctx_text_b; p.out = w.ctx_pre; p.ldo = d; p.tile_needed = ctx_needed;
     RET(gemm<EPI_F32>(H, st, impl, w.text_bf, c.d_text, B * T, WBF(H, "ctx_text.w"), p));
   }
   if (H->wait_prompt) { CK(H, cudaStreamWaitEvent(st, H->ev_prompt, 0)); H->wait_prompt = false; }
@@ -1241,7 +1250,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   RET(ln_mod(H, st, w.ctx_pre, rows_all, d, nullptr, 0, 0, 0, 1, w.ctx_text));
   {
     GemmParams q{};
-    q.M = rows_all; q.N = L * 2 * d; q.K = d; q.bias = H->bkv_all; q.out = w.kv_text; q.ldo = L * 2 * d;
+    q.M = rows_all; q.N = L * 2 * d; q.K = d; q.bias = H->bkv_all; q.out = w.kv_text; q.ldo = L * 2 * d; q.tile_needed = ctx_needed;
     RET(gemm<EPI_BF16>(H, st, impl, w.ctx_text, d, rows_all, H->wkv_all, q));
   }
   if (H->wait_noise) { CK(H, cudaStreamWaitEvent(st, H->ev_noise, 0)); H->wait_noise = false; }

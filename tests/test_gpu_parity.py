@@ -134,10 +134,12 @@ def test_teacher_adpm2_vs_oracle(path, oracle):
     assert rel(z, z_ref) < TOL_STYLE
 
 
-@pytest.mark.parametrize("B,T,P,tlen", [(3, 29, 33, (5, 29)), (2, 77, 50, (40, 77)), (2, 130, 17, (100, 130)), (1, 257, 50, (257, 257))])
+@pytest.mark.parametrize("B,T,P,tlen", [(3, 29, 33, (5, 29)), (2, 77, 50, (40, 77)), (2, 130, 17, (100, 130)), (1, 257, 50, (257, 257)),
+                                          (3, 256, 50, (20, 120)), (2, 384, 50, (130, 384))])
 def test_odd_shapes_and_prompt_masks_vs_oracle(path, oracle, B, T, P, tlen):
     """Shapes off every tile boundary (T, P not multiples of 8 / 64 / 128; resident and streaming attention; masked
-    prompt tokens), full path: 2-step CFG student + duration predictor against the fp32 oracle."""
+    prompt tokens) and long padded text with T a multiple of 128 (all-padding row tiles / key blocks are skipped by the
+    GEMMs and the streaming attention), full path: 2-step CFG student + duration predictor against the fp32 oracle."""
     inp = stz.synthetic_inputs(CFG, B, T, P=P, steps=2, seed=900 + T, var_len=tlen)
     pm = inp["prompt_mask"].clone()
     pm[0, P // 3:] = False                       # a short prompt
