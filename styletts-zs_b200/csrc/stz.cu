@@ -36,7 +36,8 @@ static std::string g_create_error;
 // handle
 // ------------------------------------------------------------------------------------------
 struct Workspace {
-  int B = 0, T = 0, P = 0, E = 0, noise_slices = 0, mod_evals = 0;
+  int B = 0, T = 0, P = 0, E = 0, noise_slices = 0;
+  size_t mod_rows = 0;        // rows of `mod` ([n_mod] floats each): max over calls of (hoisted evaluations x 2B)
   bool mod_hoisted = false;   // this call's AdaLN modulations of ALL evaluations live in `mod` ([E][2B][n_mod])
   char* base = nullptr;
   size_t bytes = 0;
@@ -61,8 +62,13 @@ struct Workspace {
 constexpr int STZ_MAX_CHAINS = 8;
 // The sigma schedule is known before the loop, so the AdaLN modulations c[e] · Wmod^T of every evaluation can be one GEMM
 // (M = E * 2B) instead of E small ones at the head of each evaluation's dependency chain.  E * 2B * n_mod floats: 78 MB at
-// cfg2 (E = 4); the 64-evaluation teacher keeps the per-evaluation GEMM.
+// cfg2 (E = 4), 620 MB at cfg3 (64 teacher evaluations, B = 32); beyond 1 GB the per-evaluation GEMM is kept.
 constexpr int STZ_HOIST_MOD_MAX_EVALS = 8;
+constexpr size_t STZ_HOIST_MOD_MAX_BYTES = (size_t)1 << 30;
+static bool hoist_mod(const stz_config& c, int B, int E) {
+  const size_t bytes = (size_t)E * 2 * B * (9 * c.n_layers + 2) * c.d_model * sizeof(float);
+  return E <= STZ_HOIST_MOD_MAX_EVALS || bytes <= STZ_HOIST_MOD_MAX_BYTES;
+}
 
 struct stz_handle {
   stz_config cfg;
@@ -539,15 +545,14 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise_slices) {
   Workspace& w = H->ws;
-  const int mod_evals_req = E <= STZ_HOIST_MOD_MAX_EVALS ? E : 1;
-  if (w.base && B <= w.B && T <= w.T && P <= w.P && E <= w.E && noise_slices <= w.noise_slices && mod_evals_req <= w.mod_evals) return 0;
+  const size_t mod_rows_req = (size_t)(hoist_mod(H->cfg, B, E) ? E : 1) * 2 * B;
+  if (w.base && B <= w.B && T <= w.T && P <= w.P && E <= w.E && noise_slices <= w.noise_slices && mod_rows_req <= w.mod_rows) return 0;
   // grow monotonically; all cached graphs point into the old arena
   for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
   H->graphs.clear();
   if (w.base) { CK(H, cudaDeviceSynchronize()); CK(H, cudaFree(w.base)); w.base = nullptr; }
   B = B > w.B ? B : w.B; T = T > w.T ? T : w.T; P = P > w.P ? P : w.P; E = E > w.E ? E : w.E;
   noise_slices = noise_slices > w.noise_slices ? noise_slices : w.noise_slices;
-  const int mod_evals = mod_evals_req > w.mod_evals ? mod_evals_req : w.mod_evals;
   const stz_config& c = H->cfg;
   const size_t d = c.d_model, Ds = c.d_style, L = c.n_layers, K = c.n_style, n_mod = (9 * L + 2) * d;
   const size_t BT = (size_t)B * T, BP = (size_t)B * P, BK = (size_t)B * K, R = 2 * BK, NS = 2 * (size_t)B;
@@ -567,7 +572,8 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   WANT(ctx_pre, (BT + BP) * d, float);
   WANT(tfeat, (size_t)E * c.d_time, float); WANT(t1, (size_t)E * d, float); WANT(temb, (size_t)E * d, float);
   WANT(coef, (size_t)E * 8, float);
-  WANT(mod, (size_t)mod_evals * NS * n_mod, float);   // few-step samplers: every evaluation's modulations at once
+  const size_t mod_rows = mod_rows_req > w.mod_rows ? (mod_rows_req > NS ? mod_rows_req : NS) : (w.mod_rows > NS ? w.mod_rows : NS);
+  WANT(mod, mod_rows * n_mod, float);   // few-step samplers: every evaluation's modulations at once
   WANT(x, BK * Ds, float); WANT(xmid, BK * Ds, float); WANT(h, R * d, float);
   WANT(noise, (size_t)noise_slices * BK * Ds, float);
   WANT(xin, R * 3 * Ds, bf16); WANT(u, R * d, bf16); WANT(u3, R * 3 * d, bf16); WANT(qkv, R * 3 * d, bf16); WANT(att, R * d, bf16);
@@ -589,7 +595,7 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
     return fail(H, STZ_E_NOMEM, "workspace of %zu bytes: %s", off, cudaGetErrorString(e));
   }
   for (auto& pr : plan) *pr.first = w.base + pr.second;
-  w.bytes = off; w.B = B; w.T = T; w.P = P; w.E = E; w.noise_slices = noise_slices; w.mod_evals = mod_evals;
+  w.bytes = off; w.B = B; w.T = T; w.P = P; w.E = E; w.noise_slices = noise_slices; w.mod_rows = mod_rows;
   CK(H, cudaMemsetAsync(w.cvec, 0, ((size_t)E * NS * d + 128 * d) * sizeof(bf16), H->stream));
   CK(H, cudaStreamSynchronize(H->stream));
   return 0;
@@ -1234,7 +1240,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
   launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
-  w.mod_hoisted = E <= STZ_HOIST_MOD_MAX_EVALS && !(H->ablate & 256);
+  w.mod_hoisted = hoist_mod(c, B, E) && !(H->ablate & 256);
   if (w.mod_hoisted) {   // AdaLN modulations of every evaluation: mod[E * NS, n_mod] = c · Wmod^T + b
     const int n_mod = (9 * L + 2) * d;
     GemmParams p{};
