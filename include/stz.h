@@ -98,13 +98,40 @@ int stz_predict_duration(stz_handle* h, const float* text_emb_dev, const uint8_t
 int stz_regulate_length(stz_handle* h, const float* feats_dev, const int32_t* dur_dev, int B, int T, int C, int F_max,
                         float* out_frames_dev, int32_t* out_frame_lens_dev, int32_t* out_frame_tok_dev, void* cuda_stream);
 
+/* On-device noise.  After stz_set_noise_seed, a NULL `noise` argument of stz_sample_style /
+ * stz_synthesize_host means: draw every noise slice on the device — Philox4x32-10, key = seed, counter = (group of four
+ * elements inside the utterance's [K*Ds] slice, utterance lo, slice, utterance hi), Box-Muller built from individually
+ * rounded fp32 operations — bit-identical to oracle/philox.py.  Utterance b of a call is global utterance
+ * first_utterance + b: an utterance's noise does not depend on the batch or the GPU it is sampled on.  Without a seed a
+ * NULL noise argument is STZ_E_ARG. */
+int stz_set_noise_seed(stz_handle* h, uint64_t seed, uint64_t first_utterance);
+
+/* The generator on its own (unit tests, callers that want the tensor): out_dev [slices, B, n_per_utt] fp32,
+ * n_per_utt % 4 == 0. */
+int stz_philox_normal(uint64_t seed, uint64_t first_utterance, int slices, int B, int n_per_utt, float* out_dev,
+                      int device, void* cuda_stream);
+
 /* Host-buffer form of the whole path (what a non-CUDA caller binds): copies the inputs H2D,
  * runs sample_style and (if out_dur_host != NULL) predict_duration on the sampled codes, copies
- * the results D2H and synchronises.  All pointers are host pointers. */
+ * the results D2H and synchronises.  All pointers are host pointers; `noise` may be NULL after stz_set_noise_seed
+ * (no noise H2D at all). */
 int stz_synthesize_host(stz_handle* h, const float* text_emb, const uint8_t* text_mask,
                         const float* prompt_feats, const uint8_t* prompt_mask, const float* noise,
                         int B, int T, int P, int steps, float cfg_scale, int sampler_kind,
                         float* out_style, int32_t* out_dur);
+
+/* The same call split for pipelining (serving loops): _submit enqueues the H2D copies (copy stream), the compute
+ * (internal stream) and the D2H copies (a third stream) of one batch into `slot` (0 or 1) and returns; _wait blocks until
+ * that slot's outputs are in the host buffers.  Each slot has its own device staging, so submitting slot 1 before
+ * waiting for slot 0 overlaps batch i+1's input copies with batch i's compute:
+ *     submit(0, batch 0); for i: submit((i+1)&1, batch i+1); wait(i&1);
+ * Host buffers handed to _submit (inputs and outputs) belong to the library until the slot's _wait returns; submitting
+ * a slot that is still in flight first waits for it.  stz_synthesize_host == _submit(0) + _wait(0). */
+int stz_synthesize_host_submit(stz_handle* h, int slot, const float* text_emb, const uint8_t* text_mask,
+                               const float* prompt_feats, const uint8_t* prompt_mask, const float* noise,
+                               int B, int T, int P, int steps, float cfg_scale, int sampler_kind,
+                               float* out_style_host, int32_t* out_dur_host);
+int stz_synthesize_host_wait(stz_handle* h, int slot);
 
 /* ---- introspection / unit-test entry points (not part of the drop-in surface) ---------- */
 

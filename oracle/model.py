@@ -178,11 +178,17 @@ class OraclePath:
     # ---- a-7 ------------------------------------------------------------------------
     @torch.no_grad()
     def sample_style(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
-                     prompt_mask=None, noise=None, sampler="student") -> torch.Tensor:
+                     prompt_mask=None, noise=None, sampler="student", seed: Optional[int] = None,
+                     first_utterance: int = 0) -> torch.Tensor:
         cfg = self.cfg
         B, T, _ = text_emb.shape
         P = prompt_feats.shape[1]
         kind = SAMPLER_TEACHER if sampler in ("teacher", SAMPLER_TEACHER) else SAMPLER_STUDENT
+        if noise is None and seed is not None:   # §8(f) rank 4: counter-based noise, oracle/philox.py
+            from . import philox
+            ns = steps + 1 if kind == SAMPLER_TEACHER else 1
+            noise = torch.from_numpy(philox.normal_noise(seed, first_utterance, ns, B, cfg.n_style * cfg.d_style))
+            noise = noise.reshape(ns, B, cfg.n_style, cfg.d_style)
         if text_mask is None:
             text_mask = torch.ones(B, T, dtype=torch.bool)
         if prompt_mask is None:

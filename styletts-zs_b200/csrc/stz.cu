@@ -22,6 +22,7 @@
 #include "gemm_ln.cuh"
 #include "gemm_ln2.cuh"
 #include "gemm_ln3.cuh"
+#include "philox.cuh"
 #include "predictor.cuh"
 #include "predictor_tc.cuh"
 #include "regulator.cuh"
@@ -53,10 +54,15 @@ struct Workspace {
   int *lens, *perm;
   uint8_t* tile_needed;   // predictor: per 128-row tile of [B*T], 1 = holds a valid token
   uint8_t* tile_needed_ctx;   // sampler: the same for the context rows [B*T text ; B*P prompt] (prompt tiles always 1)
-  // host-call staging (stz_synthesize_host)
-  float *st_text, *st_prompt, *st_noise, *st_style;
-  uint8_t *st_tmask, *st_pmask, *hs_tmask, *hs_pmask;
-  int32_t* st_dur;
+  // graph-baked mask staging (device-pointer calls)
+  uint8_t *st_tmask, *st_pmask;
+  // host-call staging (stz_synthesize_host / _submit): one set per pipeline slot, so the H2D copies of call i+1 run
+  // while call i computes
+  struct HostStage {
+    float *text, *prompt, *noise, *style;
+    uint8_t *tmask, *pmask;
+    int32_t* dur;
+  } hs[2];
 };
 
 constexpr int STZ_MAX_CHAINS = 8;
@@ -96,9 +102,17 @@ struct stz_handle {
   cudaStream_t stream = nullptr;      // internal stream (create-time work, host entry point, capture)
   // host entry point: prompt / noise H2D and the style D2H run on a second stream, overlapping the text-side
   // conditioning prep and the duration predictor
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_prompt = nullptr, ev_noise = nullptr, ev_style = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D
+  cudaStream_t out_stream = nullptr;    // D2H
+  struct HostSlot {
+    cudaEvent_t ev_text = nullptr, ev_prompt = nullptr, ev_noise = nullptr, ev_style = nullptr, ev_dur = nullptr, ev_done = nullptr;
+    bool busy = false;
+  } slot[2];
+  cudaEvent_t cur_ev_prompt = nullptr, cur_ev_noise = nullptr;   // the running host call's pending H2D events
   bool wait_prompt = false, wait_noise = false;
+  // noise == NULL: draw it on the device (philox.cuh) from this seed; utterance b of a call is global utterance noise_first_utt + b
+  bool noise_seeded = false;
+  uint64_t noise_seed = 0, noise_first_utt = 0;
   // calls share one workspace: a call enqueued on a different stream than the previous one first waits for it
   cudaStream_t last_stream = nullptr;
   cudaEvent_t last_ev = nullptr;
@@ -584,10 +598,12 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   WANT(skv, BK * 2 * ds, float);
   WANT(pa, (BT + 128) * 3 * (dh + ds), bf16); WANT(ps3, (BT + 128) * 3 * ds, bf16); WANT(pq, (BT + 128) * 3 * c.d_text, bf16);
   WANT(pstyle3, (BK + 128) * 3 * Ds, bf16); WANT(psa3, (BT + 128) * 3 * ds, bf16);
-  WANT(st_text, BT * c.d_text, float); WANT(st_prompt, BP * c.d_prompt, float);
-  WANT(st_noise, (size_t)(noise_slices > 1 ? noise_slices : 1) * BK * Ds, float); WANT(st_style, BK * Ds, float);
-  WANT(st_tmask, BT, uint8_t); WANT(st_pmask, BP, uint8_t); WANT(st_dur, BT, int32_t);
-  WANT(hs_tmask, BT, uint8_t); WANT(hs_pmask, BP, uint8_t);
+  WANT(st_tmask, BT, uint8_t); WANT(st_pmask, BP, uint8_t);
+  for (int sl = 0; sl < 2; ++sl) {
+    WANT(hs[sl].text, BT * c.d_text, float); WANT(hs[sl].prompt, BP * c.d_prompt, float);
+    WANT(hs[sl].noise, (size_t)(noise_slices > 1 ? noise_slices : 1) * BK * Ds, float); WANT(hs[sl].style, BK * Ds, float);
+    WANT(hs[sl].tmask, BT, uint8_t); WANT(hs[sl].pmask, BP, uint8_t); WANT(hs[sl].dur, BT, int32_t);
+  }
 #undef WANT
   cudaError_t e = cudaMalloc(&w.base, off);
   if (e != cudaSuccess) {
@@ -705,9 +721,10 @@ extern "C" void stz_destroy(stz_handle* H) {
   cudaFree(H->ws.base); cudaFree(H->w32); cudaFree(H->wbf); cudaFree(H->ctx_text_b); cudaFree(H->ctx_prompt_b);
   cudaFree(H->wq3); cudaFree(H->wkv3); cudaFree(H->wo3); cudaFree(H->wih3); cudaFree(H->wada3); cudaFree(H->b_kv);
   cudaFree(H->wkv_all); cudaFree(H->bkv_all);
-  if (H->ev_prompt) cudaEventDestroy(H->ev_prompt);
-  if (H->ev_noise) cudaEventDestroy(H->ev_noise);
-  if (H->ev_style) cudaEventDestroy(H->ev_style);
+  for (auto& sl : H->slot)
+    for (cudaEvent_t e : {sl.ev_text, sl.ev_prompt, sl.ev_noise, sl.ev_style, sl.ev_dur, sl.ev_done})
+      if (e) cudaEventDestroy(e);
+  if (H->out_stream) cudaStreamDestroy(H->out_stream);
   if (H->fork_ev) cudaEventDestroy(H->fork_ev);
   for (int i = 1; i < STZ_MAX_CHAINS; ++i) {
     if (H->join_ev[i]) cudaEventDestroy(H->join_ev[i]);
@@ -735,9 +752,10 @@ static int create_impl(stz_handle* H, const float* weights_host) {
   CK(H, cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
   CK(H, cudaEventCreateWithFlags(&H->last_ev, cudaEventDisableTiming));
   CK(H, cudaStreamCreateWithFlags(&H->copy_stream, cudaStreamNonBlocking));
-  CK(H, cudaEventCreateWithFlags(&H->ev_prompt, cudaEventDisableTiming));
-  CK(H, cudaEventCreateWithFlags(&H->ev_noise, cudaEventDisableTiming));
-  CK(H, cudaEventCreateWithFlags(&H->ev_style, cudaEventDisableTiming));
+  CK(H, cudaStreamCreateWithFlags(&H->out_stream, cudaStreamNonBlocking));
+  for (auto& sl : H->slot)
+    for (cudaEvent_t* e : {&sl.ev_text, &sl.ev_prompt, &sl.ev_noise, &sl.ev_style, &sl.ev_dur, &sl.ev_done})
+      CK(H, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   CK(H, cudaEventCreateWithFlags(&H->fork_ev, cudaEventDisableTiming));
   for (int i = 1; i < STZ_MAX_CHAINS; ++i) {
     CK(H, cudaStreamCreateWithFlags(&H->chain_stream[i], cudaStreamNonBlocking));
@@ -1196,7 +1214,8 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
                              const uint8_t* pmask, const float* noise, int B, int T, int P, int steps, float cfg_scale,
                              int kind, float* out, cudaStream_t st) {
   const stz_config& c = H->cfg;
-  if (!text || !prompt || !noise || !out) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (!text || !prompt || !out) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (!noise && !H->noise_seeded) return fail(H, STZ_E_ARG, "noise is NULL and no seed was set (stz_set_noise_seed)");
   if (B < 1 || T < 1 || P < 1 || steps < 1 || steps > 1024) return fail(H, STZ_E_ARG, "bad sizes B=%d T=%d P=%d steps=%d", B, T, P, steps);
   if (kind != STZ_SAMPLER_STUDENT && kind != STZ_SAMPLER_TEACHER) return fail(H, STZ_E_ARG, "bad sampler kind %d", kind);
   const int E = kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
@@ -1236,7 +1255,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     p.M = B * T; p.N = d; p.K = c.d_text; p.bias = H->ctx_text_b; p.out = w.ctx_pre; p.ldo = d; p.tile_needed = ctx_needed;
     RET(gemm<EPI_F32>(H, st, impl, w.text_bf, c.d_text, B * T, WBF(H, "ctx_text.w"), p));
   }
-  if (H->wait_prompt) { CK(H, cudaStreamWaitEvent(st, H->ev_prompt, 0)); H->wait_prompt = false; }
+  if (H->wait_prompt) { CK(H, cudaStreamWaitEvent(st, H->cur_ev_prompt, 0)); H->wait_prompt = false; }
   launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
   launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
@@ -1259,11 +1278,16 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     q.M = rows_all; q.N = L * 2 * d; q.K = d; q.bias = H->bkv_all; q.out = w.kv_text; q.ldo = L * 2 * d; q.tile_needed = ctx_needed;
     RET(gemm<EPI_BF16>(H, st, impl, w.ctx_text, d, rows_all, H->wkv_all, q));
   }
-  if (H->wait_noise) { CK(H, cudaStreamWaitEvent(st, H->ev_noise, 0)); H->wait_noise = false; }
+  if (H->wait_noise) { CK(H, cudaStreamWaitEvent(st, H->cur_ev_noise, 0)); H->wait_noise = false; }
   // ---- sampler state --------------------------------------------------------------------
-  launch_k(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0); KCHECK(H);
-  if (kind == STZ_SAMPLER_TEACHER)
+  if (!noise) {   // every slice drawn on the device, bit-identical to oracle/philox.py
+    launch_k(philox_normal_kernel, ew_grid((size_t)slices * BK * Ds / 4), 256, 0, st, w.noise, (uint32_t)H->noise_seed,
+             (uint32_t)(H->noise_seed >> 32), (unsigned long long)H->noise_first_utt, slices, B, K * Ds / 4); KCHECK(H);
+    noise = w.noise;
+  } else if (kind == STZ_SAMPLER_TEACHER) {
     CK(H, cudaMemcpyAsync(w.noise, noise, (size_t)slices * BK * Ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  launch_k(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0); KCHECK(H);
   H->launches += H->cur_launches;
   H->cur_launches = 0;
 
@@ -1504,52 +1528,120 @@ extern "C" int stz_regulate_length(stz_handle* H, const float* feats_dev, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// on-device noise
+// ------------------------------------------------------------------------------------------
+extern "C" int stz_set_noise_seed(stz_handle* H, uint64_t seed, uint64_t first_utterance) {
+  if (!H) return STZ_E_ARG;
+  H->noise_seeded = true;
+  H->noise_seed = seed;
+  H->noise_first_utt = first_utterance;
+  return 0;
+}
+
+extern "C" int stz_philox_normal(uint64_t seed, uint64_t first_utterance, int slices, int B, int n_per_utt, float* out_dev,
+                                 int device, void* cuda_stream) {
+  if (!out_dev) return fail(nullptr, STZ_E_ARG, "null argument");
+  if (slices < 1 || B < 1 || n_per_utt < 4 || n_per_utt % 4) return fail(nullptr, STZ_E_SHAPE, "slices, B >= 1 and n_per_utt %% 4 == 0 required");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, STZ_E_DEVICE, "cudaSetDevice(%d) failed", device);
+  const size_t groups = (size_t)slices * B * (n_per_utt / 4);
+  const size_t blocks = (groups + 255) / 256;
+  philox_normal_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)cuda_stream>>>(
+      out_dev, (uint32_t)seed, (uint32_t)(seed >> 32), (unsigned long long)first_utterance, slices, B, n_per_utt / 4);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, STZ_E_CUDA, "philox_normal_kernel -> %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // host-buffer end-to-end entry point
 // ------------------------------------------------------------------------------------------
-extern "C" int stz_synthesize_host(stz_handle* H, const float* text_emb, const uint8_t* text_mask,
-                                   const float* prompt_feats, const uint8_t* prompt_mask, const float* noise, int B, int T,
-                                   int P, int steps, float cfg_scale, int sampler_kind, float* out_style, int32_t* out_dur) {
+static int host_wait_slot(stz_handle* H, int slot) {
+  if (!H->slot[slot].busy) return 0;
+  H->slot[slot].busy = false;
+  CK(H, cudaEventSynchronize(H->slot[slot].ev_done));
+  return 0;
+}
+
+// Two-slot pipeline: the H2D copies run on copy_stream, compute on the internal stream, the D2H copies on out_stream, and
+// every slot has its own device staging — so between _submit(slot) and _wait(slot) the caller may _submit the other slot,
+// whose input copies then overlap this slot's compute.  Host buffers of a slot stay owned by the library until its _wait.
+extern "C" int stz_synthesize_host_submit(stz_handle* H, int slot, const float* text_emb, const uint8_t* text_mask,
+                                          const float* prompt_feats, const uint8_t* prompt_mask, const float* noise, int B,
+                                          int T, int P, int steps, float cfg_scale, int sampler_kind, float* out_style,
+                                          int32_t* out_dur) {
   if (!H) return STZ_E_ARG;
-  if (!text_emb || !prompt_feats || !noise || !out_style) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (slot < 0 || slot > 1) return fail(H, STZ_E_ARG, "slot must be 0 or 1");
+  if (!text_emb || !prompt_feats || !out_style) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (!noise && !H->noise_seeded) return fail(H, STZ_E_ARG, "noise is NULL and no seed was set (stz_set_noise_seed)");
   if (B < 1 || T < 1 || P < 1 || steps < 1) return fail(H, STZ_E_ARG, "bad sizes");
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   const stz_config& c = H->cfg;
   const int E = sampler_kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
   const int slices = sampler_kind == STZ_SAMPLER_TEACHER ? steps + 1 : 1;
+  RET(host_wait_slot(H, slot));                       // resubmitting a slot first retires its previous call
+  {
+    const Workspace& w0 = H->ws;
+    const size_t mod_rows_req = (size_t)(hoist_mod(c, B, E) ? E : 1) * 2 * B;
+    const bool grows = !w0.base || B > w0.B || T > w0.T || P > w0.P || E > w0.E || slices > w0.noise_slices || mod_rows_req > w0.mod_rows;
+    if (grows) RET(host_wait_slot(H, slot ^ 1));      // the arena is reallocated: nothing may be in flight
+  }
   RET(ensure_workspace(H, B, T, P, E, slices));
   Workspace& w = H->ws;
-  cudaStream_t st = H->stream;
-  RET(order_after_previous_call(H, st));
+  Workspace::HostStage& hs = w.hs[slot];
+  stz_handle::HostSlot& sl = H->slot[slot];
+  cudaStream_t st = H->stream, cs = H->copy_stream, os = H->out_stream;
   const size_t BK = (size_t)B * c.n_style, BT = (size_t)B * T, BP = (size_t)B * P;
-  // Main stream: masks + text H2D, then compute.  Copy stream: prompt and noise H2D (consumed after the text-side
-  // prep / at state initialisation: sample_style_impl waits on the events), later the style D2H (overlaps the
-  // duration predictor).  The staging buffers are only ever touched by this entry point, which synchronises both
-  // streams before returning, so the copy stream needs no ordering against earlier calls.
-  cudaStream_t cs = H->copy_stream;
+  // copy stream: masks + text (gate the whole call), then prompt and noise (consumed after the text-side prep / at state
+  // initialisation: sample_style_impl waits on their events)
   uint8_t *tm = nullptr, *pm = nullptr;
-  if (text_mask) { tm = w.hs_tmask; CK(H, cudaMemcpyAsync(tm, text_mask, BT, cudaMemcpyHostToDevice, st)); }
-  if (prompt_mask) { pm = w.hs_pmask; CK(H, cudaMemcpyAsync(pm, prompt_mask, BP, cudaMemcpyHostToDevice, st)); }
-  CK(H, cudaMemcpyAsync(w.st_text, text_emb, BT * c.d_text * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(H, cudaMemcpyAsync(w.st_prompt, prompt_feats, BP * c.d_prompt * sizeof(float), cudaMemcpyHostToDevice, cs));
-  CK(H, cudaEventRecord(H->ev_prompt, cs));
-  CK(H, cudaMemcpyAsync(w.st_noise, noise, (size_t)slices * BK * c.d_style * sizeof(float), cudaMemcpyHostToDevice, cs));
-  CK(H, cudaEventRecord(H->ev_noise, cs));
-  H->wait_prompt = H->wait_noise = true;
-  int rc = sample_style_impl(H, w.st_text, tm, w.st_prompt, pm, w.st_noise, B, T, P, steps, cfg_scale, sampler_kind, w.st_style, st);
-  H->wait_prompt = H->wait_noise = false;
-  if (rc != 0) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); return rc; }
-  CK(H, cudaEventRecord(H->ev_style, st));
-  CK(H, cudaStreamWaitEvent(cs, H->ev_style, 0));
-  CK(H, cudaMemcpyAsync(out_style, w.st_style, BK * c.d_style * sizeof(float), cudaMemcpyDeviceToHost, cs));
-  if (out_dur) {
-    int32_t* dur_dev = w.st_dur;
-    rc = predict_duration_impl(H, w.st_text, tm, w.st_style, B, T, dur_dev, nullptr, st);
-    if (rc != 0) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); return rc; }
-    CK(H, cudaMemcpyAsync(out_dur, dur_dev, BT * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (text_mask) { tm = hs.tmask; CK(H, cudaMemcpyAsync(tm, text_mask, BT, cudaMemcpyHostToDevice, cs)); }
+  if (prompt_mask) { pm = hs.pmask; CK(H, cudaMemcpyAsync(pm, prompt_mask, BP, cudaMemcpyHostToDevice, cs)); }
+  CK(H, cudaMemcpyAsync(hs.text, text_emb, BT * c.d_text * sizeof(float), cudaMemcpyHostToDevice, cs));
+  CK(H, cudaEventRecord(sl.ev_text, cs));
+  CK(H, cudaMemcpyAsync(hs.prompt, prompt_feats, BP * c.d_prompt * sizeof(float), cudaMemcpyHostToDevice, cs));
+  CK(H, cudaEventRecord(sl.ev_prompt, cs));
+  if (noise) {
+    CK(H, cudaMemcpyAsync(hs.noise, noise, (size_t)slices * BK * c.d_style * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CK(H, cudaEventRecord(sl.ev_noise, cs));
   }
-  CK(H, cudaStreamSynchronize(st));
-  CK(H, cudaStreamSynchronize(cs));
+  sl.busy = true;
+  auto bail = [&](int rc) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); cudaStreamSynchronize(os); sl.busy = false; return rc; };
+  if (cudaStreamWaitEvent(st, sl.ev_text, 0) != cudaSuccess) return bail(fail(H, STZ_E_CUDA, "cudaStreamWaitEvent failed"));
+  H->cur_ev_prompt = sl.ev_prompt; H->cur_ev_noise = sl.ev_noise;
+  H->wait_prompt = true;
+  H->wait_noise = noise != nullptr;
+  int rc = sample_style_impl(H, hs.text, tm, hs.prompt, pm, noise ? hs.noise : nullptr, B, T, P, steps, cfg_scale, sampler_kind, hs.style, st);
+  H->wait_prompt = H->wait_noise = false;
+  if (rc != 0) return bail(rc);
+  // style D2H overlaps the duration predictor
+  if (cudaEventRecord(sl.ev_style, st) != cudaSuccess || cudaStreamWaitEvent(os, sl.ev_style, 0) != cudaSuccess ||
+      cudaMemcpyAsync(out_style, hs.style, BK * c.d_style * sizeof(float), cudaMemcpyDeviceToHost, os) != cudaSuccess)
+    return bail(fail(H, STZ_E_CUDA, "style D2H failed"));
+  if (out_dur) {
+    rc = predict_duration_impl(H, hs.text, tm, hs.style, B, T, hs.dur, nullptr, st);
+    if (rc != 0) return bail(rc);
+    if (cudaEventRecord(sl.ev_dur, st) != cudaSuccess || cudaStreamWaitEvent(os, sl.ev_dur, 0) != cudaSuccess ||
+        cudaMemcpyAsync(out_dur, hs.dur, BT * sizeof(int32_t), cudaMemcpyDeviceToHost, os) != cudaSuccess)
+      return bail(fail(H, STZ_E_CUDA, "duration D2H failed"));
+  }
+  if (cudaEventRecord(sl.ev_done, os) != cudaSuccess) return bail(fail(H, STZ_E_CUDA, "cudaEventRecord failed"));
   return 0;
+}
+
+extern "C" int stz_synthesize_host_wait(stz_handle* H, int slot) {
+  if (!H) return STZ_E_ARG;
+  if (slot < 0 || slot > 1) return fail(H, STZ_E_ARG, "slot must be 0 or 1");
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  return host_wait_slot(H, slot);
+}
+
+extern "C" int stz_synthesize_host(stz_handle* H, const float* text_emb, const uint8_t* text_mask,
+                                   const float* prompt_feats, const uint8_t* prompt_mask, const float* noise, int B, int T,
+                                   int P, int steps, float cfg_scale, int sampler_kind, float* out_style, int32_t* out_dur) {
+  if (!H) return STZ_E_ARG;
+  RET(stz_synthesize_host_submit(H, 0, text_emb, text_mask, prompt_feats, prompt_mask, noise, B, T, P, steps, cfg_scale,
+                                 sampler_kind, out_style, out_dur));
+  return stz_synthesize_host_wait(H, 0);
 }
 
 // ------------------------------------------------------------------------------------------

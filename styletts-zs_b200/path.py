@@ -70,6 +70,14 @@ def load_library(path: Optional[str] = None):
     lib.stz_regulate_length.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.stz_synthesize_host.restype = i32
     lib.stz_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
+    lib.stz_synthesize_host_submit.restype = i32
+    lib.stz_synthesize_host_submit.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
+    lib.stz_synthesize_host_wait.restype = i32
+    lib.stz_synthesize_host_wait.argtypes = [vp, i32]
+    lib.stz_set_noise_seed.restype = i32
+    lib.stz_set_noise_seed.argtypes = [vp, C.c_uint64, C.c_uint64]
+    lib.stz_philox_normal.restype = i32
+    lib.stz_philox_normal.argtypes = [C.c_uint64, C.c_uint64, i32, i32, i32, vp, i32, vp]
     lib.stz_launch_count.restype = i64
     lib.stz_launch_count.argtypes = [vp]
     lib.stz_set_option.restype = i32
@@ -101,7 +109,7 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
-                    "stz_synthesize_host", "stz_regulate_length", "stz_launch_count", "stz_set_option", "stz_profile_read",
+                    "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_philox_normal", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16", "stz_op_attention")
 
@@ -143,6 +151,7 @@ class StyleTTSZSPath:
         if rc != 0:
             raise StzError(f"stz_create failed ({rc}): {self.lib.stz_last_error(None).decode()}")
         self._h = h
+        self._inflight = {}
 
     def close(self):
         if getattr(self, "_h", None):
@@ -213,20 +222,25 @@ class StyleTTSZSPath:
 
     # ---------------------------------------------------------------------------------
     def sample_style(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
-                     prompt_mask=None, noise=None, sampler="student") -> torch.Tensor:
+                     prompt_mask=None, noise=None, sampler="student", seed: Optional[int] = None,
+                     first_utterance: int = 0) -> torch.Tensor:
         """-> style codes [B,K,Ds] fp32 on this path's device.  ``noise`` [n_slices,B,K,Ds] is an
-        input ("identical seeds" == identical noise tensors)."""
+        input ("identical seeds" == identical noise tensors); or pass ``seed``
+        (and the global index of the batch's first utterance) to draw it on the device — the same
+        tensor as ``philox_normal(seed, first_utterance, n_slices, B)``."""
         cfg, kind = self.cfg, _kind(sampler)
         B, T, _ = text_emb.shape
         P = prompt_feats.shape[1]
-        if noise is None:
-            raise ValueError("noise tensor is required")
+        if (noise is None) == (seed is None):
+            raise ValueError("pass exactly one of noise= (tensor) or seed= (on-device Philox noise)")
         ns = n_noise_slices(steps, kind)
-        if tuple(noise.shape) != (ns, B, cfg.n_style, cfg.d_style):
+        if noise is not None and tuple(noise.shape) != (ns, B, cfg.n_style, cfg.d_style):
             raise ValueError(f"noise must be {(ns, B, cfg.n_style, cfg.d_style)}, got {tuple(noise.shape)}")
+        if seed is not None:
+            self.seed_noise(seed, first_utterance)
         with torch.cuda.device(self.device):
-            te, pf, nz = self._dev(text_emb, torch.float32), self._dev(prompt_feats, torch.float32), \
-                self._dev(noise, torch.float32)
+            te, pf = self._dev(text_emb, torch.float32), self._dev(prompt_feats, torch.float32)
+            nz = None if noise is None else self._dev(noise, torch.float32)
             tm, pm = self._mask(text_mask), self._mask(prompt_mask)
             out = torch.empty(B, cfg.n_style, cfg.d_style, dtype=torch.float32, device=self.device)
             st = torch.cuda.current_stream().cuda_stream
@@ -238,6 +252,17 @@ class StyleTTSZSPath:
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream())
         return out
+
+    def seed_noise(self, seed: int, first_utterance: int = 0):
+        """Calls that pass no noise tensor draw it on the device from (seed, first_utterance + b)."""
+        self._check(self.lib.stz_set_noise_seed(self._h, int(seed) & (2 ** 64 - 1), int(first_utterance)),
+                    "stz_set_noise_seed")
+
+    def philox_normal(self, seed: int, first_utterance: int, slices: int, B: int) -> torch.Tensor:
+        """The on-device generator's output [slices, B, K, Ds] fp32 (bit-identical to the oracle's)."""
+        cfg = self.cfg
+        out = torch.empty(slices, B, cfg.n_style, cfg.d_style, dtype=torch.float32, device=self.device)
+        return philox_normal(seed, first_utterance, slices, B, cfg.n_style * cfg.d_style, out=out)
 
     def predict_duration(self, text_emb, style_codes, *, text_mask=None, return_presum=False):
         """-> int32 frames per token [B,T] (0 on padding)."""
@@ -276,13 +301,22 @@ class StyleTTSZSPath:
 
     def synthesize_host(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
                         prompt_mask=None, noise=None, sampler="student", out_style=None, out_dur=None,
-                        with_duration=True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+                        with_duration=True, seed: Optional[int] = None, first_utterance: int = 0,
+                        slot: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """End-to-end call with HOST tensors (pinned recommended): H2D + sample_style
-        [+ predict_duration] + D2H + sync inside one C-ABI call.  This is what bench.py's `e2e` times."""
+        [+ predict_duration] + D2H + sync inside one C-ABI call.
+        With ``seed`` instead of ``noise`` the noise is drawn on the device (no noise H2D).
+        With ``slot`` (0 or 1) the call only SUBMITS the batch (stz_synthesize_host_submit) and returns the output
+        tensors immediately; they are valid after ``synthesize_host_wait(slot)``.  Alternating the two slots overlaps
+        batch i+1's input copies with batch i's compute — this is what bench.py's `e2e` times."""
         cfg, kind = self.cfg, _kind(sampler)
         B, T, _ = text_emb.shape
         P = prompt_feats.shape[1]
-        for t in (text_emb, prompt_feats, noise):
+        if (noise is None) == (seed is None):
+            raise ValueError("pass exactly one of noise= (tensor) or seed= (on-device Philox noise)")
+        if seed is not None:
+            self.seed_noise(seed, first_utterance)
+        for t in (text_emb, prompt_feats) + (() if noise is None else (noise,)):
             if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("synthesize_host takes contiguous fp32 CPU tensors")
         tm = None if text_mask is None else text_mask.to(torch.uint8).contiguous()
@@ -291,11 +325,24 @@ class StyleTTSZSPath:
             out_style = torch.empty(B, cfg.n_style, cfg.d_style, dtype=torch.float32)
         if with_duration and out_dur is None:
             out_dur = torch.empty(B, T, dtype=torch.int32)
-        rc = self.lib.stz_synthesize_host(self._h, _ptr(text_emb), _ptr(tm), _ptr(prompt_feats), _ptr(pm),
-                                          _ptr(noise), B, T, P, int(steps), float(cfg_scale), kind,
-                                          _ptr(out_style), _ptr(out_dur) if with_duration else None)
-        self._check(rc, "stz_synthesize_host")
+        if slot is None:
+            rc = self.lib.stz_synthesize_host(self._h, _ptr(text_emb), _ptr(tm), _ptr(prompt_feats), _ptr(pm),
+                                              _ptr(noise), B, T, P, int(steps), float(cfg_scale), kind,
+                                              _ptr(out_style), _ptr(out_dur) if with_duration else None)
+            self._check(rc, "stz_synthesize_host")
+        else:
+            rc = self.lib.stz_synthesize_host_submit(self._h, int(slot), _ptr(text_emb), _ptr(tm), _ptr(prompt_feats),
+                                                     _ptr(pm), _ptr(noise), B, T, P, int(steps), float(cfg_scale), kind,
+                                                     _ptr(out_style), _ptr(out_dur) if with_duration else None)
+            self._check(rc, "stz_synthesize_host_submit")
+            # host buffers belong to the library until the slot's wait: keep them (and converted masks) alive
+            self._inflight[int(slot)] = (text_emb, tm, prompt_feats, pm, noise, out_style, out_dur)
         return out_style, (out_dur if with_duration else None)
+
+    def synthesize_host_wait(self, slot: int):
+        """Blocks until the batch submitted into ``slot`` has its outputs in the host tensors."""
+        self._check(self.lib.stz_synthesize_host_wait(self._h, int(slot)), "stz_synthesize_host_wait")
+        self._inflight.pop(int(slot), None)
 
 
 def op_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], impl: int = 0) -> torch.Tensor:
@@ -309,4 +356,18 @@ def op_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
                               C.c_void_p(st))
     if rc != 0:
         raise StzError(f"stz_op_gemm_bf16 failed ({rc}): {lib.stz_last_error(None).decode()}")
+    return out
+
+
+def philox_normal(seed: int, first_utterance: int, slices: int, B: int, n_per_utt: int,
+                  out: Optional[torch.Tensor] = None, device: int = 0) -> torch.Tensor:
+    """Counter-based N(0,1) noise on the device: fp32 [slices, B, n_per_utt] (include/stz.h: stz_philox_normal)."""
+    lib = load_library()
+    if out is None:
+        out = torch.empty(slices, B, n_per_utt, dtype=torch.float32, device=torch.device("cuda", device))
+    st = torch.cuda.current_stream(out.device).cuda_stream
+    rc = lib.stz_philox_normal(int(seed) & (2 ** 64 - 1), int(first_utterance), slices, B, n_per_utt, _ptr(out),
+                               out.device.index or 0, C.c_void_p(st))
+    if rc != 0:
+        raise StzError(f"stz_philox_normal failed ({rc}): {lib.stz_last_error(None).decode()}")
     return out

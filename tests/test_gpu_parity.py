@@ -272,6 +272,79 @@ def test_length_regulator_full_size_properties(path):
 
 
 # ---------------------------------------------------------------------------------------------
+# on-device counter-based noise: bit-exact against oracle/philox.py
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,first,slices,B,n", [(0, 0, 1, 1, 4), (1234, 0, 1, 64, 25600), (2 ** 63 + 11, 5, 3, 7, 2052),
+                                                   (99, (1 << 32) + 3, 2, 3, 25600), (5, 0, 33, 2, 25600)])
+def test_philox_noise_bit_exact(seed, first, slices, B, n):
+    import numpy as np
+    from oracle import philox as PH
+    got = stz.philox_normal(seed, first, slices, B, n).cpu().numpy()
+    want = PH.normal_noise(seed, first, slices, B, n)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_philox_noise_full_size_properties(path):
+    """cfg3-sized draw (33 slices x 32 utterances): moments, and shard invariance without the oracle."""
+    z = path.philox_normal(1234, 0, 33, 32)
+    assert z.shape == (33, 32, CFG.n_style, CFG.d_style)
+    assert abs(float(z.mean())) < 1e-3 and abs(float(z.std()) - 1.0) < 1e-3 and bool(torch.isfinite(z).all())
+    assert float(z.abs().max()) < 5.8                                   # Box-Muller radius bound for 23-bit uniforms
+    assert torch.equal(z[:, 8:24], path.philox_normal(1234, 8, 33, 16))
+
+
+@pytest.mark.parametrize("sampler,steps", [("student", 4), ("teacher", 3)])
+def test_seeded_sample_style_equals_explicit_noise(path, oracle, sampler, steps):
+    """seed= draws inside the call exactly the tensor philox_normal returns; the oracle, given the same seed, agrees."""
+    B, T = 3, 24
+    inp = stz.synthetic_inputs(CFG, B, T, steps=steps, seed=77)
+    ns = steps + 1 if sampler == "teacher" else 1
+    nz = path.philox_normal(4242, 10, ns, B)
+    a = path.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 2.0, noise=nz, sampler=sampler)
+    b = path.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 2.0, seed=4242, first_utterance=10, sampler=sampler)
+    assert torch.equal(a, b)
+    ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 2.0, seed=4242, first_utterance=10, sampler=sampler)
+    assert rel(b.cpu(), ref) < 2e-2
+    # shard invariance through the whole sampler: utterances [1, 3) on their own
+    c = path.sample_style(inp["text_emb"][1:], inp["prompt_feats"][1:], steps, 2.0, seed=4242, first_utterance=11, sampler=sampler)
+    assert rel(c, b[1:]) < 5e-3
+
+
+def test_pipelined_host_slots_match_blocking_call(path):
+    """submit(0), submit(1), wait(0), wait(1) with different batches (different shapes even) == two blocking calls."""
+    a = stz.synthetic_inputs(CFG, 4, 32, steps=4, seed=21)
+    b = stz.synthetic_inputs(CFG, 3, 48, steps=4, seed=22, var_len=(8, 48))
+    ref_a = path.synthesize_host(a["text_emb"], a["prompt_feats"], 4, 2.0, noise=a["noise"])
+    ref_b = path.synthesize_host(b["text_emb"], b["prompt_feats"], 4, 2.0, noise=b["noise"], text_mask=b["text_mask"])
+    ref_a = (ref_a[0].clone(), ref_a[1].clone())
+    ref_b = (ref_b[0].clone(), ref_b[1].clone())
+    pin = lambda d: {k: (v.pin_memory() if torch.is_tensor(v) and v.dtype == torch.float32 else v) for k, v in d.items()}
+    a, b = pin(a), pin(b)
+    for _ in range(3):                                  # slots are reusable; resubmitting waits for the slot
+        oa = path.synthesize_host(a["text_emb"], a["prompt_feats"], 4, 2.0, noise=a["noise"], slot=0)
+        ob = path.synthesize_host(b["text_emb"], b["prompt_feats"], 4, 2.0, noise=b["noise"], text_mask=b["text_mask"], slot=1)
+        path.synthesize_host_wait(0)
+        path.synthesize_host_wait(1)
+        assert torch.equal(oa[0], ref_a[0]) and torch.equal(oa[1], ref_a[1])
+        assert torch.equal(ob[0], ref_b[0]) and torch.equal(ob[1], ref_b[1])
+    path.synthesize_host_wait(0)                        # waiting on an idle slot is a no-op
+    with pytest.raises(stz.StzError):
+        path.synthesize_host(a["text_emb"], a["prompt_feats"], 4, 2.0, noise=a["noise"], slot=2)
+
+
+def test_synthesize_host_with_seed_matches_device_path(path):
+    B, T = 4, 32
+    inp = stz.synthetic_inputs(CFG, B, T, steps=4, seed=9)
+    style_h, dur_h = path.synthesize_host(inp["text_emb"], inp["prompt_feats"], 4, 2.0, seed=31337)
+    style_d = path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, seed=31337)
+    assert torch.equal(style_h, style_d.cpu())
+    assert torch.equal(dur_h, path.predict_duration(inp["text_emb"], style_d).cpu())
+    with pytest.raises(ValueError):
+        path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0)
+
+
+# ---------------------------------------------------------------------------------------------
 # full-size properties (BASELINE configs[1] = cfg2 and configs[3] = cfg4 shapes)
 # ---------------------------------------------------------------------------------------------
 def test_cfg2_full_size_properties(path):

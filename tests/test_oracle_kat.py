@@ -234,3 +234,50 @@ def test_length_regulator_known_answer(tiny_weights):
     assert ln.tolist() == [5, 2]                                  # 6 frames truncated to 5
     assert tk.tolist() == [[0, 0, 2, 3, 3], [0, 1, -1, -1, -1]]
     assert torch.equal(fr[0, 2], f[0, 2]) and torch.equal(fr[1, 2:], torch.zeros(3, 4))
+
+
+# ---------------------------------------------------------------------------------------------
+# counter-based noise: oracle/philox.py
+# ---------------------------------------------------------------------------------------------
+def test_philox4x32_10_random123_known_answers():
+    """Random123's published kat_vectors for philox4x32, 10 rounds."""
+    import numpy as np
+    from oracle import philox as PH
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = PH.philox4x32_10([np.array([c], dtype=np.uint32) for c in ctr], [np.uint32(k) for k in key])
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_philox_normal_is_standard_normal_and_accurate():
+    import numpy as np
+    from scipy import stats
+    from oracle import philox as PH
+    z = PH.normal_noise(1234, 0, 2, 8, 50 * 512).astype(np.float64).ravel()
+    assert z.dtype == np.float64 and np.isfinite(z).all()
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3
+    assert abs(stats.skew(z)) < 0.02 and abs(stats.kurtosis(z)) < 0.03
+    assert stats.kstest(z[:200000], "norm").pvalue > 1e-3
+    # the fp32 polynomial log / sincos against libm in fp64
+    u = np.random.default_rng(0).random(100000).astype(np.float32)
+    u = u[u > 0]
+    assert np.abs(PH._log_u(u) - np.log(u.astype(np.float64))).max() < 2e-6
+    k = np.random.default_rng(1).integers(0, 1 << 23, 100000).astype(np.uint32)
+    s, c = PH._sincos_turn(k)
+    th = 2 * np.pi * (k.astype(np.float64) + 0.5) / 2 ** 23
+    assert np.abs(s - np.sin(th)).max() < 3e-7 and np.abs(c - np.cos(th)).max() < 3e-7
+
+
+def test_philox_noise_is_a_function_of_the_global_utterance_only():
+    """Batch / shard invariance: utterance u gets the same noise whichever batch it is drawn in."""
+    import numpy as np
+    from oracle import philox as PH
+    a = PH.normal_noise(7, 0, 3, 6, 2048)
+    assert np.array_equal(a[:, 2:5], PH.normal_noise(7, 2, 3, 3, 2048))
+    assert np.array_equal(a[1:2], PH.normal_noise(7, 0, 2, 6, 2048)[1:2])
+    assert not np.array_equal(a, PH.normal_noise(8, 0, 3, 6, 2048))
+    big = PH.normal_noise(7, (1 << 32) + 5, 1, 1, 2048)          # the high utterance word is part of the counter
+    assert not np.array_equal(big, PH.normal_noise(7, 5, 1, 1, 2048))
