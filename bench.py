@@ -281,8 +281,28 @@ def main_native(args, rank, world, local_rank):
     h2d = sum(host[k].numel() * 4 for k in host)
     d2h = out_style.numel() * 4 + out_dur.numel() * 4
 
-    roofline, cpu = None, None
+    roofline, cpu, predictor = None, None, None
     if rank == 0 and not args.ncu:
+        # ---- the duration predictor on its own (report achieved GB/s AND fp32 FLOP/s, say which binds) ----
+        pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in pe:
+            flush.zero_()
+            a.record()
+            path.predict_duration(dev["text_emb"], z)
+            b.record()
+        torch.cuda.synchronize()
+        pred_ms = sum(a.elapsed_time(b) for a, b in pe) / len(pe)
+        h, dh, ds, nl = cfg.h_lstm, cfg.d_hid, cfg.d_sty_tok, cfg.n_lstm
+        fl_tok = nl * 2 * (2 * 4 * h * (dh + ds) + 2 * 4 * h * h) + (nl - 1) * 2 * ds * 2 * dh \
+            + 2 * cfg.d_text * ds + 4 * cfg.n_style * ds + 2 * ds * ds + 2 * dh * cfg.max_dur
+        by_tok = 100e3   # <~100 KB of fp32 activations per token (each [rows, C] activation read + written once per pass)
+        ntok = B * T
+        predictor = {"ms": pred_ms, "tokens": ntok, "fp32_flops_per_token": fl_tok, "bytes_per_token": by_tok,
+                     "achieved_tflops_fp32_equiv": ntok * fl_tok / (pred_ms * 1e-3) / 1e12,
+                     "achieved_gbs": ntok * by_tok / (pred_ms * 1e-3) / 1e9,
+                     "binds": "neither HBM nor FMA throughput: the BiLSTM's serial chain (T steps x n_lstm layers x ~1.7 us per "
+                              "recurrent step: tcgen05 issue floor + gate math + DSMEM exchange of h_t across the 8-CTA cluster)",
+                     "chain_us": T * nl * 1.7}
         # ---- roofline of the dominant kernel (tcgen05 GEMM family), timed in situ -------------
         path.set_option("profile", 1)
         for _ in range(2):
@@ -357,7 +377,7 @@ def main_native(args, rank, world, local_rank):
                                  "ms_per_step": e2e_seed_ms / args.steps,
                                  "note": "the blocking e2e call with seed= instead of a host noise tensor: noise drawn on the device "
                                          "(Philox4x32-10, bit-identical to oracle/philox.py); informational, `e2e` is the headline"},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "predictor": predictor,
             "path_rtf": (dev_ms * 1e-3 / args.steps) / (frames / FRAMES_PER_S) if frames else None}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -106,6 +106,11 @@ int stz_regulate_length(stz_handle* h, const float* feats_dev, const int32_t* du
  * NULL noise argument is STZ_E_ARG. */
 int stz_set_noise_seed(stz_handle* h, uint64_t seed, uint64_t first_utterance);
 
+/* The same with explicit global utterance indices (host array, copied): utterance b of the next calls is global utterance
+ * utterance_ids[b] — for sharded batches that are not a contiguous range (shard.py's length-sorted round-robin).  The
+ * calls that follow must have B == n.  stz_set_noise_seed returns to the contiguous numbering. */
+int stz_set_noise_utterances(stz_handle* h, uint64_t seed, const uint64_t* utterance_ids, int n);
+
 /* The generator on its own (unit tests, callers that want the tensor): out_dev [slices, B, n_per_utt] fp32,
  * n_per_utt % 4 == 0. */
 int stz_philox_normal(uint64_t seed, uint64_t first_utterance, int slices, int B, int n_per_utt, float* out_dev,

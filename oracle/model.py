@@ -179,7 +179,7 @@ class OraclePath:
     @torch.no_grad()
     def sample_style(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
                      prompt_mask=None, noise=None, sampler="student", seed: Optional[int] = None,
-                     first_utterance: int = 0) -> torch.Tensor:
+                     first_utterance=0) -> torch.Tensor:
         cfg = self.cfg
         B, T, _ = text_emb.shape
         P = prompt_feats.shape[1]

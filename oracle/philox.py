@@ -103,13 +103,20 @@ def box_muller(xa, xb):
     return r * c, r * s
 
 
-def normal_noise(seed: int, first_utterance: int, slices: int, B: int, n_per_utt: int) -> np.ndarray:
-    """-> fp32 [slices, B, n_per_utt]; n_per_utt % 4 == 0."""
+def normal_noise(seed: int, first_utterance, slices: int, B: int, n_per_utt: int) -> np.ndarray:
+    """-> fp32 [slices, B, n_per_utt]; n_per_utt % 4 == 0.  `first_utterance`: int (utterance b is global utterance
+    first_utterance + b) or a sequence of B explicit global indices."""
     if n_per_utt % 4:
         raise ValueError("n_per_utt must be a multiple of 4")
     G = n_per_utt // 4
     g = np.arange(G, dtype=np.uint64)[None, None, :]
-    utt = (np.arange(B, dtype=np.uint64) + np.uint64(first_utterance))[None, :, None]
+    if isinstance(first_utterance, (int, np.integer)):
+        utt = np.arange(B, dtype=np.uint64) + np.uint64(first_utterance)
+    else:
+        utt = np.asarray([int(i) for i in first_utterance], dtype=np.uint64)
+        if utt.shape != (B,):
+            raise ValueError("need one global index per utterance")
+    utt = utt[None, :, None]
     sl = np.arange(slices, dtype=np.uint64)[:, None, None]
     shape = (slices, B, G)
     ctr = [np.broadcast_to(g, shape), np.broadcast_to(utt & _MASK, shape), np.broadcast_to(sl, shape),

@@ -81,16 +81,19 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, 
 
 }  // namespace philox
 
-// out [slices, B, n_per_utt] fp32, n_per_utt % 4 == 0; one thread per group of four elements
+// out [slices, B, n_per_utt] fp32, n_per_utt % 4 == 0; one thread per group of four elements; utterance b's global index is
+// utt_ids[b] when given (sharded batches: any subset, any order), else first_utt + b
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, uint32_t seed_lo, uint32_t seed_hi,
-                                                            unsigned long long first_utt, int slices, int B, int groups) {
+                                                            unsigned long long first_utt,
+                                                            const unsigned long long* __restrict__ utt_ids, int slices,
+                                                            int B, int groups) {
   stz::pdl_sync();   // `out` may still be read by the previous call's kernels
   const size_t total = static_cast<size_t>(slices) * B * groups;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const uint32_t g = static_cast<uint32_t>(i % groups);
     const size_t sb = i / groups;
-    const unsigned long long utt = first_utt + sb % B;
+    const unsigned long long utt = utt_ids ? utt_ids[sb % B] : first_utt + sb % B;
     uint32_t c[4] = {g, static_cast<uint32_t>(utt), static_cast<uint32_t>(sb / B), static_cast<uint32_t>(utt >> 32)};
     philox::philox4x32_10(c, seed_lo, seed_hi);
     float4 z;

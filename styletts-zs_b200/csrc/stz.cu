@@ -113,6 +113,9 @@ struct stz_handle {
   // noise == NULL: draw it on the device (philox.cuh) from this seed; utterance b of a call is global utterance noise_first_utt + b
   bool noise_seeded = false;
   uint64_t noise_seed = 0, noise_first_utt = 0;
+  std::vector<unsigned long long> noise_ids;    // explicit global utterance indices (empty: first_utt + b)
+  unsigned long long* noise_ids_dev = nullptr;
+  size_t noise_ids_cap = 0;
   // calls share one workspace: a call enqueued on a different stream than the previous one first waits for it
   cudaStream_t last_stream = nullptr;
   cudaEvent_t last_ev = nullptr;
@@ -731,6 +734,7 @@ extern "C" void stz_destroy(stz_handle* H) {
     if (H->chain_stream[i]) cudaStreamDestroy(H->chain_stream[i]);
   }
   if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
+  cudaFree(H->noise_ids_dev);
   cudaFree(H->kv_null); cudaFree(H->w_in3); cudaFree(H->w_out3); cudaFree(H->whhT); cudaFree(H->whh); cudaFree(H->lstm_b);
   if (H->last_ev) cudaEventDestroy(H->last_ev);
   if (H->stream) cudaStreamDestroy(H->stream);
@@ -1281,8 +1285,21 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   if (H->wait_noise) { CK(H, cudaStreamWaitEvent(st, H->cur_ev_noise, 0)); H->wait_noise = false; }
   // ---- sampler state --------------------------------------------------------------------
   if (!noise) {   // every slice drawn on the device, bit-identical to oracle/philox.py
+    const unsigned long long* ids = nullptr;
+    if (!H->noise_ids.empty()) {
+      if ((int)H->noise_ids.size() != B) return fail(H, STZ_E_ARG, "stz_set_noise_utterances gave %zu indices, the batch has %d utterances", H->noise_ids.size(), B);
+      if (H->noise_ids_cap < (size_t)B) {
+        CK(H, cudaStreamSynchronize(st));
+        if (H->noise_ids_dev) CK(H, cudaFree(H->noise_ids_dev));
+        H->noise_ids_dev = nullptr; H->noise_ids_cap = 0;
+        CK(H, cudaMalloc(&H->noise_ids_dev, (size_t)B * sizeof(unsigned long long)));
+        H->noise_ids_cap = B;
+      }
+      CK(H, cudaMemcpyAsync(H->noise_ids_dev, H->noise_ids.data(), (size_t)B * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+      ids = H->noise_ids_dev;
+    }
     launch_k(philox_normal_kernel, ew_grid((size_t)slices * BK * Ds / 4), 256, 0, st, w.noise, (uint32_t)H->noise_seed,
-             (uint32_t)(H->noise_seed >> 32), (unsigned long long)H->noise_first_utt, slices, B, K * Ds / 4); KCHECK(H);
+             (uint32_t)(H->noise_seed >> 32), (unsigned long long)H->noise_first_utt, ids, slices, B, K * Ds / 4); KCHECK(H);
     noise = w.noise;
   } else if (kind == STZ_SAMPLER_TEACHER) {
     CK(H, cudaMemcpyAsync(w.noise, noise, (size_t)slices * BK * Ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1535,6 +1552,17 @@ extern "C" int stz_set_noise_seed(stz_handle* H, uint64_t seed, uint64_t first_u
   H->noise_seeded = true;
   H->noise_seed = seed;
   H->noise_first_utt = first_utterance;
+  H->noise_ids.clear();
+  return 0;
+}
+
+extern "C" int stz_set_noise_utterances(stz_handle* H, uint64_t seed, const uint64_t* utterance_ids, int n) {
+  if (!H) return STZ_E_ARG;
+  if (!utterance_ids || n < 1) return fail(H, STZ_E_ARG, "utterance_ids must hold n >= 1 indices");
+  H->noise_seeded = true;
+  H->noise_seed = seed;
+  H->noise_first_utt = 0;
+  H->noise_ids.assign(utterance_ids, utterance_ids + n);
   return 0;
 }
 
@@ -1546,7 +1574,7 @@ extern "C" int stz_philox_normal(uint64_t seed, uint64_t first_utterance, int sl
   const size_t groups = (size_t)slices * B * (n_per_utt / 4);
   const size_t blocks = (groups + 255) / 256;
   philox_normal_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)cuda_stream>>>(
-      out_dev, (uint32_t)seed, (uint32_t)(seed >> 32), (unsigned long long)first_utterance, slices, B, n_per_utt / 4);
+      out_dev, (uint32_t)seed, (uint32_t)(seed >> 32), (unsigned long long)first_utterance, nullptr, slices, B, n_per_utt / 4);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, STZ_E_CUDA, "philox_normal_kernel -> %s", cudaGetErrorString(e));
   return 0;

@@ -76,6 +76,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_synthesize_host_wait.argtypes = [vp, i32]
     lib.stz_set_noise_seed.restype = i32
     lib.stz_set_noise_seed.argtypes = [vp, C.c_uint64, C.c_uint64]
+    lib.stz_set_noise_utterances.restype = i32
+    lib.stz_set_noise_utterances.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64), i32]
     lib.stz_philox_normal.restype = i32
     lib.stz_philox_normal.argtypes = [C.c_uint64, C.c_uint64, i32, i32, i32, vp, i32, vp]
     lib.stz_launch_count.restype = i64
@@ -109,7 +111,7 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
-                    "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_philox_normal", "stz_launch_count", "stz_set_option", "stz_profile_read",
+                    "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_set_noise_utterances", "stz_philox_normal", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16", "stz_op_attention")
 
@@ -223,7 +225,7 @@ class StyleTTSZSPath:
     # ---------------------------------------------------------------------------------
     def sample_style(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
                      prompt_mask=None, noise=None, sampler="student", seed: Optional[int] = None,
-                     first_utterance: int = 0) -> torch.Tensor:
+                     first_utterance=0) -> torch.Tensor:
         """-> style codes [B,K,Ds] fp32 on this path's device.  ``noise`` [n_slices,B,K,Ds] is an
         input ("identical seeds" == identical noise tensors); or pass ``seed``
         (and the global index of the batch's first utterance) to draw it on the device — the same
@@ -253,10 +255,17 @@ class StyleTTSZSPath:
                     t.record_stream(torch.cuda.current_stream())
         return out
 
-    def seed_noise(self, seed: int, first_utterance: int = 0):
-        """Calls that pass no noise tensor draw it on the device from (seed, first_utterance + b)."""
-        self._check(self.lib.stz_set_noise_seed(self._h, int(seed) & (2 ** 64 - 1), int(first_utterance)),
-                    "stz_set_noise_seed")
+    def seed_noise(self, seed: int, first_utterance=0):
+        """Calls that pass no noise tensor draw it on the device from (seed, global utterance index).
+        ``first_utterance``: an int (utterance b is first_utterance + b) or a sequence of B explicit indices."""
+        if isinstance(first_utterance, int):
+            self._check(self.lib.stz_set_noise_seed(self._h, int(seed) & (2 ** 64 - 1), int(first_utterance)),
+                        "stz_set_noise_seed")
+        else:
+            ids = [int(i) for i in first_utterance]
+            arr = (C.c_uint64 * len(ids))(*ids)
+            self._check(self.lib.stz_set_noise_utterances(self._h, int(seed) & (2 ** 64 - 1), arr, len(ids)),
+                        "stz_set_noise_utterances")
 
     def philox_normal(self, seed: int, first_utterance: int, slices: int, B: int) -> torch.Tensor:
         """The on-device generator's output [slices, B, K, Ds] fp32 (bit-identical to the oracle's)."""
@@ -301,7 +310,7 @@ class StyleTTSZSPath:
 
     def synthesize_host(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
                         prompt_mask=None, noise=None, sampler="student", out_style=None, out_dur=None,
-                        with_duration=True, seed: Optional[int] = None, first_utterance: int = 0,
+                        with_duration=True, seed: Optional[int] = None, first_utterance=0,
                         slot: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """End-to-end call with HOST tensors (pinned recommended): H2D + sample_style
         [+ predict_duration] + D2H + sync inside one C-ABI call.

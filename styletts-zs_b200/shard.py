@@ -30,7 +30,9 @@ def take_shard(inputs: Dict[str, torch.Tensor], idx: List[int]) -> Dict[str, tor
     mask = inputs["text_mask"][ii]
     t_max = max(int(mask.sum(1).max()), 1) if len(idx) else 1
     out = {"text_emb": inputs["text_emb"][ii][:, :t_max].contiguous(), "text_mask": mask[:, :t_max].contiguous(),
-           "prompt_feats": inputs["prompt_feats"][ii].contiguous(), "noise": inputs["noise"][:, ii].contiguous()}
+           "prompt_feats": inputs["prompt_feats"][ii].contiguous()}
+    if inputs.get("noise") is not None:
+        out["noise"] = inputs["noise"][:, ii].contiguous()
     if inputs.get("prompt_mask") is not None:
         out["prompt_mask"] = inputs["prompt_mask"][ii].contiguous()
     return out
@@ -40,7 +42,12 @@ def synthesize_sharded(compute: Callable[..., Tuple[torch.Tensor, torch.Tensor]]
                        rank: int, world_size: int, group=None) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
     """Runs `compute(text_emb, text_mask, prompt_feats, prompt_mask, noise) -> (style [n,K,Ds], dur [n,t])`
     on this rank's shard and gathers on the host.  Rank 0 returns (style [B,K,Ds], dur [B,T]) in the
-    original utterance order (durations zero-padded back to T); other ranks return None."""
+    original utterance order (durations zero-padded back to T); other ranks return None.
+
+    Noise: either `inputs["noise"]` ([slices,B,K,Ds], sliced per shard) or `inputs["seed"]` (int) — then
+    `compute(..., None, seed=seed, first_utterance=idx)` is called with the shard's GLOBAL utterance indices and
+    draws the counter-based noise itself (include/stz.h: stz_set_noise_utterances), so every utterance gets the
+    noise it would get in the unsharded batch without any noise tensor crossing the host."""
     B, T = inputs["text_mask"].shape
     lengths = inputs["text_mask"].sum(1).tolist()
     shards = shard_utterances(lengths, world_size)
@@ -48,7 +55,11 @@ def synthesize_sharded(compute: Callable[..., Tuple[torch.Tensor, torch.Tensor]]
     local = None
     if idx:
         sh = take_shard(inputs, idx)
-        style, dur = compute(sh["text_emb"], sh["text_mask"], sh["prompt_feats"], sh.get("prompt_mask"), sh["noise"])
+        if inputs.get("noise") is not None:
+            style, dur = compute(sh["text_emb"], sh["text_mask"], sh["prompt_feats"], sh.get("prompt_mask"), sh["noise"])
+        else:
+            style, dur = compute(sh["text_emb"], sh["text_mask"], sh["prompt_feats"], sh.get("prompt_mask"), None,
+                                 seed=int(inputs["seed"]), first_utterance=list(idx))
         local = (style.cpu(), dur.cpu())
     if world_size == 1:
         gathered = [local]

@@ -447,6 +447,30 @@ def test_sharded_path_matches_unsharded(path):
         assert int(dd.max()) <= 1 and float((dd == 0).float().mean()) > 0.9
 
 
+def test_seeded_shards_draw_the_unsharded_noise(path):
+    """Round-robin shards with explicit global utterance indices (stz_set_noise_utterances) draw, bit for bit, the noise
+    of the unsharded batch; the sampled codes agree to attention-partition noise."""
+    import numpy as np
+    from oracle import philox as PH
+    inp = stz.synthetic_inputs(CFG, 6, 40, steps=4, seed=23, var_len=(8, 40))
+    full = path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, text_mask=inp["text_mask"], seed=2024)
+    shards = stz.shard_utterances(inp["lens"].tolist(), 2)
+    for r in range(2):
+        sh = stz.take_shard({k: v for k, v in inp.items() if k != "noise"}, shards[r])
+        z = path.sample_style(sh["text_emb"], sh["prompt_feats"], 4, 2.0, text_mask=sh["text_mask"], seed=2024,
+                              first_utterance=shards[r])
+        assert rel(z, full[torch.tensor(shards[r])]) < 5e-3
+        # the same call with the oracle's noise for those global indices handed in explicitly: identical
+        nz = torch.from_numpy(PH.normal_noise(2024, shards[r], 1, len(shards[r]), CFG.n_style * CFG.d_style))
+        z2 = path.sample_style(sh["text_emb"], sh["prompt_feats"], 4, 2.0, text_mask=sh["text_mask"],
+                               noise=nz.reshape(1, len(shards[r]), CFG.n_style, CFG.d_style))
+        assert torch.equal(z, z2)
+    with pytest.raises(stz.StzError):                    # index count must match the batch
+        path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, seed=1, first_utterance=[0, 1])
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, text_mask=inp["text_mask"], seed=2024)
+    assert torch.equal(z, full)                          # an int first_utterance returns to contiguous numbering
+
+
 def test_errors_are_loud(path):
     inp = stz.synthetic_inputs(CFG, 2, 16, steps=1)
     with pytest.raises(ValueError):

@@ -70,3 +70,30 @@ def test_world_size_2_matches_single_process():
         assert p.exitcode == 0
     assert torch.allclose(style, ref_style, atol=2e-5)
     assert torch.equal(dur, ref_dur)
+
+
+def test_seeded_shards_draw_the_unsharded_noise():
+    """inputs["seed"] instead of a noise tensor: each shard draws its utterances' counter-based noise from their GLOBAL
+    indices, so the gathered result equals the unsharded seeded run (no noise tensor is sliced or moved)."""
+    from oracle.model import OraclePath
+    cfg = stz.TINY
+    o = OraclePath(cfg, stz.init_weights(cfg, 0))
+
+    def compute(text, mask, prompt, pmask, noise, seed=None, first_utterance=0):
+        z = o.sample_style(text, prompt, 2, 2.0, text_mask=mask, prompt_mask=pmask, noise=noise, seed=seed,
+                           first_utterance=first_utterance)
+        return z, o.predict_duration(text, z, text_mask=mask)
+    inp = stz.synthetic_inputs(cfg, 5, 14, steps=2, seed=11, var_len=(3, 14))
+    inp = {k: v for k, v in inp.items() if k != "noise"}
+    inp["seed"] = 99
+    full = compute(inp["text_emb"], inp["text_mask"], inp["prompt_feats"], inp["prompt_mask"], None, seed=99)
+    shards = stz.shard_utterances(inp["text_mask"].sum(1).tolist(), 2)
+    style = torch.zeros_like(full[0])
+    for r in range(2):                                   # both ranks' local halves, no process group needed
+        sh = stz.take_shard(inp, shards[r])
+        z, _ = compute(sh["text_emb"], sh["text_mask"], sh["prompt_feats"], sh.get("prompt_mask"), None, seed=99,
+                       first_utterance=shards[r])
+        style[torch.tensor(shards[r])] = z
+    assert torch.allclose(style, full[0], atol=2e-5)
+    one = stz.synthesize_sharded(compute, inp, 0, 1)     # the sharder's own seed path (world 1)
+    assert torch.allclose(one[0], full[0], atol=2e-5) and torch.equal(one[1], full[1].to(torch.int32))
