@@ -1105,7 +1105,8 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)(d / c.n_heads));
   GemmParams base{};
   base.mod = mod; base.n_mod = n_mod; base.rows_per_utt = 2 * K; base.n_style = K;
-  // ablation bits: 1 self-attn, 2 cross-attn, 4 ln_mod, 8 qkv, 16 attention out-projections, 32 q2, 64 ff1, 128 ff2, 256 mod
+  // ablation bits: 1 self-attn, 2 cross-attn, 4 ln_mod, 8 qkv, 16 attention out-projections, 32 q2, 64 ff1, 128 ff2, 256 mod,
+  // 512 empty dependent nodes, 1024 cross-attention of every layer reads layer 0's K/V (L2-resident)
   const int ab = H->ablate;
 
   if (w.mod_hoisted) {   // all evaluations' modulations were computed by one GEMM before the loop (sample_style_impl)
@@ -1183,8 +1184,9 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (!(ab & 2)) {
       AttnParams ap{};
       const int ldkv = L * 2 * d;
-      const bf16* kt = w.kv_text + ((size_t)b0 * T * L + l) * 2 * d;
-      const bf16* kp = w.kv_prompt + ((size_t)b0 * P * L + l) * 2 * d;
+      const int lk = (ab & 1024) ? 0 : l;   // attribution: every layer reads layer 0's K/V (L2-resident) -> cost of the HBM misses
+      const bf16* kt = w.kv_text + ((size_t)b0 * T * L + lk) * 2 * d;
+      const bf16* kp = w.kv_prompt + ((size_t)b0 * P * L + lk) * 2 * d;
       ap.q = qkv; ap.ldq = d; ap.out = att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 3; ap.scale_log2 = scale_log2;
       ap.seg[0] = AttnSeg{kt, kt + d, ldkv, T, T, tmask, KEY_ALL};
       ap.seg[1] = AttnSeg{kp, kp + d, ldkv, P, P, pmask, KEY_COND};
