@@ -154,6 +154,22 @@ def test_odd_shapes_and_prompt_masks_vs_oracle(path, oracle, B, T, P, tlen):
     assert float((d[m] == d_ref[m]).float().mean()) >= TOL_DUR_AGREE and bool((d[~m] == 0).all())
 
 
+@pytest.mark.parametrize("B,T,P,tlen", [(1, 1, 1, None), (2, 3, 140, (1, 3)), (2, 777, 3, (500, 777)), (1, 1024, 50, (1024, 1024)),
+                                          (2, 130, 129, (7, 130))])
+def test_extreme_shapes_vs_oracle(path, oracle, B, T, P, tlen):
+    """Single-token text, single-frame and long (> 128) prompts, the longest text the length regulator accepts (1024), odd
+    long text: every attention dispatch branch (resident, streaming tcgen05, generic streaming) against the fp32 oracle."""
+    inp = stz.synthetic_inputs(CFG, B, T, P=P, steps=1, seed=77 + T + P, var_len=tlen)
+    tm = inp.get("text_mask")
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 1, 2.0, text_mask=tm, noise=inp["noise"])
+    z_ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], 1, 2.0, text_mask=tm, noise=inp["noise"])
+    assert rel(z, z_ref) < TOL_STYLE
+    d = path.predict_duration(inp["text_emb"], z_ref, text_mask=tm).cpu()
+    d_ref = oracle.predict_duration(inp["text_emb"], z_ref, text_mask=tm)
+    m = tm if tm is not None else torch.ones(B, T, dtype=torch.bool)
+    assert float((d[m] == d_ref[m]).float().mean()) >= TOL_DUR_AGREE and bool((d[~m] == 0).all())
+
+
 def test_cfg3_teacher_32_steps_vs_oracle(path, oracle):
     """BASELINE configs[2] schedule (32 ADPM2 steps = 64 chained denoiser evaluations, ancestral noise) at a batch the
     oracle finishes in seconds: error accumulation over the whole teacher trajectory stays inside the 1e-2 budget.
