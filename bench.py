@@ -366,7 +366,8 @@ def main_native(args, rank, world, local_rank):
             "data": "synthetic (seeded N(0,1) inputs, random-init weights)", "config": workload_config(world),
             "e2e": {"value": total_utt / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "pipeline_depth": 2 if e2e_pipe_ms > 0 else 1,
-                    "how": "stz_synthesize_host_submit / _wait on two slots with pinned HOST buffers: batch i+1 is submitted "
+                    "how": "one blocking stz_synthesize_host call per step" if e2e_pipe_ms <= 0 else
+                           "stz_synthesize_host_submit / _wait on two slots with pinned HOST buffers: batch i+1 is submitted "
                            "before batch i is waited for, so its H2D overlaps batch i's compute; every step's H2D, compute, "
                            "D2H and the per-step L2 flush are inside the timed region (wall clock, max over ranks)"},
             "e2e_sync": {"value": total_utt / (e2e_sync_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
