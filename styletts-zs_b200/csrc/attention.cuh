@@ -827,19 +827,17 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
   ATC2_TR();
-  pdl_sync();
-  ATC2_TR();
-
   const uint32_t tx_bytes = p.self ? 6u * 8192u : 2u * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
-  auto produce = [&](int unit, int buf) {
+  // parts: 1 = Q (written by the previous kernel), 2 = K / V.  The cross-attention K / V of a call are constants of the
+  // evaluation loop (computed once in the conditioning prep), so the first unit's K / V boxes are requested BEFORE
+  // griddepcontrol.wait and land while the previous kernel drains.
+  auto produce_tma = [&](int unit, int buf, int parts) {
     const int b = unit / p.n_heads, head = unit - b * p.n_heads;
-    if (tid == 0) {
-      const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
-      const uint32_t bar = smem_u32(&bar_full[buf]);
-      mbar_expect_tx(&bar_full[buf], tx_bytes);
-      const int t0 = b * n_tok, hc = head * ATT_DH;
-      tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
-      tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+    const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
+    const uint32_t bar = smem_u32(&bar_full[buf]);
+    const int t0 = b * n_tok, hc = head * ATT_DH;
+    if (parts & 2) {
+      mbar_expect_tx(&bar_full[buf], tx_bytes);          // the whole unit's bytes, armed with its first part
       if (p.self) {
         tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
         tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
@@ -855,6 +853,19 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
         tma_load_2d_u32(vs + o2, &tmN, bar, p.col_v + hc, 0);
       }
     }
+    if (parts & 1) {
+      tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
+      tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+    }
+  };
+  const bool kv_early = !p.self && static_cast<int>(blockIdx.x) < p.n_units;
+  if (kv_early && tid == 0) produce_tma(blockIdx.x, 0, 2);
+  pdl_sync();
+  ATC2_TR();
+
+  auto produce = [&](int unit, int buf, int parts) {
+    const int b = unit / p.n_heads;
+    if (tid == 0) produce_tma(unit, buf, parts);
     if (tid < 128) {   // visibility of key row `tid`: bit 0 = conditional queries, bit 1 = unconditional queries
       uint8_t vis = 0;
       if (p.self) {
@@ -875,10 +886,10 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
   int buf = 0;
   uint32_t phase = 0, fph0 = 0, fph1 = 0;
-  if (static_cast<int>(blockIdx.x) < p.n_units) produce(blockIdx.x, 0);
+  if (static_cast<int>(blockIdx.x) < p.n_units) produce(blockIdx.x, 0, kv_early ? 1 : 3);
   for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
     const int next = unit + gridDim.x;
-    if (next < p.n_units) produce(next, buf ^ 1);
+    if (next < p.n_units) produce(next, buf ^ 1, 3);
     ATC2_TR();
     mbar_wait(&bar_full[buf], buf ? fph1 : fph0);
     if (buf) fph1 ^= 1u; else fph0 ^= 1u;

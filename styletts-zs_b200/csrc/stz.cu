@@ -1306,7 +1306,17 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   } else if (kind == STZ_SAMPLER_TEACHER) {
     CK(H, cudaMemcpyAsync(w.noise, noise, (size_t)slices * BK * Ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
-  launch_k(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0); KCHECK(H);
+  {
+    // Launched WITHOUT programmatic serialization: a full dependency on everything before it.  Kernels of the evaluation
+    // loop read the call's constants (context K/V, modulations) before their griddepcontrol.wait (attention_tc2_kernel's
+    // early K/V boxes); this launch guarantees the conditioning prep has completed before any of them can start, also
+    // for tiny grids where a whole chain of waiting kernels is co-resident.
+    const int pdl_saved = g_use_pdl;
+    g_use_pdl = 0;
+    launch_k(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0);
+    g_use_pdl = pdl_saved;
+    KCHECK(H);
+  }
   H->launches += H->cur_launches;
   H->cur_launches = 0;
 
