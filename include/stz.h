@@ -150,7 +150,7 @@ int64_t stz_launch_count(const stz_handle* h);
  *   "gemm_bn"        0 | 128/192/256   tile width heuristic | forced (process-wide)
  *   "gemm_cluster"   0 | 1        single-CTA tiles | cta_group::2 CTA pairs (process-wide)
  *   "fuse_ln"        3 | 0 | 1 | 2 | 4   cluster-of-two GEMM + residual + LayerNorm with the residual tile staged in the operand
- *                                 ring (from 36 row tiles up, GEMM + ln_mod kernels below) | GEMM + ln_mod kernels | one-CTA fused
+ *                                 ring (36 .. 140 and >= 350 row tiles, GEMM + ln_mod kernels otherwise) | GEMM + ln_mod kernels | one-CTA fused
  *                                 kernel | first cluster-of-two fused kernel | 3 at any size
  *   "attn_impl"      0 | 1 | 2 | 3   tcgen05 + TMA (resident keys, streaming for long text) | mma.sync resident keys |
  *                                 mma.sync streaming | tcgen05 + cp.async

@@ -1123,8 +1123,14 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   int fuse_mode = (impl == 0 && d == GLN_N) ? H->fuse_ln : 0;
   if ((fuse_mode == 3 || fuse_mode == 4) && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || 2 * ((GEMM_BM - 1 + 2 * K - 1) / (2 * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
   // below ~36 row tiles (B < ~46 at K = 50) the separate LayerNorm kernel is cheap and the fused kernel's long serial
-  // epilogue loses (measured: -2 .. -4 % at B = 16 / 32, +5 % at B >= 64); fuse_ln = 4 forces the fused kernel at any size
-  if (fuse_mode == 3 && cdiv(R, GEMM_BM) < 36) fuse_mode = 0;
+  // epilogue loses (measured: -2 .. -4 % at B = 16 / 32); from 36 to ~140 tiles (one to 1.9 waves of CTA pairs) it wins
+  // 1 .. 7 % (B = 48 .. 160); from there to ~350 tiles (two to four waves) its one-tile-per-CTA-pair grid quantises worse
+  // than the persistent GEMM + LayerNorm pair (measured 1 .. 4 % slower at B = 192 .. 384); with more waves it wins again
+  // (1.5 .. 2 % at B = 512 .. 1024).  fuse_ln = 4 forces the fused kernel at any size.
+  {
+    const int row_tiles = cdiv(R, GEMM_BM);
+    if (fuse_mode == 3 && (row_tiles < 36 || (row_tiles > 140 && row_tiles < 350))) fuse_mode = 0;
+  }
   if (fuse_mode == 4) fuse_mode = 3;
   const bool fused = fuse_mode != 0;
   GemmLnParams lb{};
