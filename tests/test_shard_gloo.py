@@ -26,10 +26,17 @@ def _oracle_compute(cfg, w):
     from oracle.model import OraclePath
     o = OraclePath(cfg, w)
 
-    def compute(text, mask, prompt, pmask, noise):
-        z = o.sample_style(text, prompt, 2, 2.0, text_mask=mask, prompt_mask=pmask, noise=noise)
+    def compute(text, mask, prompt, pmask, noise, seed=None, first_utterance=0):
+        z = o.sample_style(text, prompt, 2, 2.0, text_mask=mask, prompt_mask=pmask, noise=noise, seed=seed,
+                           first_utterance=first_utterance)
         return z, o.predict_duration(text, z, text_mask=mask)
     return compute
+
+
+def _seeded(inp, seed=99):
+    out = {k: v for k, v in inp.items() if k != "noise"}
+    out["seed"] = seed
+    return out
 
 
 def _worker(rank, world, port, q):
@@ -41,11 +48,13 @@ def _worker(rank, world, port, q):
     cfg = stz.TINY
     w = stz.init_weights(cfg, 0)
     inp = stz.synthetic_inputs(cfg, 5, 14, steps=2, seed=11, var_len=(3, 14))
-    res = stz.synthesize_sharded(_oracle_compute(cfg, w), inp, rank, world)
+    compute = _oracle_compute(cfg, w)
+    res = stz.synthesize_sharded(compute, inp, rank, world)
+    res_seeded = stz.synthesize_sharded(compute, _seeded(inp), rank, world)   # on-"device" noise from global indices
     if rank == 0:
-        q.put((res[0], res[1]))
+        q.put((res[0], res[1], res_seeded[0], res_seeded[1]))
     else:
-        assert res is None
+        assert res is None and res_seeded is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,12 +73,16 @@ def test_world_size_2_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    style, dur = q.get(timeout=240)
+    style, dur, style_seeded, dur_seeded = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert torch.allclose(style, ref_style, atol=2e-5)
     assert torch.equal(dur, ref_dur)
+    # seed mode: the two ranks drew their utterances' noise from global indices == the unsharded seeded run
+    full_seeded = _oracle_compute(cfg, w)(inp["text_emb"], inp["text_mask"], inp["prompt_feats"], inp["prompt_mask"], None, seed=99)
+    assert torch.allclose(style_seeded, full_seeded[0], atol=2e-5)
+    assert torch.equal(dur_seeded, full_seeded[1].to(torch.int32))
 
 
 def test_seeded_shards_draw_the_unsharded_noise():
