@@ -140,6 +140,15 @@ int stz_synthesize_host_wait(stz_handle* h, int slot);
 
 /* ---- introspection / unit-test entry points (not part of the drop-in surface) ---------- */
 
+/* Host-only (no device): the sigma schedule and the fused sampler-step coefficient tables of one call, as uploaded to the
+ * device.  Returns the number of denoiser evaluations E (steps for the student, 2*steps
+ * for the ADPM2 teacher) or a negative status; any output pointer may be NULL.
+ *   sigma_out [E] fp64; coef_out [E][8] fp32 = (c_x, c_mid, c_F, c_noise, c_in(next sigma), cfg_scale, dest, 0):
+ *   dest 0: x' = c_x x + c_mid x_mid + c_F F + c_noise noise, dest 1: x_mid = c_x x + c_F F;  tfeat_out [E][d_time] fp32;
+ *   init_out [2] fp64 = (sigma_0, c_in(sigma_0)). */
+int stz_debug_plan(const stz_config* cfg, int steps, int sampler_kind, float cfg_scale, double* sigma_out,
+                   float* coef_out, float* tfeat_out, double* init_out);
+
 /* Number of kernels launched by this handle since creation (graph nodes count per replay). */
 int64_t stz_launch_count(const stz_handle* h);
 

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <tuple>
@@ -692,6 +693,21 @@ static EvalPlan make_plan(const stz_config& c, int steps, int kind, float cfg_sc
     for (int i = 0; i < half; ++i) pl.tfeat.push_back((float)cos(cn * exp(log(100.0) * i / (half > 1 ? half - 1 : 1))));
   }
   return pl;
+}
+
+// Host-only: the schedule / coefficient tables of one call (no device needed) — `-m "not gpu"` tests check them against
+// oracle/schedule.py.  Returns the number of denoiser evaluations E; any output pointer may be NULL.
+//   sigma_out [E] fp64, coef_out [E][8] fp32 = (c_x, c_mid, c_F, c_noise, c_in(next), cfg_scale, dest, 0),
+//   tfeat_out [E][d_time] fp32, init_out [2] fp64 = (sigma_0, c_in(sigma_0)).
+extern "C" int stz_debug_plan(const stz_config* cfg, int steps, int sampler_kind, float cfg_scale, double* sigma_out,
+                              float* coef_out, float* tfeat_out, double* init_out) {
+  if (!cfg || steps < 1 || steps > 1024 || (sampler_kind != STZ_SAMPLER_STUDENT && sampler_kind != STZ_SAMPLER_TEACHER)) return STZ_E_ARG;
+  const EvalPlan pl = make_plan(*cfg, steps, sampler_kind, cfg_scale);
+  if (sigma_out) std::copy(pl.sigma.begin(), pl.sigma.end(), sigma_out);
+  if (coef_out) std::copy(pl.coef.begin(), pl.coef.end(), coef_out);
+  if (tfeat_out) std::copy(pl.tfeat.begin(), pl.tfeat.end(), tfeat_out);
+  if (init_out) { init_out[0] = pl.sigma0; init_out[1] = pl.cin0; }
+  return (int)pl.sigma.size();
 }
 
 // ------------------------------------------------------------------------------------------

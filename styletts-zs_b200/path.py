@@ -80,6 +80,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_set_noise_utterances.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64), i32]
     lib.stz_philox_normal.restype = i32
     lib.stz_philox_normal.argtypes = [C.c_uint64, C.c_uint64, i32, i32, i32, vp, i32, vp]
+    lib.stz_debug_plan.restype = i32
+    lib.stz_debug_plan.argtypes = [cfgp, i32, i32, f32, vp, vp, vp, vp]
     lib.stz_launch_count.restype = i64
     lib.stz_launch_count.argtypes = [vp]
     lib.stz_set_option.restype = i32
@@ -111,7 +113,7 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset", "stz_create",
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
-                    "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_set_noise_utterances", "stz_philox_normal", "stz_launch_count", "stz_set_option", "stz_profile_read",
+                    "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_set_noise_utterances", "stz_philox_normal", "stz_debug_plan", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16", "stz_op_attention")
 
@@ -380,3 +382,20 @@ def philox_normal(seed: int, first_utterance: int, slices: int, B: int, n_per_ut
     if rc != 0:
         raise StzError(f"stz_philox_normal failed ({rc}): {lib.stz_last_error(None).decode()}")
     return out
+
+
+def sampler_plan(cfg: StzConfig, steps: int, sampler="student", cfg_scale: float = 1.0):
+    """Host-only (runs without a GPU): the library's sigma schedule and fused sampler-step coefficient tables of one
+    call (include/stz.h: stz_debug_plan) -> dict(sigma [E] f64, coef [E,8] f32, tfeat [E,d_time] f32, sigma0, cin0)."""
+    lib = load_library()
+    kind = _kind(sampler)
+    E = 2 * steps if kind == SAMPLER_TEACHER else steps
+    sigma = torch.empty(E, dtype=torch.float64)
+    coef = torch.empty(E, 8, dtype=torch.float32)
+    tfeat = torch.empty(E, cfg.d_time, dtype=torch.float32)
+    init = torch.empty(2, dtype=torch.float64)
+    rc = lib.stz_debug_plan(C.byref(_cconfig(cfg)), int(steps), kind, float(cfg_scale), _ptr(sigma), _ptr(coef), _ptr(tfeat),
+                            _ptr(init))
+    if rc != E:
+        raise StzError(f"stz_debug_plan returned {rc}, expected {E} evaluations")
+    return {"sigma": sigma, "coef": coef, "tfeat": tfeat, "sigma0": float(init[0]), "cin0": float(init[1])}

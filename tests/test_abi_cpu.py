@@ -1,6 +1,7 @@
 """The C-ABI library loads on a CPU-only box and exports exactly what include/stz.h declares; the
 weight-blob layout agrees between spec.py and csrc/stz_layout.h; the product path fails loudly
-without a GPU (no CPU fallback).  No compute call is made here."""
+without a GPU (no CPU fallback); the library's host-side schedule / coefficient tables (stz_debug_plan, no device
+needed) reproduce the oracle's sampler loop.  No device compute call is made here."""
 import ctypes as C
 import os
 import re
@@ -92,3 +93,62 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+# ---------------------------------------------------------------------------------------------
+# host logic of the library without a GPU: the schedule / coefficient tables it uploads (stz_debug_plan)
+# against the oracle's schedule algebra and sampler loop
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sampler,steps", [("student", 1), ("student", 4), ("student", 7), ("teacher", 1), ("teacher", 3),
+                                           ("teacher", 32)])
+def test_library_sampler_plan_matches_oracle_loop(sampler, steps):
+    import math
+    import torch
+    from oracle import schedule as S
+    from oracle.model import sample_loop, SAMPLER_STUDENT, SAMPLER_TEACHER
+    cfg = stz.DEFAULT
+    plan = stz.sampler_plan(cfg, steps, sampler, cfg_scale=1.7)
+    sig, coef = plan["sigma"], plan["coef"].double()
+    kind = SAMPLER_TEACHER if sampler == "teacher" else SAMPLER_STUDENT
+    # a-1: the sigmas fed to the denoiser
+    if sampler == "student":
+        want = S.student_sigmas(steps, cfg)[:-1]
+    else:
+        ks = S.teacher_sigmas(steps, cfg)
+        want = []
+        for i in range(steps):
+            want += [ks[i], S.adpm2_sigmas(ks[i], ks[i + 1])[2]]
+    assert torch.allclose(sig, torch.tensor(want, dtype=torch.float64), rtol=1e-12)
+    assert abs(plan["sigma0"] - want[0]) < 1e-12 and abs(plan["cin0"] - S.edm_precond(want[0], cfg.sigma_data)[2]) < 1e-12
+    assert bool((coef[:, 5] == torch.tensor(1.7, dtype=torch.float32).double()).all())
+    # time features of c_noise = ln(sigma) / 4
+    for e, sg in enumerate(want):
+        tf = torch.tensor(S.time_features(math.log(sg) / 4.0, cfg.d_time), dtype=torch.float64)
+        assert torch.allclose(plan["tfeat"][e].double(), tf, atol=1e-6)
+    # a-2 / a-6: drive the oracle's sampler loop and the library's fused affine updates with the same toy network
+    g = torch.Generator().manual_seed(steps)
+    ns = steps + 1 if sampler == "teacher" else 1
+    noise = torch.randn(ns, 3, 5, generator=g, dtype=torch.float64)
+    net = lambda x_in, c_noise: torch.tanh(0.3 * x_in + 0.1 * c_noise)
+
+    def denoise(x, sigma):
+        c_skip, c_out, c_in, c_noise = S.edm_precond(sigma, cfg.sigma_data)
+        return c_skip * x + c_out * net(c_in * x, c_noise)
+    ref = sample_loop(cfg, denoise, noise, steps, kind)
+    x = plan["sigma0"] * noise[0]
+    x_mid = torch.zeros_like(x)
+    x_in = plan["cin0"] * x
+    for e in range(len(want)):
+        F = net(x_in, math.log(want[e]) / 4.0)
+        cx, cm, cF, cn, cin_next, _, dest, _ = (float(v) for v in coef[e])
+        if dest == 1.0:                                   # ADPM2 half step: only x_mid moves
+            x_mid = cx * x + cF * F
+            x_in = cin_next * x_mid
+        else:
+            nz = noise[e // 2 + 1] if sampler == "teacher" else 0.0
+            x = cx * x + cm * x_mid + cF * F + cn * nz
+            x_in = cin_next * x
+        nxt = want[e + 1] if e + 1 < len(want) else None
+        if nxt is not None:                               # the epilogue also emits c_in(next sigma) * state
+            assert abs(cin_next - S.edm_precond(nxt, cfg.sigma_data)[2]) < 1e-6 * max(1.0, cin_next)
+    assert torch.allclose(x, ref, rtol=2e-6, atol=2e-6)   # coefficients are stored in fp32
