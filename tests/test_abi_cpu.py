@@ -152,3 +152,22 @@ def test_library_sampler_plan_matches_oracle_loop(sampler, steps):
         if nxt is not None:                               # the epilogue also emits c_in(next sigma) * state
             assert abs(cin_next - S.edm_precond(nxt, cfg.sigma_data)[2]) < 1e-6 * max(1.0, cin_next)
     assert torch.allclose(x, ref, rtol=2e-6, atol=2e-6)   # coefficients are stored in fp32
+
+
+def test_header_is_plain_c_and_a_c_client_links_and_runs(tmp_path):
+    """include/stz.h compiles as C99 and a C program (tests/c/abi_smoke.c: no CUDA, no C++) links against libstz.so and
+    calls the host-only entry points — the boundary is a C ABI, not a C++ or torch one."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    inc, libdir = os.path.join(ROOT, "include"), os.path.join(ROOT, "styletts-zs_b200", "csrc")
+    stz.load_library()                                   # builds libstz.so if it is missing
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "stz.h")], check=True)
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc,
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lstz",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("ok 8 evaluations")
