@@ -831,41 +831,45 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   // parts: 1 = Q (written by the previous kernel), 2 = K / V.  The cross-attention K / V of a call are constants of the
   // evaluation loop (computed once in the conditioning prep), so the first unit's K / V boxes are requested BEFORE
   // griddepcontrol.wait and land while the previous kernel drains.
+  // Called by lane 0 of EVERY warp: each warp issues one box (a TMA issue costs ~150 cycles; eight of them from one
+  // thread held the whole CTA back at the next barrier).  Warp 0 arms the barrier with the unit's total bytes; boxes of
+  // other warps may complete before that — the transaction count is signed and the phase cannot complete before warp
+  // 0's arrive.
   auto produce_tma = [&](int unit, int buf, int parts) {
     const int b = unit / p.n_heads, head = unit - b * p.n_heads;
     const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
     const uint32_t bar = smem_u32(&bar_full[buf]);
     const int t0 = b * n_tok, hc = head * ATT_DH;
     if (parts & 2) {
-      mbar_expect_tx(&bar_full[buf], tx_bytes);          // the whole unit's bytes, armed with its first part
+      if (warp == 0) mbar_expect_tx(&bar_full[buf], tx_bytes);   // the whole unit's bytes, armed with its first part
       if (p.self) {
-        tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
-        tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
-        tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
-        tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
+        if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
+        else if (warp == 1) tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
+        else if (warp == 2) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
+        else if (warp == 3) tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
       } else {
         const uint32_t o1 = p.T8 * 128, o2 = (p.T8 + p.P8) * 128;
-        tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
-        tma_load_2d_u32(vs, &tmT, bar, p.col_v + hc, b * p.T);
-        tma_load_2d_u32(ks + o1, &tmP, bar, p.col_k + hc, b * p.P);
-        tma_load_2d_u32(vs + o1, &tmP, bar, p.col_v + hc, b * p.P);
-        tma_load_2d_u32(ks + o2, &tmN, bar, p.col_k + hc, 0);
-        tma_load_2d_u32(vs + o2, &tmN, bar, p.col_v + hc, 0);
+        if (warp == 0) tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
+        else if (warp == 1) tma_load_2d_u32(vs, &tmT, bar, p.col_v + hc, b * p.T);
+        else if (warp == 2) tma_load_2d_u32(ks + o1, &tmP, bar, p.col_k + hc, b * p.P);
+        else if (warp == 3) tma_load_2d_u32(vs + o1, &tmP, bar, p.col_v + hc, b * p.P);
+        else if (warp == 4) tma_load_2d_u32(ks + o2, &tmN, bar, p.col_k + hc, 0);
+        else if (warp == 5) tma_load_2d_u32(vs + o2, &tmN, bar, p.col_v + hc, 0);
       }
     }
     if (parts & 1) {
-      tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
-      tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+      if (warp == 6) tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
+      else if (warp == 7) tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
     }
   };
   const bool kv_early = !p.self && static_cast<int>(blockIdx.x) < p.n_units;
-  if (kv_early && tid == 0) produce_tma(blockIdx.x, 0, 2);
+  if (kv_early && lane == 0) produce_tma(blockIdx.x, 0, 2);
   pdl_sync();
   ATC2_TR();
 
   auto produce = [&](int unit, int buf, int parts) {
     const int b = unit / p.n_heads;
-    if (tid == 0) produce_tma(unit, buf, parts);
+    if (lane == 0) produce_tma(unit, buf, parts);
     if (tid < 128) {   // visibility of key row `tid`: bit 0 = conditional queries, bit 1 = unconditional queries
       uint8_t vis = 0;
       if (p.self) {
