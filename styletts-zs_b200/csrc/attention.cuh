@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q4 = warp & 3, half = warp >> 2;
   const int row = q4 * 32 + lane;                      // query row = TMEM lane
-  const int br = row >> 6, tok = row & 63;             // rows 0..63 conditional, 64..127 unconditional
+  const int br = row >> 6;                             // rows 0..63 conditional, 64..127 unconditional
   const int n_tok = p.n_style;
 #ifdef STZ_TRACE
   long long* tr = (g_att_trace != nullptr && tid == 0) ? g_att_trace + blockIdx.x * 32 : nullptr;
@@ -996,29 +996,40 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     const float ltot = psum[0][row] + psum[1][row];
     const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
     const int b = unit / p.n_heads, head = unit - b * p.n_heads;
-    __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
     ATC2_TR();
     mbar_wait(&bar_o, phase);
     tc_fence_after();
     ATC2_TR();
-    {  // out row = O / rowsum: this warp's 32 of the 64 columns
+    {  // out row = O / rowsum: this warp's 32 of the 64 columns, staged in the (dead) Q tile so that the global stores are
+       // full 128-byte rows (row-per-thread stores touched 32 lines per instruction: ~1 k cycles of LSU time per unit)
       uint32_t r[32];
       tmem_ld32(tmem_o + lane_addr + half * 32, r);
       tmem_ld_wait();
-      if (tok < n_tok) {
+      const uint32_t orow = qs + row * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + j * 8) = u;
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(orow + (((half * 4 + j) ^ (row & 7)) << 4),
+                     pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv),
+                     pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv),
+                     pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv),
+                     pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv));
+    }
+    tc_fence_before();
+    __syncthreads();     // O tile complete; TMEM and the row-statistic arrays are free again
+    {
+      __nv_bfloat16* obase = p.out + static_cast<size_t>(b) * p.n_q * p.ldo + head * ATT_DH;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int c = it * 256 + tid, orow_i = c >> 3, ch = c & 7;     // 8 x 16 B per 128-byte row
+        const int otok = orow_i & 63, obr = orow_i >> 6;
+        if (otok < n_tok) {
+          const uint4 v = lds_u4(qs + orow_i * 128 + ((ch ^ (orow_i & 7)) << 4));
+          *reinterpret_cast<uint4*>(obase + static_cast<size_t>(2 * otok + obr) * p.ldo + ch * 8) = v;
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();     // TMEM, this buffer and the row-statistic arrays are free again
+    fence_proxy_async();   // the next TMA boxes (async proxy) overwrite the staged tile
+    __syncthreads();     // this buffer is free again
     ATC2_TR();
     buf ^= 1;
     phase ^= 1u;

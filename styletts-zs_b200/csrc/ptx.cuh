@@ -154,6 +154,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // has completed and its writes are visible.  Both are no-ops when the kernel was launched without the attribute.
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void pdl_sync() { pdl_launch(); pdl_wait(); }
 
 // ---------------------------------------------------------------- misc
