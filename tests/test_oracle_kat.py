@@ -281,3 +281,17 @@ def test_philox_noise_is_a_function_of_the_global_utterance_only():
     assert not np.array_equal(a, PH.normal_noise(8, 0, 3, 6, 2048))
     big = PH.normal_noise(7, (1 << 32) + 5, 1, 1, 2048)          # the high utterance word is part of the counter
     assert not np.array_equal(big, PH.normal_noise(7, 5, 1, 1, 2048))
+
+
+def test_philox_normal_frozen_bit_patterns():
+    """Frozen outputs of the generator definition (counter layout, uniform mapping, polynomial Box-Muller): any change to
+    oracle/philox.py that alters a bit fails here; the CUDA kernel is held to the same bits in tests/test_gpu_parity.py."""
+    import numpy as np
+    from oracle import philox as PH
+    a = PH.normal_noise(1234, 0, 1, 1, 16)[0, 0].view(np.uint32)
+    assert [int(v) for v in a] == [0x3f9d54f8, 0xbfcee928, 0x3eede2d1, 0xbfc7bfcb, 0x3f3e4d4e, 0x3f2211b4, 0x3e40d63d,
+                                   0x3dd437c0, 0x3fd46003, 0xbe26305f, 0xbf280d37, 0xbe18edd8, 0x3f07201d, 0x3f22540d,
+                                   0x3f87d9a0, 0xbf30e697]
+    b = PH.normal_noise(2 ** 63 + 11, (1 << 32) + 3, 3, 2, 8)[2, 1].view(np.uint32)
+    assert [int(v) for v in b] == [0x3f177db5, 0xbf19577d, 0xbf812152, 0xbe716d18, 0x3f884dc3, 0xbf1b9418, 0xbe38c012,
+                                   0x3fd3134b]
