@@ -1444,7 +1444,7 @@ __global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __
     float prev_ltot = 0.f;
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
       const int buf = it & 1, par = it & 1;
-      const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+      const int b = unit / p.n_heads;
       const uint32_t qs = smem_base + buf * ATC_BUF_BYTES;
       if (warp < 4) {   // visibility of key row warp * 32 + lane -> per-branch 32-key chunk masks
         const int kr = warp * 32 + lane;

@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     const int r_in = q4 * 32 + lane;                // row inside the tile == TMEM lane
     const int m = tile_m * GEMM_BM + r_in;
     const int mm = m < p.M ? m : p.M - 1;           // clamp for loads; rows >= M are never stored (TMA clips)
-    const float* mrow = p.mod + static_cast<size_t>((mm / p.rows_per_utt) * 2 + (mm & 1)) * p.n_mod;
     const float* src = p.pos + static_cast<size_t>((mm >> 1) % p.n_style) * GLN_N;   // GLN_POS only
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + half * 128;
     const int col0 = ncol0 + half * 128;            // first global column of this warp
@@ -231,7 +230,6 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     const int r_in = q4 * 32 + lane;
     const int m = tile_m * GEMM_BM + r_in;
     const int mm = m < p.M ? m : p.M - 1;
-    const float* mrow = p.mod + static_cast<size_t>((mm / p.rows_per_utt) * 2 + (mm & 1)) * p.n_mod;
     const int col0 = ncol0 + half * 128;
     const uint32_t sw = r_in & 7;
     const float2 a0 = stats_s[0][r_in], a1 = stats_s[1][r_in], a2 = stats_s[2][r_in], a3 = stats_s[3][r_in];
