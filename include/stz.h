@@ -18,9 +18,11 @@
  *   - device entry points enqueue on `cuda_stream` (a cudaStream_t passed as void*) and
  *     return without synchronising; the caller owns all in/out buffers and keeps them alive
  *     until the stream is synchronised.  The library owns weights, workspace and CUDA graphs.
- *   - a handle is bound to one device and is not re-entrant (one host thread at a time).
+ *   - a handle is bound to one device and is not re-entrant (one host thread at a time); different handles may be
+ *     driven from different host threads concurrently (every knob is per handle).
  *   - masks are uint8 [B,T] / [B,P], 1 = valid token; text masks must be prefix masks.
- *   - there is no CPU fallback: stz_create fails with STZ_E_DEVICE on a non-sm_100 device.
+ *   - there is no CPU fallback: stz_create fails with STZ_E_DEVICE on anything but an sm_100 (compute capability 10.0)
+ *     device — the library carries sm_100a code only.
  */
 #ifndef STZ_H_
 #define STZ_H_
@@ -152,24 +154,37 @@ int stz_debug_plan(const stz_config* cfg, int steps, int sampler_kind, float cfg
 /* Number of kernels launched by this handle since creation (graph nodes count per replay). */
 int64_t stz_launch_count(const stz_handle* h);
 
-/* Knobs (product defaults first; the alternatives are measured A/B variants kept for cross-checks and tuning):
+/* The evaluation loop is captured as one CUDA graph per (B, text-length bucket, P, evaluations, sampler, masks).  Text
+ * lengths are rounded up to 32, 64, 96, 128, 192, 256, 384, 512, then multiples of 256, with the extra key positions
+ * masked, so a serving loop with free-form T captures at most ~10 graphs per (B, P, steps); at most "max_graphs" (32)
+ * are kept, least recently used evicted.  Returns the number of cached graphs; *captures_total (may be NULL) = captures
+ * since creation (a capture synchronises the stream: a warmed-up loop must not add any). */
+int stz_graph_count(const stz_handle* h, int64_t* captures_total);
+
+/* Sizes the workspace for the largest call that will be made (batch, text tokens, prompt tokens, sampler steps and kind),
+ * so that no later call reallocates it: a reallocation synchronises the device and drops every captured graph. */
+int stz_reserve(stz_handle* h, int max_B, int max_T, int max_P, int max_steps, int sampler_kind);
+
+/* Knobs of one handle (product defaults first; the alternatives are cross-checks kept for tests and tuning):
  *   "use_graph"      1 | 0        evaluation loop as one CUDA graph per shape bucket | eager launches
- *   "use_pdl"        1 | 0        programmatic dependent launch (process-wide)
- *   "gemm_impl"      0 | 1 | 2    persistent tcgen05 GEMM | SIMT cross-check kernel | first tcgen05 kernel
- *   "gemm_bn"        0 | 128/192/256   tile width heuristic | forced (process-wide)
- *   "gemm_cluster"   0 | 1        single-CTA tiles | cta_group::2 CTA pairs (process-wide)
- *   "fuse_ln"        3 | 0 | 1 | 2 | 4   cluster-of-two GEMM + residual + LayerNorm with the residual tile staged in the operand
- *                                 ring (36 .. 140 and >= 350 row tiles, GEMM + ln_mod kernels otherwise) | GEMM + ln_mod kernels | one-CTA fused
- *                                 kernel | first cluster-of-two fused kernel | 3 at any size
- *   "attn_impl"      0 | 1 | 2 | 3   tcgen05 + TMA (resident keys, streaming for long text) | mma.sync resident keys |
- *                                 mma.sync streaming | tcgen05 + cp.async
- *   "attn_tc3"       0 | 1        resident-key tcgen05 attention without | with a dedicated issuing warp
+ *   "t_buckets"      1 | 0        text-length buckets (see stz_graph_count) | exact T
+ *   "max_graphs"     32           cached graphs before least-recently-used eviction
+ *   "use_pdl"        1 | 0        programmatic dependent launch
+ *   "gemm_impl"      0 | 1        persistent tcgen05 GEMM | SIMT cross-check kernel
+ *   "gemm_bn"        0 | 128/192/256   tile width heuristic | forced
+ *   "fuse_ln"        3 | 0 | 4    residual GEMM + AdaLN in one cluster-of-two kernel where it measured faster (36 .. 140 and
+ *                                 >= 350 row tiles), GEMM + ln_mod kernels otherwise | never fused | fused at any size
+ *   "attn_impl"      0 | 2        tcgen05 + TMA attention (resident keys; streaming over 128-key blocks for long text; the
+ *                                 mma.sync streaming kernel beyond their shapes: P > 127, K > 64) | always the mma.sync kernel
  *   "chains"         1 | 2..8     utterance chains on parallel graph branches
- *   "lstm_impl"      0 | 1 | 2    tcgen05 cluster recurrence | generic kernel | fp32 FFMA cluster recurrence
+ *   "lstm_impl"      0 | 1        tcgen05 cluster recurrence | generic kernel
  *   "pred_gemm_impl" 0 | 1        split-bf16 tcgen05 predictor GEMMs | fp32 CUDA-core GEMMs
  *   "profile"        0 | 1        see stz_profile_read;   "ablate" (bit mask): tools/ablate.py timing attribution only
- * Returns STZ_E_ARG for unknown keys. */
+ * Knobs are per handle (two handles on two host threads do not interact).  Returns STZ_E_ARG for unknown keys. */
 int stz_set_option(stz_handle* h, const char* key, int value);
+/* Reads a knob back; also the read-only "last_fuse_mode" (0 | 3: what the last stz_sample_style dispatched for the residual
+ * GEMMs — tests assert that the benched configuration runs the fused kernel) and "last_T" (its text-length bucket). */
+int stz_get_option(const stz_handle* h, const char* key, int* value);
 
 /* Profile mode (set_option "profile" = 1; setting it also clears the records): sample_style /
  * predict_duration run eagerly (no CUDA graph) with a CUDA-event pair around every kernel launch.
@@ -196,10 +211,10 @@ int stz_debug_set_att_trace(stz_handle* h, long long* trace_dev);
  * for the slot meanings (tools/gemm_trace.py). */
 int stz_debug_set_gemm_trace(stz_handle* h, long long* trace_dev);
 
-/* Roofline measurement hook (bench.py): `iters` back-to-back launches of the product GEMM kernel for one shape
- * (C[M,N] = A[M,K] W[N,K]^T, epi 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual reduce-add, 6 = the fused gated residual + AdaLN kernel,
- * N = d_model) on the handle's
- * internal stream, timed with a CUDA-event pair; *avg_us = mean microseconds per launch.  Zero-filled operands. */
+/* Isolated-kernel microbenchmark (bench.py, sub-field of the roofline): `iters` back-to-back launches of the product GEMM
+ * kernel for one shape (C[M,N] = A[M,K] W[N,K]^T, epi 2 = bf16 out, 3 = GELU bf16 out, 4 = gated residual reduce-add,
+ * 6 = the fused gated residual + AdaLN kernel, N = d_model) on the handle's internal stream, timed with a CUDA-event pair;
+ * *avg_us = mean microseconds per launch.  Random operands (uniform, W scaled by 1/sqrt(K)), L2-warm. */
 int stz_bench_gemm(stz_handle* h, int M, int N, int K, int epi, int iters, double* avg_us);
 
 /* Max co-resident 8-CTA clusters of the BiLSTM recurrence kernel on the current device (diagnostic). */
@@ -213,10 +228,34 @@ int stz_op_gemm_bf16(const void* A_bf16_dev, const void* W_bf16_dev, const float
  * qkv [2*B*K, 3*d_model] in the denoiser's row layout (row = (b*K + k)*2 + branch), ldq = 3*d_model.  Otherwise
  * cross-attention: queries = first d_model columns of qkv (row stride ldq); keys [text ; prompt (conditional rows only)
  * | null prompt (unconditional rows only)], each K/V buffer holding K | V (2*d_model columns) per row.
- * out [2*B*K, d_model].  impl: 0 tcgen05 + TMA, 1 mma.sync resident keys, 2 mma.sync streaming, 3 tcgen05 + cp.async. */
+ * out [2*B*K, d_model].  impl: 0 tcgen05 + TMA (resident / streaming by shape), 2 mma.sync streaming. */
 int stz_op_attention(stz_handle* h, const void* qkv_dev, int ldq, const void* kv_text_dev, const void* kv_prompt_dev,
                      const void* kv_null_dev, const uint8_t* text_mask_dev, const uint8_t* prompt_mask_dev, int B,
                      int T, int P, void* out_dev, int impl, void* cuda_stream);
+
+/* Unit-test entries for the fused epilogues of the product GEMM kernel (device buffers; A [M,K], W [N,K] bf16).
+ *   epi 0: out fp32 [M,N] = A W^T + bias                 epi 1: ... + pos[(r / 2) % n_style]  (pos [n_style, N])
+ *   epi 2: out bf16 [M,N] = A W^T + bias                 epi 3: out bf16 = gelu_tanh(A W^T + bias)
+ *   epi 4: out fp32 [M,N] += gate[seq(r)] * (A W^T + bias), gate[s] = mod[s * n_mod + gate_off ...], seq(r) =
+ *          (r / (2 n_style)) * 2 + (r & 1): TMA reduce-add into `out` */
+int stz_op_gemm_epi(stz_handle* h, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K, int epi,
+                    void* out_dev, const float* mod_dev, int n_mod, int gate_off, const float* pos_dev, void* cuda_stream);
+
+/* The output projection with the fused sampler epilogue: F = A W^T + bias for the row pair
+ * (2j: conditional, 2j+1: unconditional), Fg = F_u + w (F_c - F_u), x' = c_x x[j] + c_mid x_mid[j] + c_F Fg + c_noise noise[j]
+ * written to x (dest 0) or x_mid (dest 1), xin rows 2j and 2j+1 = split-bf16 [hi | lo | hi] of c_in x' (row stride 3N).
+ * coef_dev: the 8 floats of one stz_debug_plan row.  x, x_mid, noise [M/2, N] fp32; tap (optional) receives Fg. */
+int stz_op_gemm_sampler(stz_handle* h, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K,
+                        float* x_dev, float* xmid_dev, const float* noise_dev, const float* coef_dev, void* xin_out_dev,
+                        float* tap_dev, void* cuda_stream);
+
+/* The fused residual GEMM + AdaLN kernel (gemmln3_kernel; N = d_model = 512, K a multiple of 256):
+ *   mode 0: h' = h + gate[seq] * (A W^T + bias)      mode 1: h' = A W^T + bias + pos[(r / 2) % n_style]
+ *   u = bf16(LN(h') * (1 + scale[seq]) + shift[seq])  ([hi | lo | hi] with row stride 3 * 512 if split3)
+ * h_dev [M,512] fp32 is read (mode 0) and overwritten with h'; gate / shift / scale rows at mod[s * n_mod + *_off]. */
+int stz_op_gemm_ln(stz_handle* h, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int K, int mode,
+                   float* h_dev, const float* mod_dev, int n_mod, int gate_off, int shift_off, int scale_off,
+                   const float* pos_dev, int split3, void* u_out_dev, void* cuda_stream);
 
 #ifdef __cplusplus
 }

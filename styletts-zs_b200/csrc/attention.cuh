@@ -281,219 +281,7 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// attention3_kernel — the product kernel whenever the whole key sequence of a unit fits in shared memory
-// (n_total <= 128, n_q <= 128; the streaming kernel above remains for longer text).
-//
-// Persistent: grid = min(units, 2 x SMs) CTAs of 8 warps, unit = (utterance, head).  A unit's Q, K, V tiles are
-// fetched with ONE cp.async group into one of two shared-memory buffers; the next unit's group is issued before
-// the current unit is computed, so global/L2 latency (and the padding-mask lookup in front of it) is paid once
-// per CTA instead of once per unit and key block.  K fragments come from ldmatrix.x4 (2 LDS per 8-key tile
-// instead of 8).  Same numerics as attention_kernel: bf16 mma.sync m16n8k16, fp32 online softmax.
-// ------------------------------------------------------------------------------------------------------
-constexpr int ATT3_ROWS = 128;
-constexpr int ATT3_BUF_BYTES = 3 * ATT3_ROWS * ATT_LDS * 2 + ATT3_ROWS;   // Q | K | V | visibility
-constexpr int ATT3_SMEM_BYTES = 2 * ATT3_BUF_BYTES;
-
-__global__ void __launch_bounds__(256, 2) attention3_kernel(const AttnParams p, int n_heads, int n_units) {
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int n_tok = p.n_q >> 1;
-  const int br = warp >> 2, qt = warp & 3;             // 4 warps per CFG branch, 16 style tokens each
-  const int tok0 = qt * 16 + g, tok1 = tok0 + 8;
-  const bool self_attn = p.nseg == 1 && p.seg[0].rule == KEY_SAME_BRANCH;
-  int n_total = 0;
-  for (int s = 0; s < p.nseg; ++s) n_total += p.seg[s].n;
-  const int n_blk = self_attn ? 2 : (n_total + ATT_KB - 1) / ATT_KB;
-  pdl_sync();
-
-  auto issue = [&](int unit, int buf) {
-    const int b = unit / n_heads, head = unit - b * n_heads;
-    uint8_t* base = att_smem + buf * ATT3_BUF_BYTES;
-    __nv_bfloat16 (*Qs)[ATT_LDS] = reinterpret_cast<__nv_bfloat16 (*)[ATT_LDS]>(base);
-    __nv_bfloat16 (*Ks)[ATT_LDS] = Qs + ATT3_ROWS;
-    __nv_bfloat16 (*Vs)[ATT_LDS] = Ks + ATT3_ROWS;
-    uint8_t* visb = base + 3 * ATT3_ROWS * ATT_LDS * 2;
-    const size_t qbase = static_cast<size_t>(b) * p.n_q;
-    // keys first (their source address depends on the padding mask): thread -> key row tid / 2, 4 chunks of K and of V
-    {
-      const int kr = tid >> 1, c0 = (tid & 1) * 4;
-      const __nv_bfloat16 *ksrc = p.seg[0].k, *vsrc = p.seg[0].v;
-      uint32_t bytes = 0;
-      uint8_t vis = 0;
-      int vk = self_attn ? 2 * (kr & 63) + (kr >> 6) : kr;     // self: rows 0..63 = conditional keys, 64..127 = unconditional
-      if (vk < n_total && (!self_attn || (kr & 63) < n_tok) && kr < n_blk * ATT_KB) {
-        int s = 0;
-        while (vk >= p.seg[s].n) { vk -= p.seg[s].n; ++s; }
-        const AttnSeg& sg = p.seg[s];
-        const bool ok = sg.mask == nullptr || sg.mask[static_cast<size_t>(b) * sg.n + vk] != 0;
-        if (ok) {
-          const size_t r = static_cast<size_t>(b) * sg.rows_per_utt + vk;
-          ksrc = sg.k + r * sg.ld + head * ATT_DH;
-          vsrc = sg.v + r * sg.ld + head * ATT_DH;
-          bytes = 16;
-          vis = sg.rule == KEY_ALL ? 3 : sg.rule == KEY_COND ? 1 : sg.rule == KEY_UNCOND ? 2 : ((vk & 1) ? 2 : 1);
-        }
-      }
-      if (kr < n_blk * ATT_KB) {
-#pragma unroll
-        for (int c = c0; c < c0 + 4; ++c) {
-          cp_async16(smem_u32(&Ks[kr][c * 8]), ksrc + c * 8, bytes);
-          cp_async16(smem_u32(&Vs[kr][c * 8]), vsrc + c * 8, bytes);
-        }
-        if (c0 == 0) visb[kr] = vis;
-      }
-    }
-    // Q, de-interleaved: smem row br * 64 + tok  <-  global row 2 * tok + br   (tok >= n_tok: zeros)
-#pragma unroll
-    for (int i = tid; i < ATT3_ROWS * 8; i += 256) {
-      const int r = i >> 3, ch = i & 7;
-      const int rb = r >> 6, tok = r & 63;
-      const bool ok = tok < n_tok;
-      cp_async16(smem_u32(&Qs[r][ch * 8]), p.q + (qbase + (ok ? 2 * tok + rb : 0)) * p.ldq + head * ATT_DH + ch * 8, ok ? 16u : 0u);
-    }
-  };
-
-  int buf = 0;
-  if (static_cast<int>(blockIdx.x) < n_units) issue(blockIdx.x, 0);
-  cp_async_commit();
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int next = unit + gridDim.x;
-    if (next < n_units) issue(next, buf ^ 1);
-    cp_async_commit();            // (possibly empty) keeps one group per iteration
-    cp_async_wait<1>();           // this unit's group has landed; the next one may still be in flight
-    __syncthreads();
-
-    const uint8_t* base = att_smem + buf * ATT3_BUF_BYTES;
-    const __nv_bfloat16 (*Qs)[ATT_LDS] = reinterpret_cast<const __nv_bfloat16 (*)[ATT_LDS]>(base);
-    const __nv_bfloat16 (*Kall)[ATT_LDS] = Qs + ATT3_ROWS;
-    const __nv_bfloat16 (*Vall)[ATT_LDS] = Kall + ATT3_ROWS;
-    const uint8_t* visb = base + 3 * ATT3_ROWS * ATT_LDS * 2;
-
-    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
-    float o[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-    uint32_t qa[4][4];
-    {
-      const int mi = lane >> 3, r = lane & 7;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        ldmatrix_x4(qa[kk], smem_u32(&Qs[warp * 16 + (mi & 1) * 8 + r][kk * 16 + (mi >> 1) * 8]));
-    }
-    const int blk_lo = self_attn ? br : 0, blk_hi = self_attn ? br + 1 : n_blk;
-    for (int blk = blk_lo; blk < blk_hi; ++blk) {
-      const __nv_bfloat16 (*Ks)[ATT_LDS] = Kall + blk * ATT_KB;
-      const __nv_bfloat16 (*Vs)[ATT_LDS] = Vall + blk * ATT_KB;
-      const uint8_t* kv = visb + blk * ATT_KB;
-      const uint32_t pair = __ballot_sync(0xffffffffu, (((kv[2 * lane] | kv[2 * lane + 1]) >> br) & 1) != 0);
-      uint32_t tmask = 0;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) tmask |= ((pair >> (4 * nt)) & 0xFu) ? (1u << nt) : 0u;
-      if (tmask == 0) continue;
-      float sc[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-        if ((tmask >> nt) & 1) {
-          const int mi = lane >> 3, r = lane & 7;
-#pragma unroll
-          for (int kp = 0; kp < 2; ++kp) {   // one ldmatrix.x4 = B fragments of two 16-wide k steps
-            uint32_t kb[4];
-            ldmatrix_x4(kb, smem_u32(&Ks[nt * 8 + r][(2 * kp + (mi >> 1)) * 16 + (mi & 1) * 8]));
-            mma_bf16_16816(sc[nt], qa[2 * kp], kb[0], kb[1]);
-            mma_bf16_16816(sc[nt], qa[2 * kp + 1], kb[2], kb[3]);
-          }
-        }
-      }
-      float bm[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const bool vis = ((tmask >> nt) & 1) && ((kv[nt * 8 + t * 2 + j] >> br) & 1);
-          sc[nt][j] = vis ? sc[nt][j] * p.scale_log2 : -INFINITY;
-          sc[nt][2 + j] = vis ? sc[nt][2 + j] * p.scale_log2 : -INFINITY;
-          bm[0] = fmaxf(bm[0], sc[nt][j]);
-          bm[1] = fmaxf(bm[1], sc[nt][2 + j]);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
-        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
-      }
-      float alpha[2], mnew[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        mnew[r] = fmaxf(mrow[r], bm[r]);
-        const float mb = mnew[r] == -INFINITY ? 0.f : mnew[r];
-        alpha[r] = exp2f(mrow[r] - mb);
-        mrow[r] = mnew[r];
-        mnew[r] = mb;
-        lrow[r] *= alpha[r];
-      }
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
-        if ((tmask >> nt) & 1) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            sc[nt][j] = exp2f(sc[nt][j] - mnew[0]);
-            sc[nt][2 + j] = exp2f(sc[nt][2 + j] - mnew[1]);
-            lrow[0] += sc[nt][j];
-            lrow[1] += sc[nt][2 + j];
-          }
-        } else {
-          sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (((tmask >> (2 * kk)) & 3u) == 0) continue;
-        uint32_t pa[4];
-        pa[0] = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
-        pa[1] = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
-        pa[2] = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
-        pa[3] = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
-#pragma unroll
-        for (int ntp = 0; ntp < 4; ++ntp) {
-          const int mi = lane >> 3, r = lane & 7;
-          uint32_t vb[4];
-          ldmatrix_x4_trans(vb, smem_u32(&Vs[kk * 16 + (mi & 1) * 8 + r][ntp * 16 + (mi >> 1) * 8]));
-          mma_bf16_16816(o[2 * ntp], pa, vb[0], vb[1]);
-          mma_bf16_16816(o[2 * ntp + 1], pa, vb[2], vb[3]);
-        }
-      }
-    }
-    // finalize + store
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
-      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
-    }
-    const float inv0 = lrow[0] > 0.f ? 1.f / lrow[0] : 0.f, inv1 = lrow[1] > 0.f ? 1.f / lrow[1] : 0.f;
-    const int b = unit / n_heads, head = unit - b * n_heads;
-    const size_t qbase = static_cast<size_t>(b) * p.n_q;
-    if (tok0 < n_tok) {
-      __nv_bfloat16* op = p.out + (qbase + 2 * tok0 + br) * p.ldo + head * ATT_DH + t * 2;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
-    }
-    if (tok1 < n_tok) {
-      __nv_bfloat16* op = p.out + (qbase + 2 * tok1 + br) * p.ldo + head * ATT_DH + t * 2;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(op + nt * 8) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
-    }
-    __syncthreads();   // everyone is done with `buf` before the next iteration's prefetch overwrites it
-    buf ^= 1;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// attention_tc_kernel — tcgen05 version of the resident-key attention (n_total <= 128, n_q <= 128).
+// tcgen05 resident-key attention (n_total <= 128, n_q <= 128): shared scheme of attention_tc2_kernel / attention_tcs_kernel.
 //
 // The mma.sync kernels above are instruction-issue bound (~9 k warp instructions per (utterance, head) unit,
 // 64 of them HMMA).  Here both contractions run on the 5th-generation tensor core and the softmax is
@@ -506,8 +294,7 @@ __global__ void __launch_bounds__(256, 2) attention3_kernel(const AttnParams p, 
 //                                    consumed as an MN-major B operand (no transpose)
 //   out = O / rowsum                 tcgen05.ld, one 128-byte row per thread
 // Row r of the tile = branch (r >> 6), style token (r & 63): a warp is branch-uniform.  Persistent CTAs of 4 warps,
-// 2 per SM; the next unit's Q/K/V are fetched with cp.async (de-interleaving, segment lookup and padding masks as
-// in attention3_kernel) while the current unit is computed.
+// 2 per SM; the next unit's Q/K/V are fetched while the current unit is computed.
 // ------------------------------------------------------------------------------------------------------
 constexpr int ATC_TILE = 128 * 128;                 // one 128-row x 128-byte operand tile
 constexpr int ATC_BUF_BYTES = 3 * ATC_TILE;         // Q | K | V   (P later overwrites Q | K)
@@ -534,214 +321,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 // its first two units into g_att_trace[cta][16].
 __device__ long long* g_att_trace = nullptr;
 
-__global__ void __launch_bounds__(128, 2) attention_tc_kernel(const AttnParams p, int n_heads, int n_units) {
-  extern __shared__ uint8_t atc_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_s, bar_o;
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint8_t visb[2][128];
-  __shared__ uint32_t colmask[2][2][4];     // [buffer][branch][32-column chunk]
-  const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#ifdef STZ_TRACE
-  long long* tr = (g_att_trace != nullptr && tid == 0) ? g_att_trace + blockIdx.x * 16 : nullptr;
-#else
-  constexpr long long* tr = nullptr;   // (make TRACE=1 enables the timeline)
-#endif
-  int tri = 0;
-#define ATC_TR() do { if (tr != nullptr && tri < 16) tr[tri++] = clock64(); } while (0)
-  ATC_TR();
-  const int n_tok = p.n_q >> 1;
-  const int br = warp >> 1;                            // rows 0..63 conditional, 64..127 unconditional
-  const int tok = tid & 63;
-  const bool self_attn = p.nseg == 1 && p.seg[0].rule == KEY_SAME_BRANCH;
-  int n_total = 0;
-  for (int s = 0; s < p.nseg; ++s) n_total += p.seg[s].n;
-
-  if (tid == 0) {
-    mbar_init(&bar_s, 1);
-    mbar_init(&bar_o, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<256>(&tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
-  ATC_TR();
-  pdl_sync();
-  ATC_TR();
-
-  // thread -> one operand row (Q row tid, K/V key row tid), eight 16-byte chunks each, written 128B-swizzled
-  auto issue = [&](int unit, int buf) {
-    const int b = unit / n_heads, head = unit - b * n_heads;
-    const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
-    const size_t qbase = static_cast<size_t>(b) * p.n_q;
-    const int kr = tid;
-    const __nv_bfloat16 *ksrc = p.seg[0].k, *vsrc = p.seg[0].v;
-    uint32_t bytes = 0;
-    uint8_t vis = 0;
-    int vk = self_attn ? 2 * (kr & 63) + (kr >> 6) : kr;     // self: rows 0..63 = conditional keys, 64..127 = unconditional
-    if (vk < n_total && (!self_attn || (kr & 63) < n_tok)) {
-      int s = 0;
-      while (vk >= p.seg[s].n) { vk -= p.seg[s].n; ++s; }
-      const AttnSeg& sg = p.seg[s];
-      const bool ok = sg.mask == nullptr || sg.mask[static_cast<size_t>(b) * sg.n + vk] != 0;
-      if (ok) {
-        const size_t r = static_cast<size_t>(b) * sg.rows_per_utt + vk;
-        ksrc = sg.k + r * sg.ld + head * ATT_DH;
-        vsrc = sg.v + r * sg.ld + head * ATT_DH;
-        bytes = 16;
-        vis = sg.rule == KEY_ALL ? 3 : sg.rule == KEY_COND ? 1 : sg.rule == KEY_UNCOND ? 2 : ((vk & 1) ? 2 : 1);
-      }
-    }
-    // coalesced copy: 8 consecutive lanes move one 128-byte row (a warp moves 4 rows per step); the per-row source
-    // pointers computed above by the row's owner thread are fetched by shuffle (rows of warp w belong to warp w)
-    const int ch = lane & 7;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int src_lane = it * 4 + (lane >> 3);
-      const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ksrc), src_lane));
-      const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(vsrc), src_lane));
-      const uint32_t by = __shfl_sync(0xffffffffu, bytes, src_lane);
-      const int row = warp * 32 + src_lane, rtok = row & 63;
-      const bool qok = rtok < n_tok;
-      const __nv_bfloat16* qsrc = p.q + (qbase + (qok ? 2 * rtok + (row >> 6) : 0)) * p.ldq + head * ATT_DH;
-      const uint32_t o = row * 128 + ((ch ^ (row & 7)) << 4);
-      cp_async16(ks + o, kp + ch * 8, by);
-      cp_async16(vs + o, vp + ch * 8, by);
-      cp_async16(qs + o, qsrc + ch * 8, qok ? 16u : 0u);
-    }
-    visb[buf][kr] = vis;
-  };
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
-  int buf = 0;
-  uint32_t phase = 0;
-  if (static_cast<int>(blockIdx.x) < n_units) issue(blockIdx.x, 0);
-  cp_async_commit();
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int next = unit + gridDim.x;
-    if (next < n_units) issue(next, buf ^ 1);
-    cp_async_commit();
-    ATC_TR();
-    cp_async_wait<1>();
-    fence_proxy_async();          // cp.async wrote through the generic proxy; the tensor core reads through the async proxy
-    __syncthreads();
-    ATC_TR();
-    {  // per-branch visibility of each 32-key chunk
-      const uint8_t v = visb[buf][warp * 32 + lane];
-      const uint32_t m0 = __ballot_sync(0xffffffffu, (v & 1) != 0), m1 = __ballot_sync(0xffffffffu, (v & 2) != 0);
-      if (lane == 0) { colmask[buf][0][warp] = m0; colmask[buf][1][warp] = m1; }
-    }
-    const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
-    if (tid == 0) {
-      tc_fence_after();
-      const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(ks);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(&bar_s);
-    }
-    __syncthreads();              // colmask visible
-    mbar_wait(&bar_s, phase);
-    tc_fence_after();
-    ATC_TR();
-
-    // ---- softmax of row `tid` ----
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    uint32_t cm[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) cm[c] = colmask[buf][br][c];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (cm[c] == 0) continue;   // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem_s + lane_addr + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((cm[c] >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
-    }
-    const float mb = (mx == -INFINITY ? 0.f : mx) * p.scale_log2;
-    float lsum = 0.f;
-    const uint32_t prow = qs + tid * 128, sw = tid & 7;     // P tile kb at qs + kb * ATC_TILE (over Q, then K)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t pb = prow + (c >> 1) * ATC_TILE;
-      if (cm[c] == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), 0u, 0u, 0u, 0u);
-        continue;
-      }
-      uint32_t r[32];
-      tmem_ld32(tmem_s + lane_addr + c * 32, r);
-      tmem_ld_wait();
-      float pv[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
-        pv[j] = ((cm[c] >> j) & 1u) ? e : 0.f;
-        lsum += pv[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
-                     pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    ATC_TR();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
-        const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
-        umma_bf16(tmem_o, da, db, idesc_o, j != 0 ? 1u : 0u);
-      }
-      umma_commit(&bar_o);
-    }
-    mbar_wait(&bar_o, phase);
-    tc_fence_after();
-    ATC_TR();
-    {  // out row = O / rowsum
-      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-      const int b = unit / n_heads, head = unit - b * n_heads;
-      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_o + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        if (tok < n_tok) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-            u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-            u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-            u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + c * 32 + j * 8) = u;
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();     // TMEM and this buffer are free again
-    ATC_TR();
-    buf ^= 1;
-    phase ^= 1u;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem_slot);
-}
-
 // ------------------------------------------------------------------------------------------------------
-// attention_tc2_kernel — attention_tc_kernel with (a) TMA operand staging and (b) 8 warps.
+// attention_tc2_kernel — the scheme above with (a) TMA operand staging and (b) 8 warps.
 //
-// (a) The timeline of attention_tc_kernel (tools/att_trace.py) showed ~1.5 k cycles of LSU time per unit just
+// (a) The timeline of a cp.async-staged first version (tools/att_trace.py) showed ~1.5 k cycles of LSU time per unit just
 //     issuing the 3072 16-byte cp.async of one unit.  Here one thread issues 6-8 TMA box copies per unit:
 //       self  : a 3-D view (column, branch, token) of the qkv buffer de-interleaves the CFG branches in the copy:
 //               box (64 cols, 1 branch, 64 tokens) -> tile rows branch * 64 + token, for Q, K and V;
@@ -1288,257 +871,6 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem_slot);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// attention_tc3_kernel — attention_tc2_kernel with a dedicated issuing warp.
-//
-// In tc2 thread 0 is both a softmax thread and the only issuer of the unit's 6-8 TMA copies and 12 tcgen05.mma
-// (~170 and ~50 cycles of issue each): ~1.5-2 k cycles of serial work per unit that the other 255 threads wait for at
-// the next __syncthreads.  Here warp 8 (one lane) does nothing but issue, runs AHEAD of the softmax warps (operands of
-// the unit after next in flight, S of the next unit computed while this unit's softmax runs), and meets them only on
-// mbarriers: bar_s (S ready), bar_p (P written by all 8 softmax warps), bar_o[2] (O ready), bar_done[2] (O drained).
-// O is double-buffered in TMEM and the epilogue of a unit is deferred until the NEXT unit's softmax has been computed,
-// so the P V round trip (issue + execution + commit) hides under that softmax.
-// The softmax warps synchronise among themselves with a named barrier.
-// ------------------------------------------------------------------------------------------------------
-constexpr int ATC3_THREADS = 288;
-__device__ __forceinline__ void att_named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__global__ void __launch_bounds__(ATC3_THREADS, 2) attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                       const __grid_constant__ CUtensorMap tmT,
-                                                                       const __grid_constant__ CUtensorMap tmP,
-                                                                       const __grid_constant__ CUtensorMap tmN,
-                                                                       const AttnTcParams p) {
-  extern __shared__ uint8_t atc_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[2], bar_s, bar_o[2], bar_p, bar_done[2];   // bar_o / bar_done: one per O accumulator
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t colmask[2][2][4];     // [unit parity][branch][32-column chunk]
-  __shared__ float pmax[2][128], psum[2][128];
-  const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tok = p.n_style;
-
-  if (tid == 0) {
-    prefetch_tmap(&tmQ);
-    prefetch_tmap(&tmT);
-    if (!p.self) { prefetch_tmap(&tmP); prefetch_tmap(&tmN); }
-    mbar_init(&bar_full[0], 1);
-    mbar_init(&bar_full[1], 1);
-    mbar_init(&bar_s, 1);
-    mbar_init(&bar_o[0], 1);
-    mbar_init(&bar_o[1], 1);
-    mbar_init(&bar_p, 8);        // one arrival per softmax warp
-    mbar_init(&bar_done[0], 8);
-    mbar_init(&bar_done[1], 8);
-    fence_barrier_init();
-  }
-  if (warp == 8) tmem_alloc<256>(&tmem_slot);
-  for (uint32_t o = tid * 16; o < 2 * ATC_BUF_BYTES; o += ATC3_THREADS * 16) st_shared_v4(smem_base + o, 0u, 0u, 0u, 0u);
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;     // O is double-buffered: columns 128..191 and 192..255
-  pdl_sync();
-
-  if (warp == 8) {
-    if (lane == 0) {
-      const uint32_t tx_bytes = p.self ? 6u * 8192u : 2u * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
-      auto produce = [&](int unit, int buf) {
-        const int b = unit / p.n_heads, head = unit - b * p.n_heads;
-        const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
-        const uint32_t bar = smem_u32(&bar_full[buf]);
-        mbar_expect_tx(&bar_full[buf], tx_bytes);
-        const int t0 = b * n_tok, hc = head * ATT_DH;
-        tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
-        tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
-        if (p.self) {
-          tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
-          tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
-          tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
-          tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
-        } else {
-          const uint32_t o1 = p.T8 * 128, o2 = (p.T8 + p.P8) * 128;
-          tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
-          tma_load_2d_u32(vs, &tmT, bar, p.col_v + hc, b * p.T);
-          tma_load_2d_u32(ks + o1, &tmP, bar, p.col_k + hc, b * p.P);
-          tma_load_2d_u32(vs + o1, &tmP, bar, p.col_v + hc, b * p.P);
-          tma_load_2d_u32(ks + o2, &tmN, bar, p.col_k + hc, 0);
-          tma_load_2d_u32(vs + o2, &tmN, bar, p.col_v + hc, 0);
-        }
-      };
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
-      auto issue_s = [&](int it) {     // S of the it-th unit of this CTA: waits for its operands
-        const int buf = it & 1;
-        mbar_wait(&bar_full[buf], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t qs = smem_base + buf * ATC_BUF_BYTES;
-        const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(qs + ATC_TILE);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&bar_s);
-      };
-      const int stride = gridDim.x;
-      int unit = blockIdx.x;
-      if (unit < p.n_units) {
-        produce(unit, 0);
-        if (unit + stride < p.n_units) produce(unit + stride, 1);
-        issue_s(0);
-      }
-      for (int it = 0; unit < p.n_units; unit += stride, ++it) {
-        const int buf = it & 1;
-        const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, vs = qs + 2 * ATC_TILE;
-        mbar_wait(&bar_p, it & 1);                              // P of this unit is in shared memory, S has been consumed
-        if (it > 1) mbar_wait(&bar_done[buf], ((it - 2) >> 1) & 1);   // the unit that last used this O accumulator has drained it
-        tc_fence_after();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
-          const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
-          umma_bf16(tmem_o + buf * 64, da, db, idesc_o, j != 0 ? 1u : 0u);
-        }
-        umma_commit(&bar_o[buf]);
-        if (unit + stride < p.n_units) issue_s(it + 1);   // runs right behind P V: ready before the softmax warps get there
-        if (unit + 2 * stride < p.n_units) {              // this unit's buffer is free once its P V has completed
-          mbar_wait(&bar_o[buf], (it >> 1) & 1);
-          produce(unit + 2 * stride, buf);
-        }
-      }
-    }
-  } else {
-    const int q4 = warp & 3, half = warp >> 2;
-    const int row = q4 * 32 + lane;                      // query row = TMEM lane
-    const int br = row >> 6, tok = row & 63;             // rows 0..63 conditional, 64..127 unconditional
-    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
-    // out row = O / rowsum (this warp's 32 of the 64 columns) of the `e`-th unit of this CTA
-    auto epilogue = [&](int unit, int e, float ltot) {
-      const int ob = e & 1;
-      const int b = unit / p.n_heads, head = unit - b * p.n_heads;
-      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
-      mbar_wait(&bar_o[ob], (e >> 1) & 1);
-      tc_fence_after();
-      const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
-      uint32_t r[32];
-      tmem_ld32(tmem_o + ob * 64 + lane_addr + half * 32, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_done[ob]);       // this O accumulator is in registers
-      if (tok < n_tok) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + j * 8) = u;
-        }
-      }
-    };
-    int it = 0, prev_unit = 0;
-    float prev_ltot = 0.f;
-    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
-      const int buf = it & 1, par = it & 1;
-      const int b = unit / p.n_heads;
-      const uint32_t qs = smem_base + buf * ATC_BUF_BYTES;
-      if (warp < 4) {   // visibility of key row warp * 32 + lane -> per-branch 32-key chunk masks
-        const int kr = warp * 32 + lane;
-        uint32_t vis = 0;
-        if (p.self) {
-          vis = (kr & 63) < n_tok ? (1u << (kr >> 6)) : 0u;
-        } else if (kr < p.T) {
-          vis = (p.tmask == nullptr || p.tmask[static_cast<size_t>(b) * p.T + kr] != 0) ? 3 : 0;
-        } else if (kr >= p.T8 && kr < p.T8 + p.P) {
-          vis = (p.pmask == nullptr || p.pmask[static_cast<size_t>(b) * p.P + (kr - p.T8)] != 0) ? 1 : 0;
-        } else if (kr == p.T8 + p.P8) {
-          vis = 2;
-        }
-        const uint32_t m0 = __ballot_sync(0xffffffffu, (vis & 1) != 0), m1 = __ballot_sync(0xffffffffu, (vis & 2) != 0);
-        if (lane == 0) { colmask[par][0][warp] = m0; colmask[par][1][warp] = m1; }
-      }
-      att_named_bar_sync(1, 256);
-      const uint32_t cm0 = colmask[par][br][half], cm1 = colmask[par][br][half + 2];
-      mbar_wait(&bar_s, par);
-      tc_fence_after();
-
-      // ---- pass 1: row max over the visible keys of this warp's chunks
-      float mx = -INFINITY;
-#pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const uint32_t cm = ci ? cm1 : cm0;
-        if (cm == 0) continue;   // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_s + lane_addr + (half + 2 * ci) * 32, r);
-        tmem_ld_wait();
-        if (cm == 0xffffffffu) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((cm >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
-        }
-      }
-      pmax[half][row] = mx;
-      att_named_bar_sync(1, 256);
-      mx = fmaxf(pmax[0][row], pmax[1][row]);
-      const float mb = (mx == -INFINITY ? 0.f : mx) * p.scale_log2;
-
-      // ---- pass 2: P = exp2(S * scale - max), masked, bf16, into the dead Q | K tiles (K-major, swizzled)
-      float lsum = 0.f;
-      const uint32_t prow = qs + row * 128, sw = row & 7;
-#pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c = half + 2 * ci;
-        const uint32_t cm = ci ? cm1 : cm0;
-        const uint32_t pb = prow + (c >> 1) * ATC_TILE;
-        if (cm == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), 0u, 0u, 0u, 0u);
-          continue;
-        }
-        uint32_t r[32];
-        tmem_ld32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
-        if (cm == 0xffffffffu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb)); lsum += pv[j]; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
-            pv[j] = ((cm >> j) & 1u) ? e : 0.f;
-            lsum += pv[j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
-                       pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
-      }
-      psum[half][row] = lsum;
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p);
-      // The row sums travel to the deferred epilogue in registers (psum is rewritten by the next unit's pass 2).
-      att_named_bar_sync(1, 256);                          // both column halves' psum are visible
-      const float ltot = psum[0][row] + psum[1][row];
-      // ---- epilogue of the PREVIOUS unit: its P V ran while this unit's softmax was computed
-      if (it > 0) epilogue(prev_unit, it - 1, prev_ltot);
-      prev_unit = unit;
-      prev_ltot = ltot;
-    }
-    if (it > 0) epilogue(prev_unit, it - 1, prev_ltot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc<256>(tmem_slot);
 }
 
 }  // namespace stz

@@ -23,21 +23,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // x [B,T,D] fp32 -> xb [B,T,D] bf16 and pooled [B,D] = masked mean over T (a-3).
 // grid = (B, D/128): a CTA owns 32 float4 columns of one utterance; 8 time slices x 32 column lanes.
+// T_src <= T: the source holds T_src tokens per utterance; tokens T_src .. T - 1 (a length bucket's padding, masked by
+// `mask`, which is [B, T]) are written as zeros without being read.
 __global__ void __launch_bounds__(256) cast_pool_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
                                                         __nv_bfloat16* __restrict__ xb, float* __restrict__ pooled,
-                                                        int T, int D) {
+                                                        int T, int D, int T_src) {
   pdl_sync();
   __shared__ float4 part[8][32];
   __shared__ int cnt_s[8];
   const int b = blockIdx.x, cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + cl;     // float4 column
-  const float* xr = x + static_cast<size_t>(b) * T * D;
+  const float* xr = x + static_cast<size_t>(b) * T_src * D;
   __nv_bfloat16* br = xb + static_cast<size_t>(b) * T * D;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
   for (int t = sl; t < T; t += 8) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(xr + static_cast<size_t>(t) * D) + c);
-    const bool ok = mask == nullptr || mask[static_cast<size_t>(b) * T + t];
+    const bool in_src = t < T_src;
+    const float4 v = in_src ? __ldg(reinterpret_cast<const float4*>(xr + static_cast<size_t>(t) * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool ok = in_src && (mask == nullptr || mask[static_cast<size_t>(b) * T + t]);
     // masked tokens are stored as zeros: their context K / V rows stay finite whatever the caller left in the
     // padding (the attention kernels load masked keys and rely on p = 0 * finite)
     uint2 u = make_uint2(0u, 0u);
@@ -113,6 +116,16 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h
       *reinterpret_cast<uint2*>(o + D) = split_lo4(y, u);
       *reinterpret_cast<uint2*>(o + 2 * D) = u;
     }
+  }
+}
+
+// dst [B, T] = src [B, T_src] (or all ones) followed by zeros: the key-padding mask of a text-length bucket.
+__global__ void __launch_bounds__(256) pad_mask_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int B, int T_src, int T) {
+  pdl_sync();
+  const size_t n = static_cast<size_t>(B) * T;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / T), t = static_cast<int>(i % T);
+    dst[i] = t < T_src ? (src != nullptr ? src[static_cast<size_t>(b) * T_src + t] : static_cast<uint8_t>(1)) : static_cast<uint8_t>(0);
   }
 }
 
@@ -202,6 +215,23 @@ __global__ void __launch_bounds__(256) split3_rows_kernel(const float* __restric
     *reinterpret_cast<uint2*>(o + segK) = split_lo4(x, hi);
     *reinterpret_cast<uint2*>(o + 2 * segK) = hi;
   }
+}
+
+// Benchmark operands (stz_bench_gemm): uniform bf16 / fp32 values in [-scale, scale) from an integer hash of the index.
+__device__ __forceinline__ float hash_uniform(size_t i, uint32_t salt) {
+  uint32_t x = static_cast<uint32_t>(i) * 0x9E3779B1u ^ (static_cast<uint32_t>(i >> 32) + salt) * 0x85EBCA77u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return static_cast<float>(x >> 8) * (2.0f / 16777216.0f) - 1.0f;
+}
+__global__ void __launch_bounds__(256) fill_random_bf16_kernel(__nv_bfloat16* __restrict__ y, size_t n, float scale, uint32_t salt) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16(scale * hash_uniform(i, salt));
+}
+__global__ void __launch_bounds__(256) fill_random_f32_kernel(float* __restrict__ y, size_t n, float scale, uint32_t salt) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    y[i] = scale * hash_uniform(i, salt);
 }
 
 // y[i] = a[i] + b[i % nb]   (bias folding at create time)

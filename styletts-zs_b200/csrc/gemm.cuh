@@ -1,10 +1,8 @@
 // Dense contractions of the style denoiser: C[M,N] = A[M,K] · W[N,K]^T (+ fused epilogue).
 //
-//   gemm_tc_kernel   — the product path: TMA (128B-swizzled K-major tiles) -> 4-stage smem ring ->
-//                      tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, 128 x BN tile) -> tcgen05.ld epilogue.
-//                      Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-//                      warps 2..5 = epilogue (one TMEM lane quadrant each).
-//   gemm_simt_kernel — same contract on CUDA cores; unit-test cross-check only ("gemm_impl" = 1).
+//   gemm2_kernel     — the product path (gemm2.cuh): persistent tcgen05 / TMEM / TMA kernel; this header holds the
+//                      parameter block, the epilogue definitions and the small fp32 CUDA-core linears.
+//   gemm_simt_kernel — same contract on CUDA cores: unit-test cross-check ("gemm_impl" = 1) and create-time M = 1 GEMMs.
 //
 // Row layout of denoiser activations ("R layout"): row r = (b*K + k)*2 + branch, branch 0 = cond,
 // 1 = uncond, so the CFG pair of one style token sits in adjacent TMEM lanes of one tile and the
@@ -51,7 +49,6 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
 
 // One row (m), 32 consecutive columns starting at n0, accumulators in v[].  Called by all 32
 // lanes of a warp whose lanes hold consecutive rows (needed by the EPI_SAMPLER pair shuffle).
@@ -146,102 +143,6 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int m, int n
   }
 }
 
-template <int BN, int STAGES>
-constexpr int gemm_smem_bytes() {
-  return STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;  // +1024: manual 1 KB alignment
-}
-
-template <int BN, int EPI, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB,
-                                                               const GemmParams p) {
-  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  constexpr int B_BYTES = BN * GEMM_BK * 2;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t acc_bar;
-  __shared__ uint32_t tmem_slot;
-
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-  const int num_kb = p.K / GEMM_BK;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(&acc_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<BN>(&tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-        const uint32_t sa = smem_base + s * (A_BYTES + B_BYTES);
-        // generic->shared address round trip: tma_load_2d wants a generic pointer only to re-derive it
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-            ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[s])), "r"(kb * GEMM_BK),
-            "r"(p.a_row0 + tile_m * GEMM_BM)
-            : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-            ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[s])),
-            "r"(kb * GEMM_BK), "r"(tile_n * BN)
-            : "memory");
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * (A_BYTES + B_BYTES);
-        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
-#pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per 16-element K step -> +2 in the >>4 address field
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
-      }
-      umma_commit(&acc_bar);
-    }
-  } else {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
-    const int m = tile_m * GEMM_BM + q * 32 + lane;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      epilogue_row32<EPI>(p, m, tile_n * BN + c * 32, v);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
-}
 
 // CUDA-core cross-check of the same contract (block = 128 rows x 32 columns, thread = row).
 template <int EPI>

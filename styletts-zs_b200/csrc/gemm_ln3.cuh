@@ -1,25 +1,53 @@
-// gemmln3_kernel — residual GEMM fused with the AdaLN that follows it, cluster of two CTAs per 128-row block, with the
-// residual tile staged in the (by then idle) operand ring.
-//
-// gemmln2_kernel proved the scheme (each CTA of the pair owns 256 of the 512 columns, the LayerNorm row statistics meet
-// over DSMEM) but lost to "GEMM + ln_mod_kernel": its epilogue fetched the residual h through two small staging tiles
-// per warp, one dependent TMA round trip per 32 columns.  Here:
+// gemmln3_kernel — a residual-writing GEMM fused with the AdaLN that follows it (style denoiser, N = d_model = 512), as a
+// CLUSTER OF TWO CTAs per 128-row block:
+//     acc   = A[128, K] · W[512, K]^T            CTA `rank` of the pair computes columns [256 rank, 256 rank + 256)
+//     h'    = h + gate[seq] * (acc + b)          (GLN_RES)     or     acc + b + pos[(r/2) % n_style]      (GLN_POS)
+//     u     = bf16( LN(h') * (1 + scale[seq]) + shift[seq] )          the next GEMM's A operand ([hi|lo|hi] if split3)
+// This replaces {GEMM with gated-residual epilogue, ln_mod_kernel}: one launch instead of two, h' written once, u produced
+// without re-reading h' from global memory.  The LayerNorm needs statistics of full 512-wide rows: each CTA reduces its
+// 256 columns, the halves of a row meet through distributed shared memory (st.shared::cluster + one cluster barrier).
+// Two earlier forms (one CTA per row block; cluster of two with per-chunk residual staging) measured slower and were
+// removed (git history: gemm_ln.cuh, gemm_ln2.cuh).  What this version does differently:
 //   * once the producer has issued the last operand tiles it keeps going around the ring and TMA-loads the CTA's whole
 //     residual tile h[128 x 256] fp32 (8 boxes of 128 rows x 32 columns = 128 KB) into the stages as the MMAs release
 //     them — under the tail of the mainloop, so the tile is resident when the accumulator is;
 //   * pass 1 forms h' = h + gate * (acc + b) IN PLACE in that tile, accumulates the row statistics, and four TMA stores
 //     per column half write h' back — no per-chunk waits;
-//   * the statistics of the two column halves / two CTAs meet through shared memory + DSMEM and one cluster barrier;
-//   * pass 2 re-reads h' from the tile, normalises + modulates, and builds the bf16 operand u in the remaining 64 KB of
+//   * pass 2 re-reads h' (kept in TMEM), normalises + modulates, and builds the bf16 operand u in the remaining 64 KB of
 //     the ring (4 boxes of 128 rows x 64 columns), stored with two TMA stores per column half.
 //   * bias and the per-sequence gate / scale / shift rows of the tile (<= 8 sequences x 256 columns) are copied into a
 //     25 KB shared-memory table by the epilogue warps WHILE the mainloop runs: fetched from L2 inside the passes they
 //     cost a full ~1.5 k-cycle round trip per 32-column chunk (measured: 13 k + 9 k cycles for the two passes).
 // Shared memory = the 4-stage operand ring (192 KB) + that table.
 #pragma once
-#include "gemm_ln2.cuh"
+#include "gemm2.cuh"
 
 namespace stz {
+
+enum GlnMode : int { GLN_RES = 0, GLN_POS = 1 };
+
+struct GemmLnParams {
+  int M, K;               // valid rows, contraction length (multiple of 64)
+  const float* bias;      // [512]
+  float* h;               // [M, 512] residual stream (read in GLN_RES, always written)
+  const float* mod;       // [n_seq, n_mod] AdaLN modulations of this evaluation
+  int n_mod, gate_off, shift_off, scale_off;
+  int rows_per_utt;       // 2 * n_style
+  const float* pos;       // [n_style, 512]  (GLN_POS)
+  int n_style;
+  int split3;             // u is the split-bf16 operand [hi | lo | hi] with row stride 3 * 512
+};
+
+constexpr int GLN_N = 512, GLN_THREADS = 320;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t local_smem_addr, uint32_t rank, float a, float b) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
+}
 
 constexpr int GLN3_STAGES = 4, GLN3_BN = 256;
 constexpr int GLN3_STAGE_BYTES = GEMM_BM * GEMM_BK * 2 + GLN3_BN * GEMM_BK * 2;   // 48 KB

@@ -47,12 +47,16 @@ __global__ void __launch_bounds__(256) style_pool_attn_kernel(const float* __res
 
 // needed[t] = 1 iff any of the rows 128 t .. 128 t + 127 of a [rows] mask is valid: the predictor's GEMMs skip 128-row
 // tiles that hold nothing but padding (variable-length batches: about half of cfg4's B x T rows).
-__global__ void __launch_bounds__(256) tile_needed_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ needed, int rows) {
+// tiles_per_utt > 0 (utterances aligned to tiles): the FIRST tile of every utterance is always needed, so consumers that
+// unconditionally visit an utterance's first key block (attention_tcs_kernel) read initialised, finite rows even for a
+// zero-length utterance.
+__global__ void __launch_bounds__(256) tile_needed_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ needed, int rows,
+                                                          int tiles_per_utt) {
   pdl_sync();
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int r0 = warp * 128;
   if (r0 >= rows) return;
-  int any = 0;
+  int any = (tiles_per_utt > 0 && warp % tiles_per_utt == 0) ? 1 : 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + i * 32 + lane;
@@ -441,146 +445,6 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
-}
-
-template <int NB>
-constexpr int lstm_cluster_smem() { return (2 * NB * LC_H + LC_SL * NB * LC_COLS) * 4; }
-
-// Thread layout of the matrix-vector phase: warp w -> k-slice (w >> 1) of 32, gate pair 2*(w & 1), lane = unit;
-// each thread keeps 2 columns x 32 k of W_hh in registers, so one broadcast LDS.128 of h feeds 8 FMAs.
-// A cluster advances NB = NBI * PASSES sequences: PASSES sweeps of NBI sequences over the same weight registers
-// (NB is chosen on the host so that all clusters of a launch are co-resident: one wave).
-template <int NBI, int PASSES>
-__global__ void __cluster_dims__(LC_CS, 1, 1) __launch_bounds__(LC_THREADS, 1)
-lstm_cluster_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const int* __restrict__ lens,
-                    const int* __restrict__ perm, float* __restrict__ out, int B, int T) {
-  constexpr int NB = NBI * PASSES;
-  static_assert(NB <= LC_THREADS / 32, "one pointwise-update warp per sequence");
-  extern __shared__ __align__(16) float lc_smem[];
-  float (*h_s)[NB][LC_H] = reinterpret_cast<float (*)[NB][LC_H]>(lc_smem);                               // [2][NB][H]
-  float (*part_s)[NB][LC_COLS] = reinterpret_cast<float (*)[NB][LC_COLS]>(lc_smem + 2 * NB * LC_H);      // [SL][NB][COLS]
-  __shared__ __align__(8) uint64_t hbar[2];   // hbar[b]: all 8 CTAs' slices of h have landed in h_s[b]
-  __shared__ int len_s[NB], seq_s[NB];
-  const int rank = static_cast<int>(cluster_ctarank());
-  const int group = blockIdx.x / LC_CS, dir = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slice = warp >> 1, g0 = (warp & 1) * 2;
-
-  float wa[LC_KS], wb[LC_KS];
-  {
-    const size_t row = static_cast<size_t>(dir) * 4 * LC_H + rank * LC_UPC + lane;
-    const float4* ra = reinterpret_cast<const float4*>(Whh + (row + g0 * LC_H) * LC_H + slice * LC_KS);
-    const float4* rb = reinterpret_cast<const float4*>(Whh + (row + (g0 + 1) * LC_H) * LC_H + slice * LC_KS);
-#pragma unroll
-    for (int i = 0; i < LC_KS / 4; ++i) {
-      const float4 a = __ldg(ra + i), b = __ldg(rb + i);
-      wa[4 * i] = a.x; wa[4 * i + 1] = a.y; wa[4 * i + 2] = a.z; wa[4 * i + 3] = a.w;
-      wb[4 * i] = b.x; wb[4 * i + 1] = b.y; wb[4 * i + 2] = b.z; wb[4 * i + 3] = b.w;
-    }
-  }
-  pdl_sync();   // W_hh (constant) was loaded above, under the previous kernel's tail
-  if (tid < NB) {
-    const int idx = group * NB + tid;
-    const int seq = idx < B ? perm[idx] : -1;
-    seq_s[tid] = seq;
-    len_s[tid] = seq >= 0 ? lens[seq] : 0;
-  }
-  if (tid == 0) {
-    mbar_init(&hbar[0], 1);
-    mbar_init(&hbar[1], 1);
-    fence_barrier_init();
-  }
-  for (int i = tid; i < 2 * NB * LC_H; i += LC_THREADS) lc_smem[i] = 0.f;
-  __syncthreads();
-  int maxlen = 0;
-#pragma unroll
-  for (int n = 0; n < NB; ++n) maxlen = max(maxlen, len_s[n]);
-  for (int n = 0; n < NB; ++n) {  // zero this CTA's unit slice of the padded tail
-    if (seq_s[n] < 0) continue;
-    for (int t = len_s[n] + warp; t < T; t += LC_THREADS / 32)
-      out[(static_cast<size_t>(seq_s[n]) * T + t) * 2 * LC_H + dir * LC_H + rank * LC_UPC + lane] = 0.f;
-  }
-  cluster_sync_all();   // peers are resident and their barriers initialised before any DSMEM traffic
-
-  const bool upd = warp < NB;   // pointwise update: warp n owns sequence n, lane = unit
-  const int my_len = upd ? len_s[warp] : 0, my_seq = upd ? seq_s[warp] : -1;
-  float c_state = 0.f;
-  float gpre[4] = {0.f, 0.f, 0.f, 0.f};
-  auto load_g = [&](int s) {
-    if (upd && s < my_len) {
-      const int t = dir == 0 ? s : my_len - 1 - s;
-      const float* gp = G + (static_cast<size_t>(my_seq) * T + t) * 8 * LC_H + dir * 4 * LC_H + rank * LC_UPC + lane;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) gpre[g] = __ldg(gp + g * LC_H);
-    }
-  };
-  load_g(0);
-  constexpr uint32_t kStepBytes = NB * LC_H * 4;
-  int cur = 0;
-  for (int s = 0; s < maxlen; ++s) {
-    if (tid == 0) mbar_expect_tx(&hbar[cur ^ 1], kStepBytes);   // arm the buffer this step's h will land in
-#pragma unroll
-    for (int pass = 0; pass < PASSES; ++pass) {
-      float acc_a[NBI], acc_b[NBI];
-#pragma unroll
-      for (int n = 0; n < NBI; ++n) { acc_a[n] = 0.f; acc_b[n] = 0.f; }
-#pragma unroll
-      for (int i = 0; i < LC_KS; i += 4) {
-#pragma unroll
-        for (int n = 0; n < NBI; ++n) {
-          const float4 hv = *reinterpret_cast<const float4*>(&h_s[cur][pass * NBI + n][slice * LC_KS + i]);
-          acc_a[n] = fmaf(wa[i], hv.x, acc_a[n]);     acc_b[n] = fmaf(wb[i], hv.x, acc_b[n]);
-          acc_a[n] = fmaf(wa[i + 1], hv.y, acc_a[n]); acc_b[n] = fmaf(wb[i + 1], hv.y, acc_b[n]);
-          acc_a[n] = fmaf(wa[i + 2], hv.z, acc_a[n]); acc_b[n] = fmaf(wb[i + 2], hv.z, acc_b[n]);
-          acc_a[n] = fmaf(wa[i + 3], hv.w, acc_a[n]); acc_b[n] = fmaf(wb[i + 3], hv.w, acc_b[n]);
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < NBI; ++n) {
-        part_s[slice][pass * NBI + n][g0 * 32 + lane] = acc_a[n];
-        part_s[slice][pass * NBI + n][(g0 + 1) * 32 + lane] = acc_b[n];
-      }
-    }
-    __syncthreads();
-    if (upd) {
-      const int n = warp;
-      float hn;
-      if (s < my_len) {
-        float pre[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float a = 0.f;
-#pragma unroll
-          for (int q = 0; q < LC_SL; ++q) a += part_s[q][n][g * 32 + lane];
-          pre[g] = gpre[g] + a;
-        }
-        const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gt = tanhf(pre[2]), og = sigmoidf_(pre[3]);
-        c_state = fg * c_state + ig * gt;
-        hn = og * tanhf(c_state);
-      } else {
-        hn = h_s[cur][n][rank * LC_UPC + lane];
-      }
-      const uint32_t dst = smem_u32(&h_s[cur ^ 1][n][rank * LC_UPC + lane]);
-      const uint32_t bar = smem_u32(&hbar[cur ^ 1]);
-#pragma unroll
-      for (int r = 0; r < LC_CS; ++r) st_async_f32(mapa_u32(dst, r), hn, mapa_u32(bar, r));
-      if (s < my_len) {
-        const int t = dir == 0 ? s : my_len - 1 - s;
-        out[(static_cast<size_t>(my_seq) * T + t) * 2 * LC_H + dir * LC_H + rank * LC_UPC + lane] = hn;
-      }
-    }
-    // wait until every CTA's slice of h_{s} has landed here
-    {
-      const uint32_t parity = (s >> 1) & 1;
-      uint32_t spins = 0;
-      while (!mbar_try_wait_cluster(&hbar[cur ^ 1], parity)) {
-        if (++spins > (1u << 24)) __trap();
-      }
-    }
-    cur ^= 1;
-    load_g(s + 1);   // consumed after the next matrix-vector phase: the L2 latency hides under it
-  }
-  cluster_sync_all();   // nobody exits while a peer could still be sending to it
 }
 
 }  // namespace stz

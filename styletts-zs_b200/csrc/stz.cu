@@ -20,8 +20,6 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
-#include "gemm_ln.cuh"
-#include "gemm_ln2.cuh"
 #include "gemm_ln3.cuh"
 #include "philox.cuh"
 #include "predictor.cuh"
@@ -70,11 +68,10 @@ constexpr int STZ_MAX_CHAINS = 8;
 // The sigma schedule is known before the loop, so the AdaLN modulations c[e] · Wmod^T of every evaluation can be one GEMM
 // (M = E * 2B) instead of E small ones at the head of each evaluation's dependency chain.  E * 2B * n_mod floats: 78 MB at
 // cfg2 (E = 4), 620 MB at cfg3 (64 teacher evaluations, B = 32); beyond 1 GB the per-evaluation GEMM is kept.
-constexpr int STZ_HOIST_MOD_MAX_EVALS = 8;
 constexpr size_t STZ_HOIST_MOD_MAX_BYTES = (size_t)1 << 30;
 static bool hoist_mod(const stz_config& c, int B, int E) {
   const size_t bytes = (size_t)E * 2 * B * (9 * c.n_layers + 2) * c.d_model * sizeof(float);
-  return E <= STZ_HOIST_MOD_MAX_EVALS || bytes <= STZ_HOIST_MOD_MAX_BYTES;
+  return bytes <= STZ_HOIST_MOD_MAX_BYTES;
 }
 
 struct stz_handle {
@@ -95,7 +92,6 @@ struct stz_handle {
   float* whh = nullptr;                                  // [n_lstm][2][4h][h]  (row-major: cluster kernel)
   float* lstm_b = nullptr;                               // [n_lstm][2][4h] = b_ih + b_hh
   // predictor GEMMs on tcgen05 at fp32-grade precision: split-bf16 weights [hi | hi | lo] (K tripled)
-  int lstm_max_clusters = 15;   // co-resident 8-CTA clusters of lstm_cluster_kernel on this device
   bool pred_tc = false;
   bf16 *wq3 = nullptr, *wkv3 = nullptr, *wo3 = nullptr, *wih3 = nullptr, *wada3 = nullptr;
   float* b_kv = nullptr;
@@ -121,13 +117,21 @@ struct stz_handle {
   cudaStream_t last_stream = nullptr;
   cudaEvent_t last_ev = nullptr;
   bool has_last = false;
-  std::map<std::tuple<int, int, int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
+  // captured evaluation loops, keyed by (B, T bucket, P, evaluations, sampler kind + mask flags); least-recently-used
+  // entries are evicted beyond max_graphs
+  struct GraphEntry { cudaGraphExec_t exec; int launches; uint64_t last_use; };
+  std::map<std::tuple<int, int, int, int, int>, GraphEntry> graphs;
+  uint64_t graph_clock = 0;
+  int64_t graph_captures = 0;   // captures since creation (stz_graph_count)
+  int max_graphs = 32;
+  int t_buckets = 1;            // round the text length up to a bucket (with masks) so that free-form T reuses graphs
+  int last_fuse_mode = 0, last_T = 0;   // what the last sample_style call dispatched (stz_get_option: tests assert the benched kernel ran)
   int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 3;
   int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
-  int attn_tc3 = 0;    // resident-key tcgen05 attention with a dedicated issuing warp (0: attention_tc2_kernel)
-  int attn_impl = 0;   // 0 = tcgen05 + TMA kernel when the keys fit (else streaming), 1 = mma.sync resident-key kernel, 2 = always streaming, 3 = tcgen05 + cp.async
+  int attn_impl = 0;   // 0 = tcgen05 + TMA kernels (resident keys, streaming for long text; mma.sync streaming beyond their shapes), 2 = always the mma.sync streaming kernel
+  int use_pdl = 1, gemm_bn = 0, gemm_cluster = 0;   // launch knobs (copied into the thread-local launch context by every entry point)
   int ablate = 0;   // tools/ablate.py: bit mask of kernel families skipped inside run_eval (timing attribution only; results are wrong)
   int64_t launches = 0;
   int cur_launches = 0;  // launches issued since the counter was last sampled (capture bookkeeping)
@@ -191,6 +195,35 @@ static int fail(stz_handle* H, int code, const char* fmt, ...) {
     if (rc_ != 0) return rc_; \
   } while (0)
 
+// Launch-time knobs of the handle whose call is running on this host thread (set by every entry point that launches:
+// LaunchScope).  Thread-local, so handles driven from different host threads never see each other's settings.
+struct LaunchCtx { int use_pdl = 1, gemm_bn = 0, gemm_cluster = 0; };
+static thread_local LaunchCtx tl_launch;
+
+static void drop_graphs(stz_handle* H) {
+  for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.exec);
+  H->graphs.clear();
+}
+
+// Text-length buckets of the captured evaluation loop: 32, 64, 96, 128, 192, 256, 384, 512, then multiples of 256.
+// A call with T tokens runs at the bucket's length with the extra key positions masked (padding invariance is a tested
+// property of the path), so a serving loop with free-form T captures at most ~10 graphs per (B, P, steps).
+static int bucket_T(int T) {
+  static const int b[] = {32, 64, 96, 128, 192, 256, 384, 512};
+  for (int v : b) if (T <= v) return v;
+  return (T + 255) / 256 * 256;
+}
+static bool runs_graphed(const stz_handle* H) { return H->use_graph && H->tap_buf == nullptr && !H->profile; }
+static int effective_T(const stz_handle* H, int T) { return runs_graphed(H) && H->t_buckets ? bucket_T(T) : T; }
+
+// Every entry point that launches kernels installs its handle's launch knobs for the calling thread.
+struct LaunchScope {
+  explicit LaunchScope(const stz_handle* H) {
+    tl_launch = LaunchCtx();
+    if (H) { tl_launch.use_pdl = H->use_pdl; tl_launch.gemm_bn = H->gemm_bn; tl_launch.gemm_cluster = H->gemm_cluster; }
+  }
+};
+
 static int order_after_previous_call(stz_handle* H, cudaStream_t st) {
   if (H->has_last && st != H->last_stream) CK(H, cudaStreamWaitEvent(st, H->last_ev, 0));
   return 0;
@@ -208,14 +241,13 @@ static int mark_call_end(stz_handle* H, cudaStream_t st) {
 // prologue while the previous kernel drains; every kernel launched this way executes griddepcontrol.wait
 // before touching global memory (ptx.cuh: pdl_wait), so completion stays transitive along the stream.
 // ------------------------------------------------------------------------------------------
-static int g_use_pdl = 1;
 template <typename... KArgs, typename... Args>
-static void launch_kc(int cluster_x, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+static void launch_kcp(bool pdl, int cluster_x, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   int n = 0;
-  if (g_use_pdl) {
+  if (pdl) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -230,8 +262,17 @@ static void launch_kc(int cluster_x, void (*kern)(KArgs...), dim3 grid, dim3 blo
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>
+static void launch_kc(int cluster_x, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_kcp(tl_launch.use_pdl != 0, cluster_x, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
 static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   launch_kc(1, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+// Full (non-programmatic) dependency on everything before it in the stream, whatever the handle's PDL setting.
+template <typename... KArgs, typename... Args>
+static void launch_k_nopdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_kcp(false, 1, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -298,30 +339,14 @@ static int make_tmap_nd(CUtensorMap* m, const void* base, int rank, const cuuint
 // ------------------------------------------------------------------------------------------
 // GEMM launchers
 // ------------------------------------------------------------------------------------------
-constexpr int GEMM_BN = 128;
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_BN = 128;   // N granularity of every GEMM
 
-template <int EPI>
-static int launch_gemm_tc(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W,
-                          const GemmParams& p) {
-  CUtensorMap ta, tb;
-  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
-      make_tmap(&tb, W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, GEMM_BN))
-    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", p.M, p.N, p.K);
-  constexpr int smem = gemm_smem_bytes<GEMM_BN, GEMM_STAGES>();
-  dim3 grid(p.N / GEMM_BN, cdiv(p.M, GEMM_BM));
-  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * p.N * p.K);
-  gemm_tc_kernel<GEMM_BN, EPI, GEMM_STAGES><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
-  if (H) { KCHECK(H); } else if (cudaGetLastError() != cudaSuccess) return STZ_E_CUDA;
-  return 0;
-}
-
-// ---- v2: persistent, TMEM double-buffered, TMA-store epilogue (gemm2.cuh) -------------------------
+// ---- persistent, TMEM double-buffered, TMA-store epilogue (gemm2.cuh) ------------------------------
 static int g_num_sms = 148;
 
-static int g_bn_override = 0;   // tuning knob ("gemm_bn"): 0 = heuristic
 static int pick_bn(int M, int N) {
-  if (g_bn_override && N % g_bn_override == 0) return g_bn_override;
+  const int bn_override = tl_launch.gemm_bn;   // tuning knob ("gemm_bn"): 0 = heuristic
+  if (bn_override && N % bn_override == 0) return bn_override;
   int best = 0;
   long best_cost = 0;
   for (int bn : {256, 192, 128}) {
@@ -335,14 +360,17 @@ static int pick_bn(int M, int N) {
   return best;
 }
 
-static int g_gemm_cluster = 0;   // knob "gemm_cluster": 1 = CTA pairs (cta_group::2, 256 x BN tiles); measured on par with single-CTA tiles at these sizes, off by default
 
 template <int BN, int EPI>
 static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, const GemmParams& p) {
   const int tiles_m = cdiv(p.M, GEMM_BM), tiles_n = p.N / BN;
   // CTA pairs (cta_group::2, 256 x BN tiles) relieve the shared-memory bandwidth bound of the single-CTA kernel;
   // used when there is at least one full round of pair tiles
-  const bool pair = g_gemm_cluster && g2_staged<EPI>() && tiles_m >= 2 && tiles_m * tiles_n > g_num_sms;
+#ifdef STZ_EXPERIMENTS   // knob "gemm_cluster": CTA pairs (cta_group::2, 256 x BN tiles); measured on par with single-CTA tiles, not in the product build
+  const bool pair = tl_launch.gemm_cluster && g2_staged<EPI>() && tiles_m >= 2 && tiles_m * tiles_n > g_num_sms;
+#else
+  constexpr bool pair = false;
+#endif
   CUtensorMap ta, tb, tc;
   memset(&tc, 0, sizeof tc);
   if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
@@ -351,11 +379,14 @@ static int launch_gemm2_bn(stz_handle* H, cudaStream_t st, const bf16* A, int ld
   if (g2_staged<EPI>() && make_tmap_out(&tc, p.out, g2_out_bf16<EPI>(), (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 64))
     return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (output) failed (M=%d N=%d ldo=%d)", p.M, p.N, p.ldo);
   ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * p.N * p.K);
+#ifdef STZ_EXPERIMENTS
   if (pair) {
     const int units = cdiv(tiles_m, 2) * tiles_n, max_clusters = g_num_sms / 2;
     const int clusters = units < max_clusters ? units : max_clusters;
     launch_kc(2, gemm2_kernel<BN, EPI, 2>, 2 * clusters, G2_THREADS, g2_smem_bytes_cm<BN, 2>(), st, ta, tb, tc, p);
-  } else {
+  } else
+#endif
+  {
     const int tiles = tiles_m * tiles_n;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     launch_k(gemm2_kernel<BN, EPI, 1>, grid, G2_THREADS, g2_smem_bytes<BN>(), st, ta, tb, tc, p);
@@ -374,38 +405,7 @@ static int launch_gemm2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, 
   return fail(H, STZ_E_SHAPE, "gemm N=%d is not a multiple of 128", p.N);
 }
 
-// ---- fused GEMM + residual/pos + AdaLN (gemm_ln.cuh): N = d_model = 512 ------------------------------
-template <int MODE>
-static int launch_gemmln(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
-                         const GemmLnParams& p) {
-  CUtensorMap ta, tb, tu, th;
-  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
-      make_tmap(&tb, W, (uint64_t)GLN_N, (uint64_t)p.K, (uint64_t)p.K, 128) ||
-      make_tmap_out(&th, p.h, false, (uint64_t)p.M, (uint64_t)GLN_N, (uint64_t)GLN_N) ||
-      make_tmap_out(&tu, u, true, (uint64_t)p.M, (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N)))
-    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (gemmln M=%d K=%d)", p.M, p.K);
-  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * GLN_N * p.K);
-  launch_k(gemmln_kernel<MODE>, cdiv(p.M, GEMM_BM), GLN_THREADS, GLN_SMEM_BYTES, st, ta, tb, tu, th, p);
-  KCHECK(H);
-  return 0;
-}
-
-// cluster-of-two variant (gemm_ln2.cuh): two CTAs per 128-row block, 256 columns each
-template <int MODE>
-static int launch_gemmln2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
-                          const GemmLnParams& p) {
-  CUtensorMap ta, tb, tu, th;
-  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
-      make_tmap(&tb, W, (uint64_t)GLN_N, (uint64_t)p.K, (uint64_t)p.K, GLN2_BN) ||
-      make_tmap_out(&th, p.h, false, (uint64_t)p.M, (uint64_t)GLN_N, (uint64_t)GLN_N) ||
-      make_tmap_out(&tu, u, true, (uint64_t)p.M, (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N)))
-    return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (gemmln2 M=%d K=%d)", p.M, p.K);
-  ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * GLN_N * p.K);
-  launch_kc(2, gemmln2_kernel<MODE>, 2 * cdiv(p.M, GEMM_BM), GLN_THREADS, GLN2_SMEM_BYTES, st, ta, tb, tu, th, p);
-  KCHECK(H);
-  return 0;
-}
-
+// ---- fused GEMM + residual/pos + AdaLN (gemm_ln3.cuh): N = d_model = 512 ------------------------------
 // residual tile staged in the operand ring (gemm_ln3.cuh)
 template <int MODE>
 static int launch_gemmln3(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
@@ -428,8 +428,12 @@ static int launch_gemmln3(stz_handle* H, cudaStream_t st, const bf16* A, int lda
 template <int BN, int EPI>
 static cudaError_t set_gemm2_attr() {
   cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes<BN>());
+#ifdef STZ_EXPERIMENTS
   if (e != cudaSuccess || !g2_staged<EPI>()) return e;
   return cudaFuncSetAttribute(gemm2_kernel<BN, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes_cm<BN, 2>());
+#else
+  return e;
+#endif
 }
 template <int EPI>
 static cudaError_t set_gemm2_attrs() {
@@ -441,43 +445,21 @@ static cudaError_t set_gemm2_attrs() {
 
 static constexpr int dur_head2_smem(int vpl) { return (32 * 128 * vpl + 8 * 32) * 4; }
 
-template <int EPI>
-static cudaError_t set_gemm_attr() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<GEMM_BN, EPI, GEMM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              gemm_smem_bytes<GEMM_BN, GEMM_STAGES>());
-}
 // Per-device opt-in to > 48 KB dynamic shared memory; done once per handle, never during graph capture.
 static cudaError_t init_kernel_attrs() {
   cudaError_t e;
-  if ((e = set_gemm_attr<EPI_F32>()) != cudaSuccess) return e;
-  if ((e = set_gemm_attr<EPI_F32_POS>()) != cudaSuccess) return e;
-  if ((e = set_gemm_attr<EPI_BF16>()) != cudaSuccess) return e;
-  if ((e = set_gemm_attr<EPI_GELU_BF16>()) != cudaSuccess) return e;
-  if ((e = set_gemm_attr<EPI_GATE_RES>()) != cudaSuccess) return e;
-  if ((e = set_gemm_attr<EPI_SAMPLER>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_F32>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_F32_POS>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_BF16>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_GELU_BF16>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_GATE_RES>()) != cudaSuccess) return e;
   if ((e = set_gemm2_attrs<EPI_SAMPLER>()) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemmln_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln3_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN3_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemmln3_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN3_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemmln2_kernel<GLN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN2_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemmln2_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN2_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<4>())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<8>())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<10>())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_cluster_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_cluster_smem<16>())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(style_pool_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (2 * 256 + 1) + 4) * 4)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(1))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(2))) != cudaSuccess) return e;
@@ -502,7 +484,6 @@ static int gemm(stz_handle* H, cudaStream_t st, int impl, const bf16* A, int lda
   if (p.N % GEMM_BN != 0 || p.K % GEMM_BK != 0 || p.M <= 0)
     return fail(H, STZ_E_SHAPE, "gemm shape M=%d N=%d K=%d unsupported (N %% 128, K %% 64)", p.M, p.N, p.K);
   if (impl == 0) return launch_gemm2<EPI>(H, st, A, lda, a_rows, W, p);
-  if (impl == 2) return launch_gemm_tc<EPI>(H, st, A, lda, a_rows, W, p);
   return launch_gemm_simt<EPI>(H, st, A, lda, W, p);
 }
 
@@ -565,9 +546,8 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   Workspace& w = H->ws;
   const size_t mod_rows_req = (size_t)(hoist_mod(H->cfg, B, E) ? E : 1) * 2 * B;
   if (w.base && B <= w.B && T <= w.T && P <= w.P && E <= w.E && noise_slices <= w.noise_slices && mod_rows_req <= w.mod_rows) return 0;
-  // grow monotonically; all cached graphs point into the old arena
-  for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
-  H->graphs.clear();
+  // grow monotonically; all cached graphs point into the old arena (stz_reserve sizes it once, up front)
+  drop_graphs(H);
   if (w.base) { CK(H, cudaDeviceSynchronize()); CK(H, cudaFree(w.base)); w.base = nullptr; }
   B = B > w.B ? B : w.B; T = T > w.T ? T : w.T; P = P > w.P ? P : w.P; E = E > w.E ? E : w.E;
   noise_slices = noise_slices > w.noise_slices ? noise_slices : w.noise_slices;
@@ -736,7 +716,7 @@ extern "C" void stz_destroy(stz_handle* H) {
   if (!H) return;
   cudaSetDevice(H->device);
   cudaDeviceSynchronize();
-  for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
+  drop_graphs(H);
   cudaFree(H->ws.base); cudaFree(H->w32); cudaFree(H->wbf); cudaFree(H->ctx_text_b); cudaFree(H->ctx_prompt_b);
   cudaFree(H->wq3); cudaFree(H->wkv3); cudaFree(H->wo3); cudaFree(H->wih3); cudaFree(H->wada3); cudaFree(H->b_kv);
   cudaFree(H->wkv_all); cudaFree(H->bkv_all);
@@ -832,7 +812,6 @@ static int create_impl(stz_handle* H, const float* weights_host) {
                                                      H->lstm_b + ((size_t)l * 2 + dr) * 4 * h, 4 * h, 4 * h);
       KCHECK(H);
     }
-  { const int mc = stz_debug_max_lstm_clusters(); if (mc > 0) H->lstm_max_clusters = mc; }
   {  // split-bf16 predictor weights
     const size_t ds = c.d_sty_tok, dh = c.d_hid, Ds = c.d_style, kin = dh + ds;
     H->pred_tc = ds % 128 == 0 && dh % 128 == 0 && kin % 64 == 0 && c.d_text % 64 == 0 && Ds % 64 == 0;
@@ -877,7 +856,7 @@ extern "C" int stz_create(const stz_config* cfg, const float* weights_host, size
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
     return fail(nullptr, STZ_E_DEVICE, "CUDA device %d not available (count %d): no CPU fallback", device, ndev);
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10 || prop.minor != 0)
     return fail(nullptr, STZ_E_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, STZ_E_DEVICE, "cudaSetDevice(%d) failed", device);
   if (load_encode()) return fail(nullptr, STZ_E_DEVICE, "cuTensorMapEncodeTiled entry point not found");
@@ -891,6 +870,7 @@ extern "C" int stz_create(const stz_config* cfg, const float* weights_host, size
     delete H;
     return STZ_E_ARG;
   }
+  LaunchScope ls(H);
   int rc = create_impl(H, weights_host);
   if (rc != 0) {
     g_create_error = H->err;
@@ -904,30 +884,47 @@ extern "C" int stz_create(const stz_config* cfg, const float* weights_host, size
 
 extern "C" int64_t stz_launch_count(const stz_handle* h) { return h ? h->launches : 0; }
 
+extern "C" int stz_graph_count(const stz_handle* h, int64_t* captures_total) {
+  if (!h) return STZ_E_ARG;
+  if (captures_total) *captures_total = h->graph_captures;
+  return (int)h->graphs.size();
+}
+
+// Sizes the workspace arena for the largest call the caller will make, so that no later call reallocates it (a
+// reallocation synchronises the device and invalidates every captured graph).
+extern "C" int stz_reserve(stz_handle* H, int max_B, int max_T, int max_P, int max_steps, int sampler_kind) {
+  if (!H) return STZ_E_ARG;
+  if (max_B < 1 || max_T < 1 || max_P < 1 || max_steps < 1 || max_steps > 1024) return fail(H, STZ_E_ARG, "bad sizes");
+  if (sampler_kind != STZ_SAMPLER_STUDENT && sampler_kind != STZ_SAMPLER_TEACHER) return fail(H, STZ_E_ARG, "bad sampler kind %d", sampler_kind);
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  const int E = sampler_kind == STZ_SAMPLER_TEACHER ? 2 * max_steps : max_steps;
+  const int slices = sampler_kind == STZ_SAMPLER_TEACHER ? max_steps + 1 : 1;
+  for (auto& sl : H->slot) if (sl.busy) return fail(H, STZ_E_ARG, "stz_reserve with a host call in flight");
+  return ensure_workspace(H, max_B, H->t_buckets ? bucket_T(max_T) : max_T, max_P, E, slices);
+}
+
 extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
   if (!H || !key) return STZ_E_ARG;
   if (!strcmp(key, "use_graph")) H->use_graph = value;
   else if (!strcmp(key, "gemm_impl")) {
-    if (H->gemm_impl != value) {
-      for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
-      H->graphs.clear();
-    }
+    if (H->gemm_impl != value) drop_graphs(H);
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
-  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") || !strcmp(key, "attn_tc3")) {
-    for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
-    H->graphs.clear();
+  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
+           !strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // baked into captured graphs
+    drop_graphs(H);
     if (!strcmp(key, "chains")) H->chains = value;
-    else if (!strcmp(key, "attn_tc3")) H->attn_tc3 = value;
-    else if (!strcmp(key, "ablate")) H->ablate = value; else if (!strcmp(key, "attn_impl")) H->attn_impl = value; else H->fuse_ln = value;
-  }
-  else if (!strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // process-wide knobs baked into captured graphs
-    for (auto& g : H->graphs) cudaGraphExecDestroy(g.second.first);
-    H->graphs.clear();
-    if (!strcmp(key, "gemm_bn")) g_bn_override = value;
-    else if (!strcmp(key, "use_pdl")) g_use_pdl = value;
-    else g_gemm_cluster = value;
+    else if (!strcmp(key, "ablate")) H->ablate = value;
+    else if (!strcmp(key, "attn_impl")) H->attn_impl = value;
+    else if (!strcmp(key, "gemm_bn")) H->gemm_bn = value;
+    else if (!strcmp(key, "use_pdl")) H->use_pdl = value;
+    else if (!strcmp(key, "gemm_cluster")) H->gemm_cluster = value;
+    else H->fuse_ln = value;
+  } else if (!strcmp(key, "t_buckets")) H->t_buckets = value;
+  else if (!strcmp(key, "max_graphs")) {
+    if (value < 1) return fail(H, STZ_E_ARG, "max_graphs must be >= 1");
+    H->max_graphs = value;
   } else if (!strcmp(key, "profile")) {
     H->profile = value;
     for (auto& r : H->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -936,17 +933,37 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
   return 0;
 }
 
-// Max co-resident clusters of the BiLSTM recurrence kernel on the current device (diagnostic).
+extern "C" int stz_get_option(const stz_handle* H, const char* key, int* value) {
+  if (!H || !key || !value) return STZ_E_ARG;
+  if (!strcmp(key, "use_graph")) *value = H->use_graph;
+  else if (!strcmp(key, "t_buckets")) *value = H->t_buckets;
+  else if (!strcmp(key, "max_graphs")) *value = H->max_graphs;
+  else if (!strcmp(key, "use_pdl")) *value = H->use_pdl;
+  else if (!strcmp(key, "gemm_impl")) *value = H->gemm_impl;
+  else if (!strcmp(key, "gemm_bn")) *value = H->gemm_bn;
+  else if (!strcmp(key, "fuse_ln")) *value = H->fuse_ln;
+  else if (!strcmp(key, "attn_impl")) *value = H->attn_impl;
+  else if (!strcmp(key, "chains")) *value = H->chains;
+  else if (!strcmp(key, "lstm_impl")) *value = H->lstm_impl;
+  else if (!strcmp(key, "pred_gemm_impl")) *value = H->pred_gemm_impl;
+  else if (!strcmp(key, "profile")) *value = H->profile;
+  else if (!strcmp(key, "last_fuse_mode")) *value = H->last_fuse_mode;
+  else if (!strcmp(key, "last_T")) *value = H->last_T;
+  else return STZ_E_ARG;
+  return 0;
+}
+
+// Max co-resident 8-CTA clusters of the BiLSTM recurrence kernel on the current device (diagnostic).
 extern "C" int stz_debug_max_lstm_clusters(void) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(LC_CS * 64, 2); cfg.blockDim = dim3(LC_THREADS); cfg.dynamicSmemBytes = lstm_cluster_smem<16>();
+  cfg.gridDim = dim3(LC_CS * 64, 2); cfg.blockDim = dim3(LT_THREADS); cfg.dynamicSmemBytes = LT_SMEM_BYTES;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = LC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = -1;
   if (init_kernel_attrs() != cudaSuccess) return -2;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel<8, 2>, &cfg) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel, &cfg) != cudaSuccess) return -1;
   return n;
 }
 
@@ -975,12 +992,14 @@ extern "C" int stz_debug_set_gemm_trace(stz_handle* H, long long* trace_dev) {
   return 0;
 }
 
+#ifdef STZ_TRACE   // experiment flags of the timeline build only (tools/gemm_trace.py); not part of include/stz.h
 extern "C" int stz_debug_set_gemm_dbg(stz_handle* H, int flags) {
   if (!H) return STZ_E_ARG;
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   CK(H, cudaMemcpyToSymbol(g_gemm_dbg, &flags, sizeof flags));
   return 0;
 }
+#endif
 
 extern "C" int stz_debug_set_lstm_trace(stz_handle* H, long long* trace_dev) {
   if (!H) return STZ_E_ARG;
@@ -1059,10 +1078,7 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
       tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
     }
     const int units = tp_.n_units;
-    if (H->attn_tc3)
-      launch_k(attention_tc3_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, ATC3_THREADS, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
-    else
-      launch_k(attention_tc2_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
+    launch_k(attention_tc2_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
   } else if (H->attn_impl == 0 && cross3 && ap.n_q <= 128 && n_style <= 64 && P8 + 1 <= 128) {
     // long text: streaming tcgen05 attention over 128-key blocks (attention_tcs_kernel)
     CUtensorMap tq, tt, tp, tn;
@@ -1089,12 +1105,6 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
     tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
     const int units = tp_.n_units;
     launch_k(attention_tcs_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATS_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
-  } else if (n_keys <= 128 && ap.n_q <= 128 && H->attn_impl == 3) {   // tcgen05 with cp.async staging (superseded by tc2)
-    const int units = B * H->cfg.n_heads;
-    launch_k(attention_tc_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 128, ATC_SMEM_BYTES, st, ap, H->cfg.n_heads, units);
-  } else if (n_keys <= ATT3_ROWS && ap.n_q <= ATT3_ROWS && H->attn_impl == 1) {   // whole key sequence resident: persistent, prefetching kernel
-    const int units = B * H->cfg.n_heads;
-    launch_k(attention3_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATT3_SMEM_BYTES, st, ap, H->cfg.n_heads, units);
   } else {
     launch_k(attention_kernel, grid, 2 * cdiv(ap.n_q / 2, 16) * 32, ATT_SMEM_BYTES, st, ap);   // ceil(K / 16) warps per CFG branch
   }
@@ -1135,9 +1145,10 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   }
   // GEMM + residual + AdaLN in one kernel.  Product: gemmln3_kernel (fuse_ln = 3) whenever its shape constraints hold
   // (d_model 512, every contraction length a multiple of 256, a 128-row tile spanning <= 8 sequences); otherwise, and for
-  // fuse_ln = 0, the GEMM + ln_mod_kernel pair.  1 / 2 select the earlier fused kernels (A/B only).
+  // fuse_ln = 0, the GEMM + ln_mod_kernel pair.
   int fuse_mode = (impl == 0 && d == GLN_N) ? H->fuse_ln : 0;
-  if ((fuse_mode == 3 || fuse_mode == 4) && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || 2 * ((GEMM_BM - 1 + 2 * K - 1) / (2 * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
+  if (fuse_mode != 3 && fuse_mode != 4) fuse_mode = 0;
+  if (fuse_mode != 0 && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || 2 * ((GEMM_BM - 1 + 2 * K - 1) / (2 * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
   // below ~36 row tiles (B < ~46 at K = 50) the separate LayerNorm kernel is cheap and the fused kernel's long serial
   // epilogue loses (measured: -2 .. -4 % at B = 16 / 32); from 36 to ~140 tiles (one to 1.9 waves of CTA pairs) it wins
   // 1 .. 7 % (B = 48 .. 160); from there to ~350 tiles (two to four waves) its one-tile-per-CTA-pair grid quantises worse
@@ -1149,6 +1160,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   }
   if (fuse_mode == 4) fuse_mode = 3;
   const bool fused = fuse_mode != 0;
+  H->last_fuse_mode = fuse_mode;
   GemmLnParams lb{};
   lb.M = R; lb.h = h; lb.mod = mod; lb.n_mod = n_mod; lb.rows_per_utt = 2 * K; lb.pos = W32(H, "pos"); lb.n_style = K;
   // residual GEMM of a sub-layer followed by the AdaLN of the next one: (gate, shift, scale) offsets into mod
@@ -1156,9 +1168,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = Kc; p.bias = bias; p.gate_off = gate_off; p.shift_off = ln_off; p.scale_off = ln_off + d; p.split3 = last ? 1 : 0;
-      if (fuse_mode == 3) return launch_gemmln3<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
-      if (fuse_mode == 2) return launch_gemmln2<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
-      return launch_gemmln<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
+      return launch_gemmln3<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
     }
     GemmParams p = base;
     p.M = R; p.N = d; p.K = Kc; p.bias = bias; p.out = h; p.ldo = d; p.gate_off = gate_off;
@@ -1170,9 +1180,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.shift_off = 0; p.scale_off = d; p.split3 = 0;
-      if (fuse_mode == 3) RET(launch_gemmln3<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
-      else if (fuse_mode == 2) RET(launch_gemmln2<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
-      else RET(launch_gemmln<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
+      RET(launch_gemmln3<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
     } else {
       GemmParams p = base;
       p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = h; p.ldo = d; p.pos = W32(H, "pos");
@@ -1248,9 +1256,18 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   if (kind != STZ_SAMPLER_STUDENT && kind != STZ_SAMPLER_TEACHER) return fail(H, STZ_E_ARG, "bad sampler kind %d", kind);
   const int E = kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
   const int slices = kind == STZ_SAMPLER_TEACHER ? steps + 1 : 1;
+  const bool graphed = runs_graphed(H);
+  // length bucket: the call runs with T = bucket and a key-padding mask over the extra positions
+  const int T_src = T;
+  T = effective_T(H, T);
   RET(ensure_workspace(H, B, T, P, E, slices));
   RET(order_after_previous_call(H, st));
   Workspace& w = H->ws;
+  H->last_T = T;
+  if (T != T_src) {
+    launch_k(pad_mask_kernel, ew_grid((size_t)B * T), 256, 0, st, tmask, w.st_tmask, B, T_src, T); KCHECK(H);
+    tmask = w.st_tmask;
+  }
   const int d = c.d_model, L = c.n_layers, K = c.n_style, Ds = c.d_style;
   const int NS = 2 * B, impl = H->gemm_impl;
   const size_t BK = (size_t)B * K;
@@ -1266,7 +1283,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   w.ctx_prompt = w.ctx_text + (size_t)B * T * d;
   w.kv_prompt = w.kv_text + (size_t)B * T * L * 2 * d;
   const int rows_all = B * (T + P);
-  launch_k(cast_pool_kernel, dim3(B, c.d_text / 128), 256, 0, st, text, tmask, w.text_bf, w.pool_text, T, c.d_text); KCHECK(H);
+  launch_k(cast_pool_kernel, dim3(B, c.d_text / 128), 256, 0, st, text, tmask, w.text_bf, w.pool_text, T, c.d_text, T_src); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_text, c.d_text, c.d_text, nullptr, 0, 0, W32(H, "ptext.w"), W32(H, "ptext.b"), w.pt, d, B, d));
   RET(linear_f32(H, st, ACT_SILU, w.tfeat, c.d_time, c.d_time, nullptr, 0, 0, W32(H, "time.w1"), W32(H, "time.b1"), w.t1, d, E, d));
   RET(linear_f32(H, st, ACT_NONE, w.t1, d, d, nullptr, 0, 0, W32(H, "time.w2"), W32(H, "time.b2"), w.temb, d, E, d));
@@ -1274,7 +1291,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   // tiles that are padding throughout are skipped by the context GEMMs — the attention never visits those key blocks.
   const uint8_t* ctx_needed = nullptr;
   if (tmask != nullptr && impl == 0 && T % 128 == 0 && T > 128) {
-    launch_k(tile_needed_kernel, cdiv(cdiv(B * T, 128), 8), 256, 0, st, tmask, w.tile_needed_ctx, B * T); KCHECK(H);
+    launch_k(tile_needed_kernel, cdiv(cdiv(B * T, 128), 8), 256, 0, st, tmask, w.tile_needed_ctx, B * T, T / 128); KCHECK(H);
     CK(H, cudaMemsetAsync(w.tile_needed_ctx + B * T / 128, 1, cdiv(B * P, 128) + 1, st));
     ctx_needed = w.tile_needed_ctx;
   }
@@ -1284,7 +1301,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     RET(gemm<EPI_F32>(H, st, impl, w.text_bf, c.d_text, B * T, WBF(H, "ctx_text.w"), p));
   }
   if (H->wait_prompt) { CK(H, cudaStreamWaitEvent(st, H->cur_ev_prompt, 0)); H->wait_prompt = false; }
-  launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt); KCHECK(H);
+  launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt, P); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
   launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
   w.mod_hoisted = hoist_mod(c, B, E) && !(H->ablate & 256);
@@ -1333,23 +1350,20 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     // loop read the call's constants (context K/V, modulations) before their griddepcontrol.wait (attention_tc2_kernel's
     // early K/V boxes); this launch guarantees the conditioning prep has completed before any of them can start, also
     // for tiny grids where a whole chain of waiting kernels is co-resident.
-    const int pdl_saved = g_use_pdl;
-    g_use_pdl = 0;
-    launch_k(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0);
-    g_use_pdl = pdl_saved;
+    launch_k_nopdl(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0);
     KCHECK(H);
   }
   H->launches += H->cur_launches;
   H->cur_launches = 0;
 
   // ---- the evaluation loop: one CUDA graph per (B, T, P, E, kind) ----------------------------
-  const bool tapping = H->tap_buf != nullptr;
-  if (H->use_graph && !tapping && !H->profile) {
+  if (graphed) {
     auto key = std::make_tuple(B, T, P, E, kind * 2 + (tmask ? 1 : 0) + (pmask ? 4 : 0));
     auto it = H->graphs.find(key);
     // the graph bakes in the mask pointers: masks are copied into library-owned staging first
     const uint8_t* tm = nullptr; const uint8_t* pm = nullptr;
-    if (tmask) { CK(H, cudaMemcpyAsync(w.st_tmask, tmask, (size_t)B * T, cudaMemcpyDeviceToDevice, st)); tm = w.st_tmask; }
+    if (tmask == w.st_tmask) tm = w.st_tmask;   // the bucket mask was built there
+    else if (tmask) { CK(H, cudaMemcpyAsync(w.st_tmask, tmask, (size_t)B * T, cudaMemcpyDeviceToDevice, st)); tm = w.st_tmask; }
     if (pmask) { CK(H, cudaMemcpyAsync(w.st_pmask, pmask, (size_t)B * P, cudaMemcpyDeviceToDevice, st)); pm = w.st_pmask; }
     if (it == H->graphs.end()) {
       cudaGraph_t graph = nullptr;
@@ -1381,11 +1395,21 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
       ce = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) return fail(H, STZ_E_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce));
-      it = H->graphs.emplace(key, std::make_pair(exec, H->cur_launches)).first;
+      if ((int)H->graphs.size() >= H->max_graphs) {   // evict the least recently used graph (its last launch may still run)
+        auto victim = H->graphs.begin();
+        for (auto jt = H->graphs.begin(); jt != H->graphs.end(); ++jt)
+          if (jt->second.last_use < victim->second.last_use) victim = jt;
+        CK(H, cudaStreamSynchronize(st));
+        cudaGraphExecDestroy(victim->second.exec);
+        H->graphs.erase(victim);
+      }
+      it = H->graphs.emplace(key, stz_handle::GraphEntry{exec, H->cur_launches, 0}).first;
+      ++H->graph_captures;
       H->cur_launches = 0;
     }
-    CK(H, cudaGraphLaunch(it->second.first, st));
-    H->launches += it->second.second;
+    it->second.last_use = ++H->graph_clock;
+    CK(H, cudaGraphLaunch(it->second.exec, st));
+    H->launches += it->second.launches;
   } else {
     for (int e = 0; e < E; ++e) RET(run_eval(H, st, e, B, 0, B, T, P, tmask, pmask));
     H->launches += H->cur_launches;
@@ -1401,6 +1425,7 @@ extern "C" int stz_sample_style(stz_handle* H, const float* text_emb_dev, const 
                                 void* cuda_stream) {
   if (!H) return STZ_E_ARG;
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  LaunchScope ls(H);
   return sample_style_impl(H, text_emb_dev, text_mask_dev, prompt_feats_dev, prompt_mask_dev, noise_dev, B, T, P, steps,
                            cfg_scale, sampler_kind, out_style_dev, (cudaStream_t)cuda_stream);
 }
@@ -1432,7 +1457,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
   // nothing: the recurrence, AdaLN and the duration head all honour the mask)
   const uint8_t* needed = nullptr;
   if (tmask != nullptr && tc && impl == 0) {
-    launch_k(tile_needed_kernel, cdiv(cdiv(BT, 128), 8), 256, 0, st, tmask, w.tile_needed, BT); KCHECK(H);
+    launch_k(tile_needed_kernel, cdiv(cdiv(BT, 128), 8), 256, 0, st, tmask, w.tile_needed, BT, 0); KCHECK(H);
     needed = w.tile_needed;
   }
   auto gemm3 = [&](const bf16* A, int K3, int rows, const bf16* W3, const float* bias, float* out, int N, bool token_rows = true) -> int {
@@ -1490,23 +1515,6 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
       if (h == LC_H && H->lstm_impl == 0) {  // product path: recurrent product on tcgen05 (split-bf16), cluster of 8 CTAs, DSMEM exchange
         const float* whh = H->whh + (size_t)l * 2 * 4 * h * h;
         launch_k(lstm_tc_kernel, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, w.G, whh, w.lens, w.perm, xo, B, T);
-      } else if (h == LC_H && H->lstm_impl == 2) {  // fp32 FFMA form: register-resident W_hh, cluster of 8 CTAs, DSMEM exchange
-        // sequences per cluster: fewest waves of co-resident clusters, then least work per step
-        int best = 8;
-        double best_cost = 1e30;
-        for (int nb : {4, 8, 10, 16}) {
-          const int clusters = 2 * cdiv(B, nb);
-          const double cost = (double)cdiv(clusters, H->lstm_max_clusters) * (1800.0 + 440.0 * nb);
-          if (cost < best_cost) { best_cost = cost; best = nb; }
-        }
-        const float* whh = H->whh + (size_t)l * 2 * 4 * h * h;
-        const dim3 grid(cdiv(B, best) * LC_CS, 2);
-        switch (best) {
-          case 4: launch_k(lstm_cluster_kernel<4, 1>, grid, LC_THREADS, lstm_cluster_smem<4>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
-          case 8: launch_k(lstm_cluster_kernel<8, 1>, grid, LC_THREADS, lstm_cluster_smem<8>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
-          case 10: launch_k(lstm_cluster_kernel<5, 2>, grid, LC_THREADS, lstm_cluster_smem<10>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
-          default: launch_k(lstm_cluster_kernel<8, 2>, grid, LC_THREADS, lstm_cluster_smem<16>(), st, w.G, whh, w.lens, w.perm, xo, B, T); break;
-        }
       } else {
         lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
       }
@@ -1553,6 +1561,7 @@ extern "C" int stz_predict_duration(stz_handle* H, const float* text_emb_dev, co
                                     void* cuda_stream) {
   if (!H) return STZ_E_ARG;
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  LaunchScope ls(H);
   return predict_duration_impl(H, text_emb_dev, text_mask_dev, style_dev, B, T, out_dur_dev, out_presum_dev,
                                (cudaStream_t)cuda_stream);
 }
@@ -1569,6 +1578,7 @@ extern "C" int stz_regulate_length(stz_handle* H, const float* feats_dev, const 
   if (T > LR_MAX_T || C < 4 || C % 4) return fail(H, STZ_E_SHAPE, "length regulator supports T <= %d, C %% 4 == 0", LR_MAX_T);
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  LaunchScope ls(H);
   H->cur_launches = 0;
   launch_k(length_regulate_kernel, dim3(cdiv(F_max, LR_FRAMES), B), LR_THREADS, 0, st, feats_dev, dur_dev, out_frames_dev,
            out_frame_lens_dev, out_frame_tok_dev, T, C, F_max);
@@ -1638,16 +1648,17 @@ extern "C" int stz_synthesize_host_submit(stz_handle* H, int slot, const float* 
   if (B < 1 || T < 1 || P < 1 || steps < 1) return fail(H, STZ_E_ARG, "bad sizes");
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   const stz_config& c = H->cfg;
+  LaunchScope ls(H);
   const int E = sampler_kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
   const int slices = sampler_kind == STZ_SAMPLER_TEACHER ? steps + 1 : 1;
   RET(host_wait_slot(H, slot));                       // resubmitting a slot first retires its previous call
   {
     const Workspace& w0 = H->ws;
     const size_t mod_rows_req = (size_t)(hoist_mod(c, B, E) ? E : 1) * 2 * B;
-    const bool grows = !w0.base || B > w0.B || T > w0.T || P > w0.P || E > w0.E || slices > w0.noise_slices || mod_rows_req > w0.mod_rows;
+    const bool grows = !w0.base || B > w0.B || effective_T(H, T) > w0.T || P > w0.P || E > w0.E || slices > w0.noise_slices || mod_rows_req > w0.mod_rows;
     if (grows) RET(host_wait_slot(H, slot ^ 1));      // the arena is reallocated: nothing may be in flight
   }
-  RET(ensure_workspace(H, B, T, P, E, slices));
+  RET(ensure_workspace(H, B, effective_T(H, T), P, E, slices));
   Workspace& w = H->ws;
   Workspace::HostStage& hs = w.hs[slot];
   stz_handle::HostSlot& sl = H->slot[slot];
@@ -1716,12 +1727,12 @@ extern "C" int stz_op_gemm_bf16(const void* A, const void* W, const float* bias,
   if (load_encode()) return fail(nullptr, STZ_E_DEVICE, "cuTensorMapEncodeTiled entry point not found");
   if (N % GEMM_BN || K % GEMM_BK || M < 1) return fail(nullptr, STZ_E_SHAPE, "N %% 128, K %% 64 required");
   if (init_kernel_attrs() != cudaSuccess) return fail(nullptr, STZ_E_CUDA, "cudaFuncSetAttribute failed");
+  LaunchScope ls(nullptr);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = C; p.ldo = N;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int rc = impl == 0   ? launch_gemm2<EPI_F32>(nullptr, st, (const bf16*)A, K, M, (const bf16*)W, p)
-           : impl == 2 ? launch_gemm_tc<EPI_F32>(nullptr, st, (const bf16*)A, K, M, (const bf16*)W, p)
-                       : launch_gemm_simt<EPI_F32>(nullptr, st, (const bf16*)A, K, (const bf16*)W, p);
+  int rc = impl == 0 ? launch_gemm2<EPI_F32>(nullptr, st, (const bf16*)A, K, M, (const bf16*)W, p)
+                     : launch_gemm_simt<EPI_F32>(nullptr, st, (const bf16*)A, K, (const bf16*)W, p);
   if (rc != 0 && g_create_error.empty()) g_create_error = "gemm launch failed";
   return rc;
 }
@@ -1736,6 +1747,7 @@ extern "C" int stz_op_attention(stz_handle* H, const void* qkv, int ldq, const v
   if (!H || !qkv || !out || B < 1) return STZ_E_ARG;
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   const stz_config& c = H->cfg;
+  LaunchScope ls(H);
   const int d = c.d_model, K = c.n_style;
   const bf16* q = (const bf16*)qkv;
   AttnParams ap{};
@@ -1770,6 +1782,7 @@ extern "C" int stz_bench_gemm(stz_handle* H, int M, int N, int K, int epi, int i
   if (N % 128 || K % 64) return fail(H, STZ_E_SHAPE, "N %% 128, K %% 64 required");
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   cudaStream_t st = H->stream;
+  LaunchScope ls(H);
   bf16 *A = nullptr, *W = nullptr, *Cb = nullptr;
   float *Cf = nullptr, *bias = nullptr, *mod = nullptr;
   const int rpu = 2 * H->cfg.n_style, n_seq = 2 * cdiv(M, rpu) + 2;
@@ -1779,11 +1792,14 @@ extern "C" int stz_bench_gemm(stz_handle* H, int M, int N, int K, int epi, int i
   CK(H, cudaMalloc(&Cf, (size_t)M * N * sizeof(float)));
   CK(H, cudaMalloc(&bias, (size_t)N * sizeof(float)));
   CK(H, cudaMalloc(&mod, (size_t)n_seq * 3 * N * sizeof(float)));
-  CK(H, cudaMemsetAsync(A, 0, (size_t)(M + 128) * K * sizeof(bf16), st));
-  CK(H, cudaMemsetAsync(W, 0, (size_t)N * K * sizeof(bf16), st));
-  CK(H, cudaMemsetAsync(Cf, 0, (size_t)M * N * sizeof(float), st));
-  CK(H, cudaMemsetAsync(bias, 0, (size_t)N * sizeof(float), st));
-  CK(H, cudaMemsetAsync(mod, 0, (size_t)n_seq * 3 * N * sizeof(float), st));
+  // random operands (a zero-filled problem flatters the tensor pipe: no operand toggling, lower power); the gate of the
+  // residual forms is kept small so that hundreds of accumulating launches stay finite
+  fill_random_bf16_kernel<<<ew_grid((size_t)(M + 128) * K), 256, 0, st>>>(A, (size_t)(M + 128) * K, 1.0f, 1u);
+  fill_random_bf16_kernel<<<ew_grid((size_t)N * K), 256, 0, st>>>(W, (size_t)N * K, 1.0f / sqrtf((float)K), 2u);
+  fill_random_f32_kernel<<<ew_grid((size_t)M * N), 256, 0, st>>>(Cf, (size_t)M * N, 1.0f, 3u);
+  fill_random_f32_kernel<<<ew_grid((size_t)N), 256, 0, st>>>(bias, (size_t)N, 0.1f, 4u);
+  fill_random_f32_kernel<<<ew_grid((size_t)n_seq * 3 * N), 256, 0, st>>>(mod, (size_t)n_seq * 3 * N, 1e-3f, 5u);
+  CK(H, cudaGetLastError());
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.ldo = N; p.mod = mod; p.n_mod = N; p.gate_off = 0; p.rows_per_utt = rpu;
   p.n_style = H->cfg.n_style;
@@ -1822,4 +1838,69 @@ extern "C" int stz_bench_gemm(stz_handle* H, int M, int N, int K, int epi, int i
   if (ce != cudaSuccess) return fail(H, STZ_E_CUDA, "bench gemm -> %s", cudaGetErrorString(ce));
   *avg_us = (double)ms * 1e3 / iters;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// unit-test entry points for the fused epilogues of the product GEMM kernels (tests/test_gpu_kernels.py compare each
+// with a plain PyTorch fp32 restatement of the same op)
+// ------------------------------------------------------------------------------------------
+extern "C" int stz_op_gemm_epi(stz_handle* H, const void* A, const void* W, const float* bias, int M, int N, int K, int epi,
+                               void* out, const float* mod, int n_mod, int gate_off, const float* pos, void* cuda_stream) {
+  if (!H || !A || !W || !out) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  LaunchScope ls(H);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = N; p.mod = mod; p.n_mod = n_mod; p.gate_off = gate_off;
+  p.rows_per_utt = 2 * H->cfg.n_style; p.n_style = H->cfg.n_style; p.pos = pos;
+  int rc;
+  switch (epi) {
+    case EPI_F32: rc = gemm<EPI_F32>(H, st, 0, (const bf16*)A, K, M, (const bf16*)W, p); break;
+    case EPI_F32_POS:
+      if (!pos) return fail(H, STZ_E_ARG, "EPI_F32_POS needs pos");
+      rc = gemm<EPI_F32_POS>(H, st, 0, (const bf16*)A, K, M, (const bf16*)W, p); break;
+    case EPI_BF16: rc = gemm<EPI_BF16>(H, st, 0, (const bf16*)A, K, M, (const bf16*)W, p); break;
+    case EPI_GELU_BF16: rc = gemm<EPI_GELU_BF16>(H, st, 0, (const bf16*)A, K, M, (const bf16*)W, p); break;
+    case EPI_GATE_RES:
+      if (!mod) return fail(H, STZ_E_ARG, "EPI_GATE_RES needs mod");
+      rc = gemm<EPI_GATE_RES>(H, st, 0, (const bf16*)A, K, M, (const bf16*)W, p); break;
+    default: return fail(H, STZ_E_ARG, "epi %d is not a plain epilogue (see stz_op_gemm_sampler / stz_op_gemm_ln)", epi);
+  }
+  H->cur_launches = 0;
+  return rc;
+}
+
+extern "C" int stz_op_gemm_sampler(stz_handle* H, const void* A, const void* W, const float* bias, int M, int N, int K,
+                                   float* x, float* xmid, const float* noise, const float* coef_dev, void* xin_out,
+                                   float* tap, void* cuda_stream) {
+  if (!H || !A || !W || !x || !xmid || !noise || !coef_dev || !xin_out) return STZ_E_ARG;
+  if (M % 2) return fail(H, STZ_E_SHAPE, "the sampler epilogue pairs rows: M must be even");
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  LaunchScope ls(H);
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.ldo = N; p.rows_per_utt = 2 * H->cfg.n_style; p.n_style = H->cfg.n_style;
+  p.x = x; p.xmid = xmid; p.noise = noise; p.coef = coef_dev; p.xin = (bf16*)xin_out; p.tap = tap;
+  const int rc = gemm<EPI_SAMPLER>(H, (cudaStream_t)cuda_stream, 0, (const bf16*)A, K, M, (const bf16*)W, p);
+  H->cur_launches = 0;
+  return rc;
+}
+
+extern "C" int stz_op_gemm_ln(stz_handle* H, const void* A, const void* W, const float* bias, int M, int K, int mode,
+                              float* h, const float* mod, int n_mod, int gate_off, int shift_off, int scale_off,
+                              const float* pos, int split3, void* u_out, void* cuda_stream) {
+  if (!H || !A || !W || !bias || !h || !mod || !u_out) return STZ_E_ARG;
+  if (H->cfg.d_model != GLN_N) return fail(H, STZ_E_SHAPE, "the fused GEMM + AdaLN kernel needs d_model = %d", GLN_N);
+  if (mode == GLN_POS && !pos) return fail(H, STZ_E_ARG, "GLN_POS needs pos");
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  LaunchScope ls(H);
+  GemmLnParams p{};
+  p.M = M; p.K = K; p.bias = bias; p.h = h; p.mod = mod; p.n_mod = n_mod; p.gate_off = gate_off; p.shift_off = shift_off;
+  p.scale_off = scale_off; p.rows_per_utt = 2 * H->cfg.n_style; p.pos = pos; p.n_style = H->cfg.n_style; p.split3 = split3 ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc;
+  if (mode == GLN_RES) rc = launch_gemmln3<GLN_RES>(H, st, (const bf16*)A, K, M, (const bf16*)W, (bf16*)u_out, p);
+  else if (mode == GLN_POS) rc = launch_gemmln3<GLN_POS>(H, st, (const bf16*)A, K, M, (const bf16*)W, (bf16*)u_out, p);
+  else return fail(H, STZ_E_ARG, "mode must be 0 (residual) or 1 (positional)");
+  H->cur_launches = 0;
+  return rc;
 }

@@ -86,6 +86,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_launch_count.argtypes = [vp]
     lib.stz_set_option.restype = i32
     lib.stz_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.stz_get_option.restype = i32
+    lib.stz_get_option.argtypes = [vp, C.c_char_p, C.POINTER(i32)]
     lib.stz_profile_read.restype = i32
     lib.stz_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     lib.stz_bench_gemm.restype = i32
@@ -104,6 +106,16 @@ def load_library(path: Optional[str] = None):
     lib.stz_op_attention.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]
     lib.stz_op_gemm_bf16.restype = i32
     lib.stz_op_gemm_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.stz_op_gemm_epi.restype = i32
+    lib.stz_op_gemm_epi.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp]
+    lib.stz_op_gemm_sampler.restype = i32
+    lib.stz_op_gemm_sampler.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.stz_op_gemm_ln.restype = i32
+    lib.stz_op_gemm_ln.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]
+    lib.stz_graph_count.restype = i32
+    lib.stz_graph_count.argtypes = [vp, C.POINTER(i64)]
+    lib.stz_reserve.restype = i32
+    lib.stz_reserve.argtypes = [vp, i32, i32, i32, i32, i32]
     if lib.stz_abi_version() != ABI_VERSION:
         raise StzError(f"ABI mismatch: library {lib.stz_abi_version()} vs python {ABI_VERSION}")
     if path is None:
@@ -115,7 +127,8 @@ EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset
                     "stz_destroy", "stz_last_error", "stz_sample_style", "stz_predict_duration",
                     "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_set_noise_utterances", "stz_philox_normal", "stz_debug_plan", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
-                    "stz_op_gemm_bf16", "stz_op_attention")
+                    "stz_op_gemm_bf16", "stz_op_attention", "stz_op_gemm_epi", "stz_op_gemm_sampler", "stz_op_gemm_ln",
+                    "stz_graph_count", "stz_reserve", "stz_get_option")
 
 
 def _kind(sampler) -> int:
@@ -176,8 +189,61 @@ class StyleTTSZSPath:
     def set_option(self, key: str, value: int):
         self._check(self.lib.stz_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
 
+    def get_option(self, key: str) -> int:
+        v = C.c_int()
+        self._check(self.lib.stz_get_option(self._h, key.encode(), C.byref(v)), f"get_option({key})")
+        return int(v.value)
+
     def launch_count(self) -> int:
         return int(self.lib.stz_launch_count(self._h))
+
+    def graph_count(self) -> Tuple[int, int]:
+        """(cached CUDA graphs, captures since creation) of the evaluation loop (include/stz.h: stz_graph_count)."""
+        tot = C.c_int64()
+        n = self.lib.stz_graph_count(self._h, C.byref(tot))
+        if n < 0:
+            raise StzError("stz_graph_count failed")
+        return int(n), int(tot.value)
+
+    def reserve(self, max_B: int, max_T: int, max_P: Optional[int] = None, max_steps: int = 4, sampler="student"):
+        """Size the workspace once for the largest call (no reallocation -> captured graphs survive)."""
+        P = self.cfg.n_style if max_P is None else max_P
+        self._check(self.lib.stz_reserve(self._h, int(max_B), int(max_T), int(P), int(max_steps), _kind(sampler)),
+                    "stz_reserve")
+
+    # ---- unit-test entries: fused epilogues of the product GEMM kernels ------------------------------------------------
+    def op_gemm_epi(self, A, W, bias, epi: int, *, out=None, mod=None, gate_off: int = 0, pos=None) -> torch.Tensor:
+        M, K = A.shape
+        N = W.shape[0]
+        if out is None:
+            out = torch.empty(M, N, device=A.device, dtype=torch.bfloat16 if epi in (2, 3) else torch.float32)
+        st = torch.cuda.current_stream().cuda_stream
+        n_mod = 0 if mod is None else mod.shape[1]
+        self._check(self.lib.stz_op_gemm_epi(self._h, _ptr(A), _ptr(W), _ptr(bias), M, N, K, int(epi), _ptr(out), _ptr(mod),
+                                             n_mod, int(gate_off), _ptr(pos), C.c_void_p(st)), "stz_op_gemm_epi")
+        return out
+
+    def op_gemm_sampler(self, A, W, bias, x, xmid, noise, coef, *, tap=None) -> torch.Tensor:
+        """Updates x / xmid in place, returns xin [M, 3N] bf16."""
+        M, K = A.shape
+        N = W.shape[0]
+        xin = torch.empty(M, 3 * N, device=A.device, dtype=torch.bfloat16)
+        st = torch.cuda.current_stream().cuda_stream
+        self._check(self.lib.stz_op_gemm_sampler(self._h, _ptr(A), _ptr(W), _ptr(bias), M, N, K, _ptr(x), _ptr(xmid),
+                                                 _ptr(noise), _ptr(coef), _ptr(xin), _ptr(tap), C.c_void_p(st)),
+                    "stz_op_gemm_sampler")
+        return xin
+
+    def op_gemm_ln(self, A, W, bias, h, mod, *, mode: int = 0, gate_off: int = 0, shift_off: int = 0, scale_off: int = 0,
+                   pos=None, split3: bool = False) -> torch.Tensor:
+        """Overwrites h with h', returns u [M, 512] (or [M, 1536] if split3) bf16."""
+        M, K = A.shape
+        u = torch.empty(M, (3 if split3 else 1) * self.cfg.d_model, device=A.device, dtype=torch.bfloat16)
+        st = torch.cuda.current_stream().cuda_stream
+        self._check(self.lib.stz_op_gemm_ln(self._h, _ptr(A), _ptr(W), _ptr(bias), M, K, int(mode), _ptr(h), _ptr(mod),
+                                            mod.shape[1], int(gate_off), int(shift_off), int(scale_off), _ptr(pos),
+                                            1 if split3 else 0, _ptr(u), C.c_void_p(st)), "stz_op_gemm_ln")
+        return u
 
     PROFILE_CLASSES = ("gemm_tc", "attention", "ln_mod", "linear_f32", "lstm_rec", "pred_ew", "other")
 

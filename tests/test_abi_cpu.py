@@ -35,6 +35,18 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.stz_abi_version() == stz.ABI_VERSION
 
 
+def test_library_exports_nothing_the_header_does_not_declare():
+    """The other direction: every stz_* symbol in the dynamic symbol table is declared in include/stz.h."""
+    import shutil
+    import subprocess
+    if shutil.which("nm") is None:
+        pytest.skip("nm not available")
+    so = os.path.join(ROOT, "styletts-zs_b200", "csrc", "libstz.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], check=True, capture_output=True, text=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("stz_")})
+    assert exported == _header_functions()
+
+
 @pytest.mark.parametrize("cfg", [stz.DEFAULT, stz.TINY], ids=["default", "tiny"])
 def test_weight_layout_matches_spec(lib, cfg):
     cc = P._cconfig(cfg)

@@ -206,7 +206,7 @@ def _attention_reference(q, k, v, vis):
     return torch.einsum("hqk,khd->qhd", torch.softmax(s, -1), v).reshape(q.shape[0], -1)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["tcgen05_tma", "mma_resident", "mma_streaming", "tcgen05_cpasync"])
+@pytest.mark.parametrize("impl", [0, 2], ids=["tcgen05_tma", "mma_streaming"])
 @pytest.mark.parametrize("B", [1, 5])
 def test_self_attention_vs_torch_fp32(path, impl, B):
     d, K, H = CFG.d_model, CFG.n_style, CFG.n_heads
@@ -222,7 +222,7 @@ def test_self_attention_vs_torch_fp32(path, impl, B):
             assert rel(got, ref) < 2e-2, (b, br)     # bf16 P and bf16 output rounding
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["tcgen05_tma", "mma_resident", "mma_streaming", "tcgen05_cpasync"])
+@pytest.mark.parametrize("impl", [0, 2], ids=["tcgen05_tma", "mma_streaming"])
 @pytest.mark.parametrize("T,P", [(64, 50), (13, 50), (40, 7), (100, 50), (300, 50), (512, 50), (129, 3)])
 def test_cross_attention_vs_torch_fp32(path, impl, T, P):
     d, K, H, B = CFG.d_model, CFG.n_style, CFG.n_heads, 3
@@ -321,7 +321,7 @@ def test_seeded_sample_style_equals_explicit_noise(path, oracle, sampler, steps)
     b = path.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 2.0, seed=4242, first_utterance=10, sampler=sampler)
     assert torch.equal(a, b)
     ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 2.0, seed=4242, first_utterance=10, sampler=sampler)
-    assert rel(b.cpu(), ref) < 2e-2
+    assert rel(b.cpu(), ref) < TOL_STYLE
     # shard invariance through the whole sampler: utterances [1, 3) on their own
     c = path.sample_style(inp["text_emb"][1:], inp["prompt_feats"][1:], steps, 2.0, seed=4242, first_utterance=11, sampler=sampler)
     assert rel(c, b[1:]) < 5e-3
@@ -498,3 +498,123 @@ def test_errors_are_loud(path):
     # the handle stays usable after an error
     z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 1, 2.0, noise=inp["noise"])
     assert bool(torch.isfinite(z).all())
+
+
+# ---------------------------------------------------------------------------------------------
+# the BENCHED configurations, at their exact sizes, against the fp32 oracle (tolerance 1e-2): these are the shapes
+# whose dispatch (fused GEMM + AdaLN kernel, hoisted modulations, streaming attention) the small cases above do not reach
+# ---------------------------------------------------------------------------------------------
+def test_cfg2_exact_size_vs_oracle(path, oracle):
+    """BASELINE configs[1] exactly as bench.py runs it: B = 64, T = 64, 4-step CFG student, w = 2, then the duration
+    predictor.  50 row tiles -> the residual GEMMs run the fused GEMM + AdaLN kernel (gemmln3_kernel): asserted."""
+    inp = stz.synthetic_inputs(CFG, 64, 64, steps=4, seed=1234)
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, noise=inp["noise"])
+    assert path.get_option("last_fuse_mode") == 3 and path.get_option("last_T") == 64
+    z_ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, noise=inp["noise"])
+    assert rel(z, z_ref) < TOL_STYLE
+    d = path.predict_duration(inp["text_emb"], z_ref).cpu()
+    d_ref = oracle.predict_duration(inp["text_emb"], z_ref)
+    assert float((d == d_ref).float().mean()) >= TOL_DUR_AGREE
+
+
+def test_cfg3_exact_size_vs_oracle(path, oracle):
+    """BASELINE configs[2] exactly: B = 32, T = 64, 32 ADPM2 teacher steps = 64 chained CFG evaluations, ancestral noise
+    (~30 s of oracle on 16 cores)."""
+    inp = stz.synthetic_inputs(CFG, 32, 64, steps=32, sampler=stz.SAMPLER_TEACHER, seed=1234)
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 32, 2.0, noise=inp["noise"], sampler="teacher")
+    z_ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], 32, 2.0, noise=inp["noise"], sampler="teacher")
+    assert rel(z, z_ref) < TOL_STYLE
+
+
+def test_cfg4_sampler_inside_full_batch_vs_oracle(path, oracle):
+    """BASELINE configs[3]: B = 256, T in [16, 512] with padding masks, 4-step CFG student.  The CUDA path samples the whole
+    batch (streaming attention, padded-tile skipping, fused kernel at 200 row tiles -> GEMM + ln_mod by the dispatch rule);
+    the oracle recomputes 16 of its utterances on their own (utterances are independent)."""
+    B, T = 256, 512
+    inp = stz.synthetic_inputs(CFG, B, T, steps=4, seed=4321, var_len=(16, 512))
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, text_mask=inp["text_mask"], noise=inp["noise"])
+    assert bool(torch.isfinite(z).all())
+    sl = slice(100, 116)
+    tmax = int(inp["lens"][sl].max())
+    z_ref = oracle.sample_style(inp["text_emb"][sl, :tmax], inp["prompt_feats"][sl], 4, 2.0,
+                                text_mask=inp["text_mask"][sl, :tmax], noise=inp["noise"][:, sl])
+    assert rel(z[sl], z_ref) < TOL_STYLE
+    # and the predictor on those utterances, fed identical codes, inside the full batch
+    style = torch.zeros(B, CFG.n_style, CFG.d_style)
+    style[sl] = z_ref
+    d = path.predict_duration(inp["text_emb"], style, text_mask=inp["text_mask"]).cpu()
+    d_ref = oracle.predict_duration(inp["text_emb"][sl, :tmax], z_ref, text_mask=inp["text_mask"][sl, :tmax])
+    mm = inp["text_mask"][sl, :tmax]
+    assert float((d[sl, :tmax][mm] == d_ref[mm]).float().mean()) >= TOL_DUR_AGREE
+
+
+@pytest.mark.parametrize("B,T,steps,sampler", [(2, 24, 2, "student"), (3, 40, 3, "teacher")])
+def test_fused_gemm_adaln_forced_at_small_batch_vs_oracle(path, oracle, B, T, steps, sampler):
+    """fuse_ln = 4 forces gemmln3_kernel at any size: the small oracle cases through the benched kernel."""
+    kind = stz.SAMPLER_TEACHER if sampler == "teacher" else stz.SAMPLER_STUDENT
+    inp = stz.synthetic_inputs(CFG, B, T, steps=steps, sampler=kind, seed=31, var_len=(T // 2, T))
+    path.set_option("fuse_ln", 4)
+    try:
+        z = path.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 2.0, text_mask=inp["text_mask"], noise=inp["noise"],
+                              sampler=sampler)
+        assert path.get_option("last_fuse_mode") == 3
+    finally:
+        path.set_option("fuse_ln", 3)
+    z_ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 2.0, text_mask=inp["text_mask"],
+                                noise=inp["noise"], sampler=sampler)
+    assert rel(z, z_ref) < TOL_STYLE
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA-graph cache: text-length buckets, LRU cap, reserved workspace
+# ---------------------------------------------------------------------------------------------
+def test_graph_buckets_serving_loop(weights, oracle):
+    """200 calls with random T in [16, 512] capture at most 10 graphs (one per length bucket) and, after stz_reserve, never
+    reallocate the workspace; results at a bucketed length still match the oracle at the true length."""
+    p = stz.StyleTTSZSPath(CFG, weights, device=0)
+    try:
+        B = 4
+        p.reserve(B, 512, max_steps=2)
+        g = torch.Generator().manual_seed(0)
+        text = torch.randn(B, 512, CFG.d_text, generator=g).cuda()
+        prompt = torch.randn(B, CFG.n_style, CFG.d_prompt, generator=g).cuda()
+        noise = torch.randn(1, B, CFG.n_style, CFG.d_style, generator=g).cuda()
+        seen = set()
+        for i in range(200):
+            T = int(torch.randint(16, 513, (1,), generator=g))
+            p.sample_style(text[:, :T].contiguous(), prompt, 2, 2.0, noise=noise)
+            seen.add(p.get_option("last_T"))
+        torch.cuda.synchronize()
+        cached, captured = p.graph_count()
+        assert seen <= {32, 64, 96, 128, 192, 256, 384, 512}
+        assert cached == len(seen) <= 8 and captured == cached          # every capture was a new bucket: no re-capture
+        for T in (17, 100, 300):                                        # bucketed run == oracle at the true length
+            z = p.sample_style(text[:, :T].contiguous(), prompt, 2, 2.0, noise=noise)
+            z_ref = oracle.sample_style(text[:, :T].cpu(), prompt.cpu(), 2, 2.0, noise=noise.cpu())
+            assert rel(z, z_ref) < TOL_STYLE
+        assert p.graph_count()[1] == captured                           # no new capture either
+        # LRU cap
+        p.set_option("max_graphs", 3)
+        for T in (20, 50, 90, 120, 180, 250):
+            p.sample_style(text[:, :T].contiguous(), prompt, 1, 2.0, noise=noise)
+        assert p.graph_count()[0] <= max(3, cached)
+        z1 = p.sample_style(text[:, :20].contiguous(), prompt, 1, 2.0, noise=noise)      # evicted -> re-captured, same bits
+        z2 = p.sample_style(text[:, :20].contiguous(), prompt, 1, 2.0, noise=noise)
+        assert torch.equal(z1, z2)
+    finally:
+        p.close()
+
+
+def test_zero_length_utterance_is_finite(path):
+    """An utterance whose text is entirely masked (length 0) in a long padded batch: context K/V of its first key block are
+    still computed (skipped tiles must not leave uninitialised rows in front of the streaming attention)."""
+    B, T = 3, 256
+    inp = stz.synthetic_inputs(CFG, B, T, steps=2, seed=8, var_len=(140, 256))
+    tm = inp["text_mask"].clone()
+    tm[1] = False
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], 2, 2.0, text_mask=tm, noise=inp["noise"])
+    assert bool(torch.isfinite(z).all())
+    # the other utterances do not notice
+    z_ref = path.sample_style(inp["text_emb"][[0, 2]], inp["prompt_feats"][[0, 2]], 2, 2.0, text_mask=tm[[0, 2]],
+                              noise=inp["noise"][:, [0, 2]])
+    assert rel(z[[0, 2]], z_ref) < 5e-3
