@@ -119,7 +119,7 @@ struct stz_handle {
   bool has_last = false;
   // captured evaluation loops, keyed by (B, T bucket, P, evaluations, sampler kind + mask flags); least-recently-used
   // entries are evicted beyond max_graphs
-  struct GraphEntry { cudaGraphExec_t exec; int launches; uint64_t last_use; };
+  struct GraphEntry { cudaGraphExec_t exec; int launches; uint64_t last_use; int fuse_mode; };
   std::map<std::tuple<int, int, int, int, int>, GraphEntry> graphs;
   uint64_t graph_clock = 0;
   int64_t graph_captures = 0;   // captures since creation (stz_graph_count)
@@ -485,6 +485,13 @@ static int gemm(stz_handle* H, cudaStream_t st, int impl, const bf16* A, int lda
     return fail(H, STZ_E_SHAPE, "gemm shape M=%d N=%d K=%d unsupported (N %% 128, K %% 64)", p.M, p.N, p.K);
   if (impl == 0) return launch_gemm2<EPI>(H, st, A, lda, a_rows, W, p);
   return launch_gemm_simt<EPI>(H, st, A, lda, W, p);
+}
+
+// fused residual GEMM + AdaLN (gemm_ln3.cuh)
+template <int MODE>
+static int launch_gemmln(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
+                         const GemmLnParams& p) {
+  return launch_gemmln3<MODE>(H, st, A, lda, a_rows, W, u, p);
 }
 
 static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, int ld1, int K1, const float* X2, int ld2,
@@ -1168,7 +1175,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = Kc; p.bias = bias; p.gate_off = gate_off; p.shift_off = ln_off; p.scale_off = ln_off + d; p.split3 = last ? 1 : 0;
-      return launch_gemmln3<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
+      return launch_gemmln<GLN_RES>(H, st, A, Kc, R, Wt, last ? u3 : u, p);
     }
     GemmParams p = base;
     p.M = R; p.N = d; p.K = Kc; p.bias = bias; p.out = h; p.ldo = d; p.gate_off = gate_off;
@@ -1180,7 +1187,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     if (fused) {
       GemmLnParams p = lb;
       p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.shift_off = 0; p.scale_off = d; p.split3 = 0;
-      RET(launch_gemmln3<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
+      RET(launch_gemmln<GLN_POS>(H, st, xin, 3 * Ds, R, H->w_in3, u, p));
     } else {
       GemmParams p = base;
       p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = h; p.ldo = d; p.pos = W32(H, "pos");
@@ -1395,19 +1402,19 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
       ce = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) return fail(H, STZ_E_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(ce));
-      if ((int)H->graphs.size() >= H->max_graphs) {   // evict the least recently used graph (its last launch may still run)
+      while ((int)H->graphs.size() >= H->max_graphs) {   // evict the least recently used graphs (the stream was synchronised above)
         auto victim = H->graphs.begin();
         for (auto jt = H->graphs.begin(); jt != H->graphs.end(); ++jt)
           if (jt->second.last_use < victim->second.last_use) victim = jt;
-        CK(H, cudaStreamSynchronize(st));
         cudaGraphExecDestroy(victim->second.exec);
         H->graphs.erase(victim);
       }
-      it = H->graphs.emplace(key, stz_handle::GraphEntry{exec, H->cur_launches, 0}).first;
+      it = H->graphs.emplace(key, stz_handle::GraphEntry{exec, H->cur_launches, 0, H->last_fuse_mode}).first;
       ++H->graph_captures;
       H->cur_launches = 0;
     }
     it->second.last_use = ++H->graph_clock;
+    H->last_fuse_mode = it->second.fuse_mode;
     CK(H, cudaGraphLaunch(it->second.exec, st));
     H->launches += it->second.launches;
   } else {
@@ -1813,7 +1820,7 @@ extern "C" int stz_bench_gemm(stz_handle* H, int M, int N, int K, int epi, int i
         GemmLnParams q{};
         q.M = M; q.K = K; q.bias = bias; q.h = Cf; q.mod = mod; q.n_mod = 3 * N; q.gate_off = 0; q.shift_off = N; q.scale_off = 2 * N;
         q.rows_per_utt = rpu; q.pos = nullptr; q.n_style = H->cfg.n_style; q.split3 = 0;
-        return launch_gemmln3<GLN_RES>(H, st, A, K, M, W, Cb, q);
+        return launch_gemmln<GLN_RES>(H, st, A, K, M, W, Cb, q);
       }
       default: return fail(H, STZ_E_ARG, "epi %d not benchable", epi);
     }
@@ -1898,8 +1905,8 @@ extern "C" int stz_op_gemm_ln(stz_handle* H, const void* A, const void* W, const
   p.scale_off = scale_off; p.rows_per_utt = 2 * H->cfg.n_style; p.pos = pos; p.n_style = H->cfg.n_style; p.split3 = split3 ? 1 : 0;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   int rc;
-  if (mode == GLN_RES) rc = launch_gemmln3<GLN_RES>(H, st, (const bf16*)A, K, M, (const bf16*)W, (bf16*)u_out, p);
-  else if (mode == GLN_POS) rc = launch_gemmln3<GLN_POS>(H, st, (const bf16*)A, K, M, (const bf16*)W, (bf16*)u_out, p);
+  if (mode == GLN_RES) rc = launch_gemmln<GLN_RES>(H, st, (const bf16*)A, K, M, (const bf16*)W, (bf16*)u_out, p);
+  else if (mode == GLN_POS) rc = launch_gemmln<GLN_POS>(H, st, (const bf16*)A, K, M, (const bf16*)W, (bf16*)u_out, p);
   else return fail(H, STZ_E_ARG, "mode must be 0 (residual) or 1 (positional)");
   H->cur_launches = 0;
   return rc;

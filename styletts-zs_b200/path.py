@@ -18,7 +18,8 @@ import torch
 from .spec import (ABI_VERSION, DEFAULT, SAMPLER_STUDENT, SAMPLER_TEACHER, StzConfig, n_noise_slices,
                    weight_offsets)
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstz.so")
+# STZ_LIBRARY: an alternative build of the same sources (the timeline build libstz_trace.so of tools/*_trace.py)
+_LIB_PATH = os.environ.get("STZ_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstz.so")
 _lib = None
 
 

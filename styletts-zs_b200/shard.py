@@ -11,6 +11,8 @@ passes StyleTTSZSPath.synthesize_host, the CPU tests pass the oracle.
 """
 from __future__ import annotations
 
+import math
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -80,3 +82,90 @@ def synthesize_sharded(compute: Callable[..., Tuple[torch.Tensor, torch.Tensor]]
         style_out[ii] = st
         dur_out[ii, :du.shape[1]] = du.to(torch.int32)
     return style_out, dur_out
+
+
+class SharedHostOutputs:
+    """The host-side gather without a gather: one /dev/shm-backed mapping per job, shared by the ranks of one box.  Rank r's
+    device->host copies land directly in slab r (the mapping is registered as pinned memory when CUDA is present), so
+    after a barrier rank 0 holds every rank's results in host memory — no collective, no pickling, no extra copy but the
+    final re-ordering into the caller's utterance order (``assemble``).
+
+    ``tag`` names the job and must be the same on every rank (bench.py uses MASTER_PORT); ``barrier`` is a callable that
+    synchronises the ranks (``dist.barrier`` of a gloo / nccl group; a no-op for world_size 1)."""
+
+    def __init__(self, tag: str, B: int, T: int, K: int, Ds: int, rank: int, world_size: int, barrier: Callable[[], None],
+                 pin: bool = True):
+        self.rank, self.world, self.B, self.T, self.K, self.Ds = rank, world_size, B, T, K, Ds
+        self.n_max = math.ceil(B / world_size)
+        self._paths = [f"/dev/shm/stz_{tag}_style", f"/dev/shm/stz_{tag}_dur"]
+        n_style, n_dur = world_size * self.n_max * K * Ds, world_size * self.n_max * T
+        if rank == 0:
+            for path, nbytes in zip(self._paths, (4 * n_style, 4 * n_dur)):
+                with open(path, "wb") as f:
+                    f.truncate(nbytes)
+        barrier()
+        self.style = torch.from_file(self._paths[0], shared=True, size=n_style, dtype=torch.float32).view(world_size, self.n_max, K, Ds)
+        self.dur = torch.from_file(self._paths[1], shared=True, size=n_dur, dtype=torch.int32).view(world_size, self.n_max * T)
+        self._registered = []
+        if pin and torch.cuda.is_available():
+            rt = torch.cuda.cudart()
+            for t in (self.style, self.dur):
+                if int(rt.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)) == 0:
+                    self._registered.append(t.data_ptr())
+        self.pinned = len(self._registered) == 2
+        barrier()
+
+    def slab(self, n: int, t: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """This rank's output buffers: style [n,K,Ds] fp32 and durations [n,t] int32 (contiguous)."""
+        return self.style[self.rank, :n], self.dur[self.rank, :n * t].view(n, t)
+
+    def assemble(self, shards: List[List[int]], shard_T: List[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Rank 0, after the barrier: results in the caller's utterance order (durations zero-padded to T)."""
+        style = torch.empty(self.B, self.K, self.Ds)
+        dur = torch.zeros(self.B, self.T, dtype=torch.int32)
+        for r, idx in enumerate(shards):
+            if not idx:
+                continue
+            ii = torch.tensor(idx, dtype=torch.long)
+            n, t = len(idx), shard_T[r]
+            style.index_copy_(0, ii, self.style[r, :n])
+            dur[ii, :t] = self.dur[r, :n * t].view(n, t)
+        return style, dur
+
+    def close(self, barrier: Optional[Callable[[], None]] = None):
+        if self._registered:
+            rt = torch.cuda.cudart()
+            for ptr in self._registered:
+                rt.cudaHostUnregister(ptr)
+            self._registered = []
+        self.style = self.dur = None
+        if barrier is not None:
+            barrier()
+        if self.rank == 0:
+            for path in self._paths:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+
+
+def synthesize_sharded_shm(compute: Callable[..., Tuple[torch.Tensor, torch.Tensor]], shard_inputs: Optional[Dict[str, torch.Tensor]],
+                           shards: List[List[int]], shard_T: List[int], out: SharedHostOutputs,
+                           barrier: Callable[[], None]) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    """The product form of ``synthesize_sharded``: this rank's shard (``shard_inputs`` = ``take_shard(inputs, shards[rank])``,
+    prepared by the caller: in a server every rank receives its own utterances) runs through
+    ``compute(text_emb, text_mask, prompt_feats, prompt_mask, noise, out_style=..., out_dur=...)`` with the output buffers
+    inside the shared host mapping; a barrier; rank 0 re-orders.  Returns (style [B,K,Ds], dur [B,T]) on rank 0, None elsewhere."""
+    idx = shards[out.rank]
+    if idx:
+        o_style, o_dur = out.slab(len(idx), shard_T[out.rank])
+        sh = shard_inputs
+        res = compute(sh["text_emb"], sh["text_mask"], sh["prompt_feats"], sh.get("prompt_mask"), sh.get("noise"),
+                      out_style=o_style, out_dur=o_dur)
+        if res is not None and res[0] is not None and res[0].data_ptr() != o_style.data_ptr():   # a compute without out= support
+            o_style.copy_(res[0])
+            o_dur.copy_(res[1])
+    barrier()
+    if out.rank != 0:
+        return None
+    return out.assemble(shards, shard_T)

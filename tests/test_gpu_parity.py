@@ -569,8 +569,9 @@ def test_fused_gemm_adaln_forced_at_small_batch_vs_oracle(path, oracle, B, T, st
 # CUDA-graph cache: text-length buckets, LRU cap, reserved workspace
 # ---------------------------------------------------------------------------------------------
 def test_graph_buckets_serving_loop(weights, oracle):
-    """200 calls with random T in [16, 512] capture at most 10 graphs (one per length bucket) and, after stz_reserve, never
-    reallocate the workspace; results at a bucketed length still match the oracle at the true length."""
+    """A serving loop: 200 variable-length batches (lengths in [16, 512], padded to the batch's longest utterance, padding
+    mask passed) capture at most 8 graphs — one per text-length bucket — and, after stz_reserve, never reallocate the
+    workspace or re-capture; a bucketed call still matches the oracle at the true length."""
     p = stz.StyleTTSZSPath(CFG, weights, device=0)
     try:
         B = 4
@@ -581,23 +582,35 @@ def test_graph_buckets_serving_loop(weights, oracle):
         noise = torch.randn(1, B, CFG.n_style, CFG.d_style, generator=g).cuda()
         seen = set()
         for i in range(200):
-            T = int(torch.randint(16, 513, (1,), generator=g))
-            p.sample_style(text[:, :T].contiguous(), prompt, 2, 2.0, noise=noise)
+            lens = torch.randint(16, 513, (B,), generator=g)
+            T = int(lens.max())
+            mask = (torch.arange(T)[None] < lens[:, None]).cuda()
+            p.sample_style(text[:, :T].contiguous(), prompt, 2, 2.0, noise=noise, text_mask=mask)
             seen.add(p.get_option("last_T"))
         torch.cuda.synchronize()
         cached, captured = p.graph_count()
         assert seen <= {32, 64, 96, 128, 192, 256, 384, 512}
         assert cached == len(seen) <= 8 and captured == cached          # every capture was a new bucket: no re-capture
         for T in (17, 100, 300):                                        # bucketed run == oracle at the true length
-            z = p.sample_style(text[:, :T].contiguous(), prompt, 2, 2.0, noise=noise)
-            z_ref = oracle.sample_style(text[:, :T].cpu(), prompt.cpu(), 2, 2.0, noise=noise.cpu())
+            lens = torch.tensor([T, max(1, T // 2), T - 3, T])
+            mask = torch.arange(T)[None] < lens[:, None]
+            z = p.sample_style(text[:, :T].contiguous(), prompt, 2, 2.0, noise=noise, text_mask=mask)
+            z_ref = oracle.sample_style(text[:, :T].cpu(), prompt.cpu(), 2, 2.0, noise=noise.cpu(), text_mask=mask)
             assert rel(z, z_ref) < TOL_STYLE
-        assert p.graph_count()[1] == captured                           # no new capture either
+        assert p.graph_count()[1] <= captured + 3                       # at most the buckets not visited by the loop
+        # unmasked calls at a length that is not a bucket run masked at the bucket; at an exact bucket length they keep the
+        # mask-free graph (1.4 % faster at cfg2: the benched configuration), so a bucket holds at most two graphs
+        z = p.sample_style(text[:, :100].contiguous(), prompt, 2, 2.0, noise=noise)
+        z_ref = oracle.sample_style(text[:, :100].cpu(), prompt.cpu(), 2, 2.0, noise=noise.cpu())
+        assert rel(z, z_ref) < TOL_STYLE and p.get_option("last_T") == 128
         # LRU cap
         p.set_option("max_graphs", 3)
         for T in (20, 50, 90, 120, 180, 250):
             p.sample_style(text[:, :T].contiguous(), prompt, 1, 2.0, noise=noise)
-        assert p.graph_count()[0] <= max(3, cached)
+        assert p.graph_count()[0] <= 3
+        p.set_option("max_graphs", 2)
+        for T in (20, 50, 90):
+            p.sample_style(text[:, :T].contiguous(), prompt, 1, 2.0, noise=noise)
         z1 = p.sample_style(text[:, :20].contiguous(), prompt, 1, 2.0, noise=noise)      # evicted -> re-captured, same bits
         z2 = p.sample_style(text[:, :20].contiguous(), prompt, 1, 2.0, noise=noise)
         assert torch.equal(z1, z2)

@@ -51,10 +51,20 @@ def _worker(rank, world, port, q):
     compute = _oracle_compute(cfg, w)
     res = stz.synthesize_sharded(compute, inp, rank, world)
     res_seeded = stz.synthesize_sharded(compute, _seeded(inp), rank, world)   # on-"device" noise from global indices
+    # the product form: outputs land in a shared host mapping (no collective on the data path), rank 0 re-orders
+    shards = stz.shard_utterances(inp["lens"].tolist(), world)
+    shard_T = [max(int(inp["lens"][i]) for i in sh) if sh else 1 for sh in shards]
+    out = stz.SharedHostOutputs(f"test{port}", 5, 14, cfg.n_style, cfg.d_style, rank, world, dist.barrier)
+
+    def compute_out(text, mask, prompt, pmask, noise, out_style=None, out_dur=None):
+        return compute(text, mask, prompt, pmask, noise)      # no out= support: the sharder copies into the slab
+    res_shm = stz.synthesize_sharded_shm(compute_out, stz.take_shard(inp, shards[rank]) if shards[rank] else None, shards,
+                                         shard_T, out, dist.barrier)
     if rank == 0:
-        q.put((res[0], res[1], res_seeded[0], res_seeded[1]))
+        q.put((res[0], res[1], res_seeded[0], res_seeded[1], res_shm[0].clone(), res_shm[1].clone()))
     else:
-        assert res is None and res_seeded is None
+        assert res is None and res_seeded is None and res_shm is None
+    out.close(dist.barrier)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -73,12 +83,14 @@ def test_world_size_2_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    style, dur, style_seeded, dur_seeded = q.get(timeout=240)
+    style, dur, style_seeded, dur_seeded, style_shm, dur_shm = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert torch.allclose(style, ref_style, atol=2e-5)
     assert torch.equal(dur, ref_dur)
+    assert torch.equal(style_shm, style) and torch.equal(dur_shm, dur)       # shared-memory gather == object gather
+    assert not os.path.exists(f"/dev/shm/stz_test{port}_style")               # rank 0 unlinked the mapping
     # seed mode: the two ranks drew their utterances' noise from global indices == the unsharded seeded run
     full_seeded = _oracle_compute(cfg, w)(inp["text_emb"], inp["text_mask"], inp["prompt_feats"], inp["prompt_mask"], None, seed=99)
     assert torch.allclose(style_seeded, full_seeded[0], atol=2e-5)

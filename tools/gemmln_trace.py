@@ -6,7 +6,7 @@ import torch
 import styletts_zs_b200 as stz
 cfg = stz.DEFAULT
 path = stz.StyleTTSZSPath(cfg, stz.init_weights(cfg, 0))
-path.set_option("fuse_ln", 3)
+path.set_option("fuse_ln", 4)  # force the fused kernel
 path.set_option("use_graph", 0)
 inp = stz.synthetic_inputs(cfg, 64, 64, steps=1, seed=1)
 dev = {k: inp[k].cuda() for k in ("text_emb", "prompt_feats", "noise")}
