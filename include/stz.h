@@ -100,6 +100,18 @@ int stz_predict_duration(stz_handle* h, const float* text_emb_dev, const uint8_t
 int stz_regulate_length(stz_handle* h, const float* feats_dev, const int32_t* dur_dev, int B, int T, int C, int F_max,
                         float* out_frames_dev, int32_t* out_frame_lens_dev, int32_t* out_frame_tok_dev, void* cuda_stream);
 
+/* Prosody heads — F0 and energy curves over the length-regulated frames (second half; the
+ * "duration/prosody predictor" of BASELINE.json's north_star):
+ *     frames = regulate([d_enc | s_tok], dur)   d_enc = the duration encoder's output (input of its final BiLSTM)
+ *     y = BiLSTM_pros(frames) (packed by frame count);  z = gelu_tanh([y | s_frame] W_h1^T + b_h1)
+ *     f0 = z[:, :d_hid/2] . w_f0 + b_f0,  energy = z[:, d_hid/2:] . w_en + b_en,  0 past the utterance's frame count.
+ * Runs predict_duration's forward first; dur_in_dev [B,T] (may be NULL) overrides the predicted durations for the
+ * regulator (e.g. ground-truth alignments); out_dur_dev [B,T] (may be NULL) receives the predicted ones.
+ *   out_f0_dev, out_energy_dev [B,F_max] fp32; out_frame_lens_dev [B] int32 = min(sum of durations, F_max).  T <= 1024. */
+int stz_predict_prosody(stz_handle* h, const float* text_emb_dev, const uint8_t* text_mask_dev, const float* style_dev,
+                        const int32_t* dur_in_dev, int B, int T, int F_max, float* out_f0_dev, float* out_energy_dev,
+                        int32_t* out_frame_lens_dev, int32_t* out_dur_dev, void* cuda_stream);
+
 /* On-device noise.  After stz_set_noise_seed, a NULL `noise` argument of stz_sample_style /
  * stz_synthesize_host means: draw every noise slice on the device — Philox4x32-10, key = seed, counter = (group of four
  * elements inside the utterance's [K*Ds] slice, utterance lo, slice, utterance hi), Box-Muller built from individually

@@ -203,19 +203,7 @@ class OraclePath:
     # ---- a-8 .. a-11 ----------------------------------------------------------------
     def _lstms(self):
         if self._lstm is None:
-            cfg, W = self.cfg, self.W
-            mods = []
-            for l in range(cfg.n_lstm):
-                m = torch.nn.LSTM(cfg.d_hid + cfg.d_sty_tok, cfg.h_lstm, batch_first=True, bidirectional=True)
-                with torch.no_grad():
-                    for dr, suf in (("f", ""), ("r", "_reverse")):
-                        p = f"lstm{l}.{dr}."
-                        getattr(m, "weight_ih_l0" + suf).copy_(W[p + "w_ih"])
-                        getattr(m, "weight_hh_l0" + suf).copy_(W[p + "w_hh"])
-                        getattr(m, "bias_ih_l0" + suf).copy_(W[p + "b_ih"])
-                        getattr(m, "bias_hh_l0" + suf).copy_(W[p + "b_hh"])
-                mods.append(m.eval())
-            self._lstm = mods
+            self._lstm = [self._lstm_module(f"lstm{l}") for l in range(self.cfg.n_lstm)]
         return self._lstm
 
     @torch.no_grad()
@@ -245,6 +233,53 @@ class OraclePath:
         a = attention(q, k, v, cfg.n_sp_heads, None, _Ops(False))
         return F.linear(a, W["sp.o.w"], W["sp.o.b"])
 
+    def _lstm_module(self, prefix):
+        cfg, W = self.cfg, self.W
+        m = torch.nn.LSTM(cfg.d_hid + cfg.d_sty_tok, cfg.h_lstm, batch_first=True, bidirectional=True)
+        with torch.no_grad():
+            for dr, suf in (("f", ""), ("r", "_reverse")):
+                p = f"{prefix}.{dr}."
+                getattr(m, "weight_ih_l0" + suf).copy_(W[p + "w_ih"])
+                getattr(m, "weight_hh_l0" + suf).copy_(W[p + "w_hh"])
+                getattr(m, "bias_ih_l0" + suf).copy_(W[p + "b_ih"])
+                getattr(m, "bias_hh_l0" + suf).copy_(W[p + "b_hh"])
+        return m.eval()
+
+    @staticmethod
+    def _packed_bilstm(lstm, inp, lens, total_length):
+        """BiLSTM with packed-sequence semantics (the reverse direction starts at each sequence's own last valid step);
+        zero-length sequences produce zeros."""
+        out = torch.zeros(inp.shape[0], total_length, 2 * lstm.hidden_size)
+        nz = torch.nonzero(lens > 0).flatten()
+        if nz.numel():
+            packed = torch.nn.utils.rnn.pack_padded_sequence(inp[nz], lens[nz].cpu(), batch_first=True, enforce_sorted=False)
+            o, _ = lstm(packed)
+            o, _ = torch.nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=total_length)
+            out[nz] = o
+        return out
+
+    @torch.no_grad()
+    def _duration_encoder(self, text_emb, style_codes, text_mask):
+        """a-8 + a-9: -> (d_enc [B,T,d_hid] = input of the final BiLSTM, x [B,T,d_hid] = its output, s_tok [B,T,d_sty_tok])."""
+        cfg, W = self.cfg, self.W
+        B, T, _ = text_emb.shape
+        lens = text_mask.sum(1)
+        # masks are prefix masks (padding at the end), as produced by a length vector
+        assert bool((text_mask == (torch.arange(T)[None] < lens[:, None])).all()), "text_mask must be a prefix mask"
+        mf = text_mask.to(torch.float32)[..., None]
+        s_tok = self.style_per_token(text_emb, style_codes)
+        x, d_enc = text_emb, None
+        for l, lstm in enumerate(self._lstms()):
+            if l == cfg.n_lstm - 1:
+                d_enc = x
+            inp = torch.cat([x, s_tok], -1)
+            x = self._packed_bilstm(lstm, inp, lens, T)
+            if l < cfg.n_lstm - 1:
+                gb = F.linear(s_tok, W[f"adaln{l}.w"], W[f"adaln{l}.b"])
+                x = layer_norm(x) * (1 + gb[..., :cfg.d_hid]) + gb[..., cfg.d_hid:]
+                x = x * mf
+        return d_enc, x, s_tok
+
     @torch.no_grad()
     def predict_duration(self, text_emb, style_codes, *, text_mask=None, return_presum=False):
         cfg, W = self.cfg, self.W
@@ -253,21 +288,41 @@ class OraclePath:
         if text_mask is None:
             text_mask = torch.ones(B, T, dtype=torch.bool)
         text_mask = text_mask.bool()
-        lens = text_mask.sum(1)
-        # masks are prefix masks (padding at the end), as produced by a length vector
-        assert bool((text_mask == (torch.arange(T)[None] < lens[:, None])).all()), "text_mask must be a prefix mask"
         mf = text_mask.to(torch.float32)[..., None]
-        s_tok = self.style_per_token(text_emb, style_codes)
-        x = text_emb
-        for l, lstm in enumerate(self._lstms()):
-            inp = torch.cat([x, s_tok], -1)
-            packed = torch.nn.utils.rnn.pack_padded_sequence(inp, lens.cpu(), batch_first=True, enforce_sorted=False)
-            out, _ = lstm(packed)
-            x, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=T)
-            if l < cfg.n_lstm - 1:
-                gb = F.linear(s_tok, W[f"adaln{l}.w"], W[f"adaln{l}.b"])
-                x = layer_norm(x) * (1 + gb[..., :cfg.d_hid]) + gb[..., cfg.d_hid:]
-                x = x * mf
+        _, x, _ = self._duration_encoder(text_emb, style_codes, text_mask)
         s = torch.sigmoid(F.linear(x, W["dur.w"], W["dur.b"])).sum(-1)           # a-10
         dur = (torch.round(s).clamp(min=1) * mf[..., 0]).to(torch.int32)        # half-to-even
         return (dur, s) if return_presum else dur
+
+    @torch.no_grad()
+    def predict_prosody(self, text_emb, style_codes, *, text_mask=None, durations=None, max_frames=None):
+        """SURVEY.md §8(f) rank 2, second half — the F0 / energy ("prosody") heads behind the length regulator, pinned here
+        (the reference has no code; the shape follows the StyleTTS lineage's F0Ntrain: a shared recurrent layer over the
+        length-regulated duration-encoder features, then one small head per curve):
+            en      = regulate([d_enc | s_tok], durations)                      [B,F,d_hid + d_sty_tok]
+            y       = BiLSTM_pros(en)   (packed by frame length)                 [B,F,d_hid]
+            z       = gelu_tanh([y | s_frame] W_h1^T + b_h1)                     [B,F,2 d_pros]   (s_frame = en[..., d_hid:])
+            f0      = z[..., :d_pros] . w_f0 + b_f0,  energy = z[..., d_pros:] . w_en + b_en      0 past the frame length
+        durations=None uses predict_duration's.  -> (f0 [B,F], energy [B,F], frame_lens [B] int32, durations [B,T] int32)."""
+        cfg, W = self.cfg, self.W
+        text_emb, style_codes = text_emb.float(), style_codes.float()
+        B, T, _ = text_emb.shape
+        if text_mask is None:
+            text_mask = torch.ones(B, T, dtype=torch.bool)
+        text_mask = text_mask.bool()
+        mf = text_mask.to(torch.float32)[..., None]
+        d_enc, x, s_tok = self._duration_encoder(text_emb, style_codes, text_mask)
+        if durations is None:
+            s = torch.sigmoid(F.linear(x, W["dur.w"], W["dur.b"])).sum(-1)
+            durations = (torch.round(s).clamp(min=1) * mf[..., 0]).to(torch.int32)
+        durations = durations.to(torch.int32)
+        F_max = int(max_frames) if max_frames is not None else cfg.max_dur * T
+        en, flen = self.regulate_length(torch.cat([d_enc, s_tok], -1), durations, max_frames=F_max)
+        if not hasattr(self, "_pros_lstm"):
+            self._pros_lstm = self._lstm_module("pros.lstm")
+        y = self._packed_bilstm(self._pros_lstm, en, flen.to(torch.int64), F_max)
+        z = gelu_tanh(F.linear(torch.cat([y, en[..., cfg.d_hid:]], -1), W["pros.h1.w"], W["pros.h1.b"]))
+        fm = (torch.arange(F_max)[None] < flen[:, None]).to(torch.float32)
+        f0 = (z[..., :cfg.d_pros] @ W["pros.f0.w"] + W["pros.f0.b"]) * fm
+        en_curve = (z[..., cfg.d_pros:] @ W["pros.en.w"] + W["pros.en.b"]) * fm
+        return f0, en_curve, flen, durations

@@ -95,6 +95,19 @@ struct stz_handle {
   bool pred_tc = false;
   bf16 *wq3 = nullptr, *wkv3 = nullptr, *wo3 = nullptr, *wih3 = nullptr, *wada3 = nullptr;
   float* b_kv = nullptr;
+  // prosody heads: shared BiLSTM + two small heads behind the length regulator
+  bf16 *wih3_pros = nullptr, *wh1_3 = nullptr;
+  float *whh_pros = nullptr, *lstm_b_pros = nullptr;
+  struct ProsodyWs {        // sized by (B, F_max), grown on demand; separate from the sampler / predictor arena
+    char* base = nullptr;
+    size_t bytes = 0;
+    int B = 0, F = 0, T = 0;
+    float *frames, *G, *y;
+    bf16* pa;
+    int *flens, *perm, *dur;
+    uint8_t* needed;
+  } pws;
+  const float* last_d_enc = nullptr;   // predict_duration_impl: the duration encoder's output (input of the final BiLSTM)
   Workspace ws;
   cudaStream_t stream = nullptr;      // internal stream (create-time work, host entry point, capture)
   // host entry point: prompt / noise H2D and the style D2H run on a second stream, overlapping the text-side
@@ -727,6 +740,7 @@ extern "C" void stz_destroy(stz_handle* H) {
   cudaFree(H->ws.base); cudaFree(H->w32); cudaFree(H->wbf); cudaFree(H->ctx_text_b); cudaFree(H->ctx_prompt_b);
   cudaFree(H->wq3); cudaFree(H->wkv3); cudaFree(H->wo3); cudaFree(H->wih3); cudaFree(H->wada3); cudaFree(H->b_kv);
   cudaFree(H->wkv_all); cudaFree(H->bkv_all);
+  cudaFree(H->wih3_pros); cudaFree(H->wh1_3); cudaFree(H->whh_pros); cudaFree(H->lstm_b_pros); cudaFree(H->pws.base);
   for (auto& sl : H->slot)
     for (cudaEvent_t e : {sl.ev_text, sl.ev_prompt, sl.ev_noise, sl.ev_style, sl.ev_dur, sl.ev_done})
       if (e) cudaEventDestroy(e);
@@ -840,6 +854,20 @@ static int create_impl(stz_handle* H, const float* weights_host) {
       RET(split(W32(H, "sp.o.w"), H->wo3, ds, ds));
       CK(H, cudaMemcpyAsync(H->b_kv, W32(H, "sp.k.b"), ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
       CK(H, cudaMemcpyAsync(H->b_kv + ds, W32(H, "sp.v.b"), ds * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      // prosody heads: shared BiLSTM (both directions' input projections in one GEMM) + the two heads' hidden layer
+      CK(H, cudaMalloc(&H->wih3_pros, (size_t)8 * h * 3 * kin * sizeof(bf16)));
+      CK(H, cudaMalloc(&H->wh1_3, (size_t)dh * 3 * kin * sizeof(bf16)));
+      CK(H, cudaMalloc(&H->whh_pros, (size_t)2 * 4 * h * h * sizeof(float)));
+      CK(H, cudaMalloc(&H->lstm_b_pros, (size_t)2 * 4 * h * sizeof(float)));
+      for (int dr = 0; dr < 2; ++dr) {
+        const std::string p = std::string("pros.lstm.") + (dr ? "r." : "f.");
+        RET(split(W32(H, p + "w_ih"), H->wih3_pros + (size_t)dr * 4 * h * 3 * kin, 4 * h, kin));
+        CK(H, cudaMemcpyAsync(H->whh_pros + (size_t)dr * 4 * h * h, W32(H, p + "w_hh"), (size_t)4 * h * h * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+        add_vec_kernel<<<ew_grid(4 * h), 256, 0, st>>>(W32(H, p + "b_ih"), W32(H, p + "b_hh"), H->lstm_b_pros + (size_t)dr * 4 * h, 4 * h, 4 * h);
+        KCHECK(H);
+      }
+      RET(split(W32(H, "pros.h1.w"), H->wh1_3, dh, kin));
       for (int l = 0; l < c.n_lstm; ++l) {
         for (int dr = 0; dr < 2; ++dr)
           RET(split(W32(H, "lstm" + std::to_string(l) + (dr ? ".r.w_ih" : ".f.w_ih")),
@@ -1507,6 +1535,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
   constexpr int NB = 8;
   const size_t lstm_smem = (size_t)NB * h * 5 * sizeof(float);
   for (int l = 0; l < c.n_lstm; ++l) {
+    if (l == c.n_lstm - 1) H->last_d_enc = x;   // the duration encoder's output: what the prosody heads regulate
     if (tc) {  // G = [x | s_tok] W_ih^T + (b_ih + b_hh), both directions in one GEMM (N = 8h)
       RET(gemm3(w.pa, 3 * kin, BT, H->wih3 + (size_t)l * 8 * h * 3 * kin, H->lstm_b + (size_t)l * 8 * h, w.G, 8 * h));
     } else {
@@ -1588,11 +1617,107 @@ extern "C" int stz_regulate_length(stz_handle* H, const float* feats_dev, const 
   LaunchScope ls(H);
   H->cur_launches = 0;
   launch_k(length_regulate_kernel, dim3(cdiv(F_max, LR_FRAMES), B), LR_THREADS, 0, st, feats_dev, dur_dev, out_frames_dev,
-           out_frame_lens_dev, out_frame_tok_dev, T, C, F_max);
+           out_frame_lens_dev, out_frame_tok_dev, T, C, F_max, (const float*)nullptr, 0);
   KCHECK(H);
   H->launches += H->cur_launches;
   H->cur_launches = 0;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// prosody heads (second half): F0 and energy curves over the length-regulated frames
+// ------------------------------------------------------------------------------------------
+static int ensure_prosody_ws(stz_handle* H, int B, int F, int T) {
+  stz_handle::ProsodyWs& w = H->pws;
+  if (w.base && B <= w.B && F <= w.F && T <= w.T) return 0;
+  if (w.base) { CK(H, cudaDeviceSynchronize()); CK(H, cudaFree(w.base)); w.base = nullptr; }
+  B = B > w.B ? B : w.B; F = F > w.F ? F : w.F; T = T > w.T ? T : w.T;
+  const stz_config& c = H->cfg;
+  const size_t BF = (size_t)B * F, kin = c.d_hid + c.d_sty_tok, h8 = 4 * (size_t)c.d_hid;
+  size_t off = 0;
+  std::vector<std::pair<void**, size_t>> plan;
+  auto want = [&](void** p, size_t bytes) { plan.push_back({p, off}); off = align_up(off + bytes, 1024); };
+  want((void**)&w.frames, BF * kin * sizeof(float));
+  want((void**)&w.pa, (BF + 128) * 3 * kin * sizeof(bf16));
+  want((void**)&w.G, BF * h8 * sizeof(float));
+  want((void**)&w.y, BF * c.d_hid * sizeof(float));
+  want((void**)&w.flens, (size_t)B * sizeof(int)); want((void**)&w.perm, (size_t)B * sizeof(int));
+  want((void**)&w.dur, (size_t)B * T * sizeof(int));
+  want((void**)&w.needed, BF / 128 + 2);
+  cudaError_t e = cudaMalloc(&w.base, off);
+  if (e != cudaSuccess) {
+    w = stz_handle::ProsodyWs();
+    return fail(H, STZ_E_NOMEM, "prosody workspace of %zu bytes: %s", off, cudaGetErrorString(e));
+  }
+  for (auto& pr : plan) *pr.first = w.base + pr.second;
+  w.bytes = off; w.B = B; w.F = F; w.T = T;
+  return 0;
+}
+
+extern "C" int stz_predict_prosody(stz_handle* H, const float* text_emb_dev, const uint8_t* text_mask_dev, const float* style_dev,
+                                   const int32_t* dur_in_dev, int B, int T, int F_max, float* out_f0_dev, float* out_energy_dev,
+                                   int32_t* out_frame_lens_dev, int32_t* out_dur_dev, void* cuda_stream) {
+  if (!H) return STZ_E_ARG;
+  if (!text_emb_dev || !style_dev || !out_f0_dev || !out_energy_dev || !out_frame_lens_dev) return fail(H, STZ_E_ARG, "null tensor argument");
+  if (B < 1 || T < 1 || F_max < 1) return fail(H, STZ_E_ARG, "bad sizes B=%d T=%d F_max=%d", B, T, F_max);
+  const stz_config& c = H->cfg;
+  const int dh = c.d_hid, ds = c.d_sty_tok, h = dh / 2, kin = dh + ds, dp = dh / 2;
+  if (!H->pred_tc || h != LC_H || T > LR_MAX_T || dp % 128 || dp > 512)
+    return fail(H, STZ_E_SHAPE, "prosody heads need the tensor-core predictor configuration (d_hid 512, d_sty_tok %% 128 == 0) and T <= %d", LR_MAX_T);
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  LaunchScope ls(H);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  RET(ensure_prosody_ws(H, B, F_max, T));
+  stz_handle::ProsodyWs& w = H->pws;
+  // the duration predictor's forward: durations (unless given) and, in the workspace, d_enc and s_tok
+  int32_t* dur_pred = out_dur_dev ? out_dur_dev : w.dur;
+  RET(predict_duration_impl(H, text_emb_dev, text_mask_dev, style_dev, B, T, dur_pred, nullptr, st));
+  const int32_t* dur = dur_in_dev ? dur_in_dev : dur_pred;
+  const size_t BF = (size_t)B * F_max;
+  H->cur_launches = 0;
+  // frames = regulate([d_enc | s_tok], dur)
+  launch_k(length_regulate_kernel, dim3(cdiv(F_max, LR_FRAMES), B), LR_THREADS, 0, st, H->last_d_enc, dur, w.frames, w.flens,
+           (int32_t*)nullptr, T, dh, F_max, (const float*)H->ws.stok, ds); KCHECK(H);
+  launch_k(perm_from_lens_kernel, 1, 1024, 0, st, (const int*)w.flens, w.perm, B); KCHECK(H);
+  launch_k(frame_tile_needed_kernel, cdiv(cdiv((long long)BF, 128), 256), 256, 0, st, (const int*)w.flens, w.needed, B, F_max); KCHECK(H);
+  CK(H, cudaMemcpyAsync(out_frame_lens_dev, w.flens, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  auto split_rows = [&](const float* src, int ld, int Kc, int off) -> int {
+    ProfScope ps(H, st, PC_PRED_EW, (double)BF * Kc * 10.0);
+    launch_k(split3_rows_kernel, ew_grid(BF * (Kc / 4)), 256, 0, st, src, ld, Kc, w.pa, 3 * kin, kin, off, BF);
+    KCHECK(H);
+    return 0;
+  };
+  auto gemm3 = [&](const bf16* W3, const float* bias, float* out, int N) -> int {
+    GemmParams p{};
+    p.M = (int)BF; p.N = N; p.K = 3 * kin; p.bias = bias; p.out = out; p.ldo = N; p.tile_needed = w.needed;
+    return gemm<EPI_F32>(H, st, H->gemm_impl, w.pa, 3 * kin, (int)BF, W3, p);
+  };
+  // shared BiLSTM over the frames (packed by frame count)
+  RET(split_rows(w.frames, kin, kin, 0));
+  RET(gemm3(H->wih3_pros, H->lstm_b_pros, w.G, 8 * h));
+  {
+    ProfScope ps(H, st, PC_LSTM, 2.0 * BF * 2.0 * h * 4.0 * h);
+    launch_k(lstm_tc_kernel, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, (const float*)w.G, (const float*)H->whh_pros,
+             (const int*)w.flens, (const int*)w.perm, w.y, B, F_max);
+    KCHECK(H);
+  }
+  // z = [y | s_frame] W_h1^T + b_h1 (the s_frame columns of the operand are still in place), then the two heads
+  RET(split_rows(w.y, dh, dh, 0));
+  RET(gemm3(H->wh1_3, W32(H, "pros.h1.b"), w.G, dh));
+  {
+    ProfScope ps(H, st, PC_PRED_EW, (double)BF * (dh * 4.0 + 8.0));
+    const dim3 grid(cdiv((long long)BF, 8));
+    switch (dp / 128) {
+      case 1: launch_k(prosody_head_kernel<1>, grid, 256, 0, st, (const float*)w.G, W32(H, "pros.f0.w"), W32(H, "pros.f0.b"), W32(H, "pros.en.w"), W32(H, "pros.en.b"), (const int*)w.flens, out_f0_dev, out_energy_dev, B, F_max); break;
+      case 2: launch_k(prosody_head_kernel<2>, grid, 256, 0, st, (const float*)w.G, W32(H, "pros.f0.w"), W32(H, "pros.f0.b"), W32(H, "pros.en.w"), W32(H, "pros.en.b"), (const int*)w.flens, out_f0_dev, out_energy_dev, B, F_max); break;
+      case 4: launch_k(prosody_head_kernel<4>, grid, 256, 0, st, (const float*)w.G, W32(H, "pros.f0.w"), W32(H, "pros.f0.b"), W32(H, "pros.en.w"), W32(H, "pros.en.b"), (const int*)w.flens, out_f0_dev, out_energy_dev, B, F_max); break;
+      default: return fail(H, STZ_E_SHAPE, "d_hid %d unsupported by the prosody heads", dh);
+    }
+    KCHECK(H);
+  }
+  H->launches += H->cur_launches;
+  H->cur_launches = 0;
+  return mark_call_end(H, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -62,6 +62,16 @@ inline std::vector<WeightEntry> build_layout(const stz_config& c, size_t* total)
     }
   }
   add("dur.w", (size_t)c.max_dur * dh); add("dur.b", c.max_dur);
+  // prosody (F0 / energy) heads behind the length regulator: appended, so the offsets above never move
+  const size_t dp = dh / 2;
+  for (const char* dr : {"f", "r"}) {
+    const std::string p = std::string("pros.lstm.") + dr + ".";
+    add(p + "w_ih", 4 * h * (dh + ds)); add(p + "w_hh", 4 * h * h);
+    add(p + "b_ih", 4 * h); add(p + "b_hh", 4 * h);
+  }
+  add("pros.h1.w", 2 * dp * (dh + ds)); add("pros.h1.b", 2 * dp);
+  add("pros.f0.w", dp); add("pros.f0.b", 1);
+  add("pros.en.w", dp); add("pros.en.b", 1);
   if (total) *total = off;
   return E;
 }

@@ -69,6 +69,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_predict_duration.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
     lib.stz_regulate_length.restype = i32
     lib.stz_regulate_length.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.stz_predict_prosody.restype = i32
+    lib.stz_predict_prosody.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.stz_synthesize_host.restype = i32
     lib.stz_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
     lib.stz_synthesize_host_submit.restype = i32
@@ -129,7 +131,7 @@ EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset
                     "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_set_noise_utterances", "stz_philox_normal", "stz_debug_plan", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16", "stz_op_attention", "stz_op_gemm_epi", "stz_op_gemm_sampler", "stz_op_gemm_ln",
-                    "stz_graph_count", "stz_reserve", "stz_get_option")
+                    "stz_graph_count", "stz_reserve", "stz_get_option", "stz_predict_prosody")
 
 
 def _kind(sampler) -> int:
@@ -358,6 +360,28 @@ class StyleTTSZSPath:
                 if t is not None:
                     t.record_stream(torch.cuda.current_stream())
         return (out, pre) if return_presum else out
+
+    def predict_prosody(self, text_emb, style_codes, *, text_mask=None, durations=None, max_frames: Optional[int] = None):
+        """F0 / energy heads behind the length regulator -> (f0 [B,F], energy [B,F] fp32, frame_lens [B] int32,
+        durations [B,T] int32 as predicted); ``durations`` overrides the predicted ones for the regulator."""
+        B, T, _ = text_emb.shape
+        F_max = int(max_frames) if max_frames is not None else self.cfg.max_dur * T
+        with torch.cuda.device(self.device):
+            te, sc = self._dev(text_emb, torch.float32), self._dev(style_codes, torch.float32)
+            tm = self._mask(text_mask)
+            du = None if durations is None else self._dev(durations, torch.int32)
+            f0 = torch.empty(B, F_max, dtype=torch.float32, device=self.device)
+            en = torch.empty(B, F_max, dtype=torch.float32, device=self.device)
+            fl = torch.empty(B, dtype=torch.int32, device=self.device)
+            dur = torch.empty(B, T, dtype=torch.int32, device=self.device)
+            st = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.stz_predict_prosody(self._h, _ptr(te), _ptr(tm), _ptr(sc), _ptr(du), B, T, F_max, _ptr(f0), _ptr(en),
+                                              _ptr(fl), _ptr(dur), C.c_void_p(st))
+            self._check(rc, "stz_predict_prosody")
+            for t in (te, sc, tm, du):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream())
+        return f0, en, fl, dur
 
     def regulate_length(self, feats, durations, *, max_frames: Optional[int] = None, return_tokens: bool = False):
         """Length regulator: frames[b, f] = feats[b, token of frame f] for the integer durations of predict_duration.

@@ -62,6 +62,11 @@ class StzConfig:
     def h_lstm(self) -> int:
         return self.d_hid // 2
 
+    @property
+    def d_pros(self) -> int:
+        """Hidden width of each prosody head (F0, energy)."""
+        return self.d_hid // 2
+
     def as_dict(self):
         return asdict(self)
 
@@ -123,6 +128,15 @@ def weight_entries(cfg: StzConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
         if l < cfg.n_lstm - 1:
             a((f"adaln{l}.w", (2 * dh, ds), "w")); a((f"adaln{l}.b", (2 * dh,), "b"))
     a(("dur.w", (cfg.max_dur, dh), "dw")); a(("dur.b", (cfg.max_dur,), "db"))
+    # --- prosody (F0 / energy) heads behind the length regulator -----------------------------
+    # appended after every entry above, so the offsets (and the seeded values) of the path's weights do not move
+    for dr in ("f", "r"):
+        p = f"pros.lstm.{dr}."
+        a((p + "w_ih", (4 * h, dh + ds), "w")); a((p + "w_hh", (4 * h, h), "w"))
+        a((p + "b_ih", (4 * h,), "b")); a((p + "b_hh", (4 * h,), "b"))
+    a(("pros.h1.w", (2 * cfg.d_pros, dh + ds), "w")); a(("pros.h1.b", (2 * cfg.d_pros,), "b"))
+    a(("pros.f0.w", (cfg.d_pros,), "w")); a(("pros.f0.b", (1,), "b"))
+    a(("pros.en.w", (cfg.d_pros,), "w")); a(("pros.en.b", (1,), "b"))
     return E
 
 

@@ -631,3 +631,47 @@ def test_zero_length_utterance_is_finite(path):
     z_ref = path.sample_style(inp["text_emb"][[0, 2]], inp["prompt_feats"][[0, 2]], 2, 2.0, text_mask=tm[[0, 2]],
                               noise=inp["noise"][:, [0, 2]])
     assert rel(z[[0, 2]], z_ref) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# prosody heads (second half): F0 / energy over the length-regulated frames
+# ---------------------------------------------------------------------------------------------
+TOL_PROSODY = 2e-3     # fp32-grade arithmetic (split-bf16 tensor-core products, fp32 recurrence): max |err| / max |ref|
+
+
+@pytest.mark.parametrize("B,T,F,tlen", [(1, 5, 64, None), (3, 24, 300, (6, 24)), (4, 64, 1024, (20, 64)), (2, 40, 100, (30, 40))])
+def test_prosody_heads_vs_oracle(path, oracle, B, T, F, tlen):
+    """predict_prosody against the oracle on identical inputs (the oracle's style codes): identical durations and frame
+    counts, F0 / energy curves to fp32-grade tolerance; F = 100 truncates (frame totals exceed it)."""
+    inp = stz.synthetic_inputs(CFG, B, T, steps=1, seed=50 + T, var_len=tlen)
+    tm = inp["text_mask"] if tlen else None
+    style = 0.7 * torch.randn(B, CFG.n_style, CFG.d_style, generator=torch.Generator().manual_seed(T))
+    f0_ref, en_ref, fl_ref, d_ref = oracle.predict_prosody(inp["text_emb"], style, text_mask=tm, max_frames=F)
+    f0, en, fl, d = path.predict_prosody(inp["text_emb"], style, text_mask=tm, max_frames=F)
+    m = inp["text_mask"]
+    assert float((d.cpu()[m] == d_ref[m]).float().mean()) >= TOL_DUR_AGREE
+    # the curves with the ORACLE's durations as the alignment (identical inputs for the heads)
+    f0, en, fl, _ = path.predict_prosody(inp["text_emb"], style, text_mask=tm, durations=d_ref, max_frames=F)
+    assert torch.equal(fl.cpu(), fl_ref)
+    assert rel(f0, f0_ref) < TOL_PROSODY and rel(en, en_ref) < TOL_PROSODY
+    valid = torch.arange(F)[None] < fl_ref[:, None]
+    assert bool((f0.cpu()[~valid] == 0).all()) and bool((en.cpu()[~valid] == 0).all())
+
+
+def test_prosody_heads_cfg2_size_properties(path):
+    """cfg2-sized (B = 64, T = 64): finite, zero past the frame count, and each utterance on its own (unpadded batch of one)
+    gives the same curves — the recurrence is packed per utterance."""
+    B, T, F = 64, 64, 1536
+    inp = stz.synthetic_inputs(CFG, B, T, steps=1, seed=77, var_len=(10, 64))
+    style = 0.7 * torch.randn(B, CFG.n_style, CFG.d_style, generator=torch.Generator().manual_seed(9))
+    f0, en, fl, d = path.predict_prosody(inp["text_emb"], style, text_mask=inp["text_mask"], max_frames=F)
+    assert bool(torch.isfinite(f0).all()) and bool(torch.isfinite(en).all())
+    assert torch.equal(fl.cpu(), d.cpu().sum(1).clamp(max=F).to(torch.int32))
+    valid = torch.arange(F, device="cuda")[None] < fl[:, None]
+    assert bool((f0[~valid] == 0).all()) and float(f0[valid].std()) > 1e-3
+    for b in (0, 31, 63):
+        n = int(inp["lens"][b])
+        f0b, enb, flb, _ = path.predict_prosody(inp["text_emb"][b:b + 1, :n], style[b:b + 1], max_frames=F)
+        assert int(flb[0]) == int(fl[b])
+        k = int(fl[b])
+        assert float((f0b[0, :k] - f0[b, :k]).abs().max()) < 1e-3 and float((enb[0, :k] - en[b, :k]).abs().max()) < 1e-3
