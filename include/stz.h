@@ -47,7 +47,11 @@ typedef enum stz_status {
 
 typedef enum stz_sampler_kind {
   STZ_SAMPLER_STUDENT = 0, /* distilled few-step student: Euler on Karras(steps) + terminal 0 */
-  STZ_SAMPLER_TEACHER = 1  /* teacher: ADPM2 on Karras(steps+1), 2 denoiser evals per step     */
+  STZ_SAMPLER_TEACHER = 1, /* teacher: ADPM2 on Karras(steps+1), 2 denoiser evals per step     */
+  STZ_SAMPLER_GUIDED = 2   /* guidance-conditioned student: the distillation bakes classifier-free
+                              guidance into the network — `cfg_scale` enters as an embedding of the conditioning vector and
+                              ONE conditional branch is evaluated per step (half the denoiser rows of the CFG pair); same
+                              Euler schedule and noise as STZ_SAMPLER_STUDENT */
 } stz_sampler_kind;
 
 /* Field order mirrors styletts-zs_b200/spec.py:StzConfig. */

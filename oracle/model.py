@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import schedule as S
 
-SAMPLER_STUDENT, SAMPLER_TEACHER = 0, 1
+SAMPLER_STUDENT, SAMPLER_TEACHER, SAMPLER_GUIDED = 0, 1, 2
 
 
 def _bf16(x: torch.Tensor) -> torch.Tensor:
@@ -99,13 +99,23 @@ class Conditioning:
             self.kv.append(tuple(ops.lin(c, w, b, tag="kv2") for c in self.ctx))
 
 
+def guidance_embedding(cfg, W, omega: float) -> torch.Tensor:
+    """the guidance scale as an input of the distilled student — sinusoidal features of omega / 4
+    (the time embedding's frequencies) through a two-layer MLP, added to the conditioning vector.  -> [d]"""
+    feat = torch.tensor(S.time_features(omega / 4.0, cfg.d_time), dtype=torch.float64).to(torch.float32)
+    return F.linear(F.silu(F.linear(feat, W["gs.w1"], W["gs.b1"])), W["gs.w2"], W["gs.b2"])
+
+
 def denoiser_F(cfg, W, x_in: torch.Tensor, c_noise: float, cond: Conditioning, branch: int,
-               ops: _Ops) -> torch.Tensor:
+               ops: _Ops, g_emb=None) -> torch.Tensor:
     """a-4: F_theta(x_in, c_noise | text, prompt-or-null).  x_in [B,K,Ds] -> [B,K,Ds]."""
     d, L, H = cfg.d_model, cfg.n_layers, cfg.n_heads
     feat = torch.tensor(S.time_features(c_noise, cfg.d_time), dtype=torch.float64).to(torch.float32)
     t = F.linear(F.silu(F.linear(feat, W["time.w1"], W["time.b1"])), W["time.w2"], W["time.b2"])
-    c = F.silu(t[None, :] + cond.pooled[branch])                       # [B,d]
+    pre = t[None, :] + cond.pooled[branch]
+    if g_emb is not None:
+        pre = pre + g_emb[None, :]
+    c = F.silu(pre)                                                     # [B,d]
     mod = ops.lin(c, W["mod.w"], W["mod.b"], tag="mod")                         # [B,(9L+2)d]
 
     def m(i):  # modulation chunk i -> [B,1,d]
@@ -143,9 +153,17 @@ def guided_denoise(cfg, W, x, sigma: float, cond: Conditioning, cfg_scale: float
     return c_skip * x + c_out * Fg
 
 
+def guided_student_denoise(cfg, W, x, sigma: float, cond: Conditioning, omega: float, ops: _Ops):
+    """The guidance-conditioned student (README.md:5 "the style diffusion model is distilled"):
+    D = c_skip x + c_out F(c_in x; sigma, omega | text, prompt) — ONE conditional branch, omega as an embedding."""
+    c_skip, c_out, c_in, c_noise = S.edm_precond(sigma, cfg.sigma_data)
+    Fg = denoiser_F(cfg, W, c_in * x, c_noise, cond, 0, ops, g_emb=guidance_embedding(cfg, W, omega))
+    return c_skip * x + c_out * Fg
+
+
 def sample_loop(cfg, denoise, noise: torch.Tensor, steps: int, sampler: int) -> torch.Tensor:
     """a-6/a-7: the sampler loop around D(x, sigma) = denoise(x, sigma)."""
-    if sampler == SAMPLER_STUDENT:
+    if sampler in (SAMPLER_STUDENT, SAMPLER_GUIDED):
         sig = S.student_sigmas(steps, cfg)
         x = sig[0] * noise[0]
         for i in range(steps):
@@ -183,7 +201,8 @@ class OraclePath:
         cfg = self.cfg
         B, T, _ = text_emb.shape
         P = prompt_feats.shape[1]
-        kind = SAMPLER_TEACHER if sampler in ("teacher", SAMPLER_TEACHER) else SAMPLER_STUDENT
+        kind = SAMPLER_TEACHER if sampler in ("teacher", SAMPLER_TEACHER) else \
+            (SAMPLER_GUIDED if sampler in ("guided", SAMPLER_GUIDED) else SAMPLER_STUDENT)
         if noise is None and seed is not None:   # §8(f) rank 4: counter-based noise, oracle/philox.py
             from . import philox
             ns = steps + 1 if kind == SAMPLER_TEACHER else 1
@@ -197,7 +216,10 @@ class OraclePath:
             raise ValueError("noise tensor is an input (identical seeds == identical noise tensors)")
         cond = Conditioning(cfg, self.W, text_emb.float(), text_mask.bool(), prompt_feats.float(),
                             prompt_mask.bool(), self.ops)
-        den = lambda x, s: guided_denoise(cfg, self.W, x, s, cond, cfg_scale, self.ops)
+        if kind == SAMPLER_GUIDED:
+            den = lambda x, s: guided_student_denoise(cfg, self.W, x, s, cond, cfg_scale, self.ops)
+        else:
+            den = lambda x, s: guided_denoise(cfg, self.W, x, s, cond, cfg_scale, self.ops)
         return sample_loop(cfg, den, noise.float(), steps, kind)
 
     # ---- a-8 .. a-11 ----------------------------------------------------------------

@@ -35,6 +35,7 @@ struct AttnParams {
   int nseg;
   AttnSeg seg[3];
   float scale_log2;        // log2(e) / sqrt(d_head)
+  int single;              // single-branch row layout: n_q = n_style query rows per utterance (tcgen05 kernels only)
 };
 
 constexpr int ATT_DH = 64;
@@ -347,6 +348,8 @@ struct AttnTcParams {
   const uint8_t* pmask;    // [B, P] or nullptr
   int n_style;             // tokens per branch
   float scale_log2;
+  int single;              // single-branch row layout (guidance-conditioned student): query row = b * n_style + token, only tile
+                           // rows 0..63 (the "conditional" half) are loaded and written; the unit is still (utterance, head)
 };
 
 __device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   // Only V rows that no TMA box covers must be finite (p = 0 times NaN would poison O); K rows the boxes do not cover only
   // produce S columns that the visibility select discards, and Q / P rows are always fully written.  Self-attention boxes
   // cover every row, so nothing is cleared there; cross-attention clears the two V tiles.
-  if (!p.self) {
+  if (!p.self || p.single) {     // (single-branch self-attention loads only rows 0..63 of V)
     for (uint32_t o = tid * 16; o < 2 * ATC_TILE; o += 256 * 16) {
       const uint32_t buf = o / ATC_TILE, off = o % ATC_TILE;
       st_shared_v4(smem_base + buf * ATC_BUF_BYTES + 2 * ATC_TILE + off, 0u, 0u, 0u, 0u);
@@ -410,7 +413,8 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
   ATC2_TR();
-  const uint32_t tx_bytes = p.self ? 6u * 8192u : 2u * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
+  const uint32_t nbox = p.single ? 1u : 2u;             // 64-row boxes per operand (one per branch)
+  const uint32_t tx_bytes = p.self ? 3u * nbox * 8192u : nbox * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
   // parts: 1 = Q (written by the previous kernel), 2 = K / V.  The cross-attention K / V of a call are constants of the
   // evaluation loop (computed once in the conditioning prep), so the first unit's K / V boxes are requested BEFORE
   // griddepcontrol.wait and land while the previous kernel drains.
@@ -427,9 +431,9 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
       if (warp == 0) mbar_expect_tx(&bar_full[buf], tx_bytes);   // the whole unit's bytes, armed with its first part
       if (p.self) {
         if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
-        else if (warp == 1) tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
+        else if (warp == 1 && !p.single) tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
         else if (warp == 2) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
-        else if (warp == 3) tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
+        else if (warp == 3 && !p.single) tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
       } else {
         const uint32_t o1 = p.T8 * 128, o2 = (p.T8 + p.P8) * 128;
         if (warp == 0) tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     }
     if (parts & 1) {
       if (warp == 6) tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
-      else if (warp == 7) tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+      else if (warp == 7 && !p.single) tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
     }
   };
   const bool kv_early = !p.self && static_cast<int>(blockIdx.x) < p.n_units;
@@ -605,9 +609,9 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
       for (int it = 0; it < 4; ++it) {
         const int c = it * 256 + tid, orow_i = c >> 3, ch = c & 7;     // 8 x 16 B per 128-byte row
         const int otok = orow_i & 63, obr = orow_i >> 6;
-        if (otok < n_tok) {
+        if (otok < n_tok && !(p.single && obr)) {
           const uint4 v = lds_u4(qs + orow_i * 128 + ((ch ^ (orow_i & 7)) << 4));
-          *reinterpret_cast<uint4*>(obase + static_cast<size_t>(2 * otok + obr) * p.ldo + ch * 8) = v;
+          *reinterpret_cast<uint4*>(obase + static_cast<size_t>(p.single ? otok : 2 * otok + obr) * p.ldo + ch * 8) = v;
         }
       }
     }
@@ -721,9 +725,9 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
     }
     const int nblk = nbv + 1;                  // valid text blocks, then the prompt + null block (id nbt)
     if (tid == 0) {
-      mbar_expect_tx(&bar_q, 2u * 8192u);
+      mbar_expect_tx(&bar_q, p.single ? 8192u : 2u * 8192u);
       tma_load_3d_u32(qs, &tmQ, smem_u32(&bar_q), head * ATT_DH, 0, b * n_tok);
-      tma_load_3d_u32(qs + 8192, &tmQ, smem_u32(&bar_q), head * ATT_DH, 1, b * n_tok);
+      if (!p.single) tma_load_3d_u32(qs + 8192, &tmQ, smem_u32(&bar_q), head * ATT_DH, 1, b * n_tok);
       load_block(b, head, 0, 0);
       load_block(b, head, 1, nblk > 2 ? 1 : nbt);       // nblk >= 2 always
       issue_s(0);
@@ -849,11 +853,11 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
     tc_fence_after();
     {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + 2 * tok + br) * p.ldo + head * ATT_DH + half * 32;
+      __nv_bfloat16* op = p.out + (static_cast<size_t>(b) * p.n_q + (p.single ? tok : 2 * tok + br)) * p.ldo + head * ATT_DH + half * 32;
       uint32_t r[32];
       tmem_ld32(tmem_o + lane_addr + half * 32, r);
       tmem_ld_wait();
-      if (tok < n_tok) {
+      if (tok < n_tok && !(p.single && br)) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) cast_pool_kernel(const float* __restrict_
 template <int VPL>
 __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h, int rows, const float* __restrict__ mod,
                                                      int n_mod, int shift_off, int scale_off, int rows_per_utt,
-                                                     __nv_bfloat16* __restrict__ out, int split3) {
+                                                     __nv_bfloat16* __restrict__ out, int split3, int single) {
   pdl_sync();
   constexpr int D = 128 * VPL;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ h
   // the modulation rows do not depend on the statistics: fetch them under the two reductions
   float4 sc[VPL], sh[VPL];
   if (mod != nullptr) {
-    const float* mrow = mod + static_cast<size_t>((row / rows_per_utt) * 2 + (row & 1)) * n_mod;
+    const float* mrow = mod + static_cast<size_t>(single ? row / rows_per_utt : (row / rows_per_utt) * 2 + (row & 1)) * n_mod;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       sc[i] = __ldg(reinterpret_cast<const float4*>(mrow + scale_off) + i * 32 + lane);
@@ -130,9 +130,11 @@ __global__ void __launch_bounds__(256) pad_mask_kernel(const uint8_t* __restrict
 }
 
 // c[e, s, :] = bf16(SiLU(t_emb[e] + ptext[b] + (branch ? null_pp : pprompt[b])))   s = 2b + branch
+// single-branch layout (guidance-conditioned student): s = b, always the prompt; g_emb [D] (the guidance-scale embedding) is added
 __global__ void __launch_bounds__(256) cvec_kernel(const float* __restrict__ temb, const float* __restrict__ pt,
                                                    const float* __restrict__ pp, const float* __restrict__ null_pp,
-                                                   __nv_bfloat16* __restrict__ cvec, int E, int n_seq, int D) {
+                                                   __nv_bfloat16* __restrict__ cvec, int E, int n_seq, int D, int single,
+                                                   const float* __restrict__ g_emb) {
   pdl_sync();
   const size_t total = static_cast<size_t>(E) * n_seq * D;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -140,16 +142,18 @@ __global__ void __launch_bounds__(256) cvec_kernel(const float* __restrict__ tem
     const int c = static_cast<int>(i % D);
     const int s = static_cast<int>((i / D) % n_seq);
     const int e = static_cast<int>(i / (static_cast<size_t>(D) * n_seq));
-    const int b = s >> 1;
-    const float p2 = (s & 1) ? null_pp[c] : pp[static_cast<size_t>(b) * D + c];
-    cvec[i] = __float2bfloat16(silu(temb[static_cast<size_t>(e) * D + c] + pt[static_cast<size_t>(b) * D + c] + p2));
+    const int b = single ? s : s >> 1;
+    const float p2 = (!single && (s & 1)) ? null_pp[c] : pp[static_cast<size_t>(b) * D + c];
+    const float g = g_emb != nullptr ? g_emb[c] : 0.f;
+    cvec[i] = __float2bfloat16(silu(temb[static_cast<size_t>(e) * D + c] + pt[static_cast<size_t>(b) * D + c] + p2 + g));
   }
 }
 
-// x = sigma0 * noise0 ; xin rows 2j, 2j+1 = split-bf16 [hi | lo | hi] of c_in0 * x[j]  (row stride 3D)
+// x = sigma0 * noise0 ; xin rows nrep*j .. nrep*j + nrep - 1 = split-bf16 [hi | lo | hi] of c_in0 * x[j]  (row stride 3D);
+// nrep = 2 for the CFG pair layout, 1 for the single-branch layout
 __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict__ noise0, float* __restrict__ x,
                                                          __nv_bfloat16* __restrict__ xin, size_t n_rows, int D,
-                                                         float sigma0, float cin0) {
+                                                         float sigma0, float cin0, int nrep) {
   pdl_sync();
   const size_t nvec = n_rows * (D >> 2);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
@@ -163,9 +167,8 @@ __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict
     uint2 u;
     u.x = pack_bf16(y.x, y.y); u.y = pack_bf16(y.z, y.w);
     const uint2 lo = split_lo4(y, u);
-#pragma unroll
-    for (int br = 0; br < 2; ++br) {
-      __nv_bfloat16* o = xin + (2 * j + br) * 3 * D + c;
+    for (int br = 0; br < nrep; ++br) {
+      __nv_bfloat16* o = xin + (nrep * j + br) * 3 * D + c;
       *reinterpret_cast<uint2*>(o) = u;
       *reinterpret_cast<uint2*>(o + D) = lo;
       *reinterpret_cast<uint2*>(o + 2 * D) = u;

@@ -32,9 +32,10 @@ struct GemmParams {
   // EPI_GATE_RES / EPI_F32_POS
   const float* mod;     // [n_seq, n_mod] AdaLN modulations of this eval
   int n_mod, gate_off;
-  int rows_per_utt;     // 2 * n_style
+  int rows_per_utt;     // rows of one utterance: 2 * n_style (CFG pair layout) or n_style (single-branch layout)
   const float* pos;     // [n_style, N]
   int n_style;
+  int single;           // 0: R layout, row = (b*K + k)*2 + branch (CFG pair); 1: row = b*K + k (guidance-conditioned student)
   // EPI_SAMPLER: state x / xmid [B*K, N] fp32, noise slice [B*K, N], next input xin [M, N] bf16
   float* x;
   float* xmid;
@@ -46,6 +47,12 @@ struct GemmParams {
   // keep whatever they held; only legal when nothing downstream reads them: the duration predictor with text masks)
   const uint8_t* tile_needed;
 };
+
+// sequence (row of the modulation table) and style token of an activation row, for both row layouts
+__device__ __forceinline__ int seq_of_row(int m, int rows_per_utt, int single) {
+  return single ? m / rows_per_utt : (m / rows_per_utt) * 2 + (m & 1);
+}
+__device__ __forceinline__ int tok_of_row(int m, int n_style, int single) { return (single ? m : (m >> 1)) % n_style; }
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -65,7 +72,7 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int m, int n
   if constexpr (EPI == EPI_F32 || EPI == EPI_F32_POS) {
     if (!valid) return;
     if constexpr (EPI == EPI_F32_POS) {
-      const float* pr = p.pos + static_cast<size_t>((m >> 1) % p.n_style) * p.N + n0;
+      const float* pr = p.pos + static_cast<size_t>(tok_of_row(m, p.n_style, p.single)) * p.N + n0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 b = __ldg(reinterpret_cast<const float4*>(pr + j));
@@ -91,7 +98,7 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int m, int n
     }
   } else if constexpr (EPI == EPI_GATE_RES) {
     if (!valid) return;
-    const int seq = (m / p.rows_per_utt) * 2 + (m & 1);
+    const int seq = seq_of_row(m, p.rows_per_utt, p.single);
     const float* g = p.mod + static_cast<size_t>(seq) * p.n_mod + p.gate_off + n0;
     float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + n0;
 #pragma unroll
@@ -105,15 +112,17 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int m, int n
     const float cx = __ldg(p.coef + 0), cm = __ldg(p.coef + 1), cF = __ldg(p.coef + 2), cn = __ldg(p.coef + 3);
     const float cin = __ldg(p.coef + 4), w = __ldg(p.coef + 5);
     const bool to_mid = __ldg(p.coef + 6) != 0.0f;
-    const bool is_cond = (m & 1) == 0;
+    const bool is_cond = p.single || (m & 1) == 0;
+    if (!p.single) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
-      float Fc = is_cond ? v[j] : other, Fu = is_cond ? other : v[j];
-      v[j] = Fu + w * (Fc - Fu);
+      for (int j = 0; j < 32; ++j) {
+        float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
+        float Fc = is_cond ? v[j] : other, Fu = is_cond ? other : v[j];
+        v[j] = Fu + w * (Fc - Fu);
+      }
     }
     if (!valid) return;
-    const size_t so = static_cast<size_t>(m >> 1) * p.N + n0;
+    const size_t so = static_cast<size_t>(p.single ? m : (m >> 1)) * p.N + n0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       float4 xv = *reinterpret_cast<const float4*>(p.x + so + j);

@@ -73,16 +73,22 @@ __device__ __forceinline__ uint32_t gelu_tanh_f16x2_to_bf16x2(float a, float b) 
 // The guided F of the 16 state rows is transposed through a 2 KB shared-memory tile so that the state update runs
 // with lane = (state row, 16-column half): every global access is a full 32-byte sector run (the row-per-thread
 // form issued 24 scattered 8-byte stores per thread and chunk and was bound by L1 store transactions).
+// Single-branch layout (guidance-conditioned student): no CFG pair — every tile row is a state row; the warp's 32 rows go
+// through the same transposed update in two halves of 16.
 __device__ __forceinline__ void sampler_epilogue32(const GemmParams& p, int m0, int n0, float (&v)[32], uint32_t stage, int lane) {
-  const float w = __ldg(p.coef + 5);
+  if (!p.single) {
+    const float w = __ldg(p.coef + 5);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
-    const float Fc = (lane & 1) ? other : v[j], Fu = (lane & 1) ? v[j] : other;
-    v[j] = Fu + w * (Fc - Fu);
+    for (int j = 0; j < 32; ++j) {
+      const float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
+      const float Fc = (lane & 1) ? other : v[j], Fu = (lane & 1) ? v[j] : other;
+      v[j] = Fu + w * (Fc - Fu);
+    }
   }
-  if ((lane & 1) == 0) {
-    const int r = lane >> 1;
+  const int n_half = p.single ? 2 : 1;
+  for (int hf = 0; hf < n_half; ++hf) {
+  if (p.single ? (lane >> 4) == hf : (lane & 1) == 0) {
+    const int r = p.single ? (lane & 15) : (lane >> 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       st_shared_v4(stage + r * 128 + ((j ^ (r & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
@@ -90,14 +96,15 @@ __device__ __forceinline__ void sampler_epilogue32(const GemmParams& p, int m0, 
   }
   __syncwarp();
   const int r = lane >> 1, hs = lane & 1;
-  const int srow = (m0 >> 1) + r;                       // state row
-  if (2 * srow < p.M) {
+  const int srow = p.single ? m0 + 16 * hf + r : (m0 >> 1) + r;                       // state row
+  const int nrep = p.single ? 1 : 2;                    // activation rows fed by one state row
+  if (nrep * srow < p.M) {
     const float cx = __ldg(p.coef + 0), cm = __ldg(p.coef + 1), cF = __ldg(p.coef + 2), cn = __ldg(p.coef + 3);
     const float cin = __ldg(p.coef + 4);
     const bool to_mid = __ldg(p.coef + 6) != 0.0f;
     const size_t so = static_cast<size_t>(srow) * p.N + n0 + hs * 16;
     float* dst = (to_mid ? p.xmid : p.x) + so;
-    __nv_bfloat16* xo = p.xin + static_cast<size_t>(2 * srow) * 3 * p.N + n0 + hs * 16;
+    __nv_bfloat16* xo = p.xin + static_cast<size_t>(nrep * srow) * 3 * p.N + n0 + hs * 16;
 #pragma unroll
     for (int jj = 0; jj < 4; jj += 2) {
       float4 o[2];
@@ -128,8 +135,7 @@ __device__ __forceinline__ void sampler_epilogue32(const GemmParams& p, int m0, 
       h1.x = pack_bf16(y1.x, y1.y); h1.y = pack_bf16(y1.z, y1.w);
       const uint2 l0 = split_lo4(y0, h0), l1 = split_lo4(y1, h1);
       const uint4 hi = make_uint4(h0.x, h0.y, h1.x, h1.y), lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < nrep; ++b) {
         __nv_bfloat16* xr = xo + static_cast<size_t>(b) * 3 * p.N + jj * 4;
         *reinterpret_cast<uint4*>(xr) = hi;
         *reinterpret_cast<uint4*>(xr + p.N) = lo;
@@ -137,7 +143,8 @@ __device__ __forceinline__ void sampler_epilogue32(const GemmParams& p, int m0, 
       }
     }
   }
-  __syncwarp();   // the staging tile is reused by this warp's next chunk
+  __syncwarp();   // the staging tile is reused by this warp's next half / chunk
+  }
 }
 template <int EPI>
 constexpr bool g2_staged() { return EPI == EPI_F32 || EPI == EPI_F32_POS || EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_GATE_RES; }
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         const float* gate = nullptr;
         if constexpr (EPI == EPI_GATE_RES) {
           const int mm = m < p.M ? m : p.M - 1;
-          gate = p.mod + static_cast<size_t>((mm / p.rows_per_utt) * 2 + (mm & 1)) * p.n_mod + p.gate_off;
+          gate = p.mod + static_cast<size_t>(seq_of_row(mm, p.rows_per_utt, p.single)) * p.n_mod + p.gate_off;
         }
         // bias / gate of the NEXT sub-chunk are fetched while the current one is processed (and, for the first,
         // while the accumulator is still being produced): no dependent global latency inside the loop
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
             }
             if constexpr (EPI == EPI_F32_POS) {   // + pos[(row / 2) % n_style]  (input projection)
               const int mm = m < p.M ? m : p.M - 1;
-              const float4* pr = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>((mm >> 1) % p.n_style) * p.N + tile_n * BN + col);
+              const float4* pr = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(tok_of_row(mm, p.n_style, p.single)) * p.N + tile_n * BN + col);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 pq = __ldg(pr + j);

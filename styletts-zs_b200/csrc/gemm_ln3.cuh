@@ -36,6 +36,7 @@ struct GemmLnParams {
   const float* pos;       // [n_style, 512]  (GLN_POS)
   int n_style;
   int split3;             // u is the split-bf16 operand [hi | lo | hi] with row stride 3 * 512
+  int single;             // row layout (see GemmParams::single)
 };
 
 constexpr int GLN_N = 512, GLN_THREADS = 320;
@@ -166,13 +167,13 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     const int r_in = q4 * 32 + lane;                // row inside the tile == TMEM lane
     const int m = tile_m * GEMM_BM + r_in;
     const int mm = m < p.M ? m : p.M - 1;           // clamp for loads; rows >= M are never stored (TMA clips)
-    const float* src = p.pos + static_cast<size_t>((mm >> 1) % p.n_style) * GLN_N;   // GLN_POS only
+    const float* src = p.pos + static_cast<size_t>(tok_of_row(mm, p.n_style, p.single)) * GLN_N;   // GLN_POS only
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + half * 128;
     const int col0 = ncol0 + half * 128;            // first global column of this warp
     const uint32_t sw = r_in & 7;
     // modulation table: every epilogue thread copies its share while the mainloop runs
     const int m_first = tile_m * GEMM_BM < p.M ? tile_m * GEMM_BM : p.M - 1;
-    const int seq_first = (m_first / p.rows_per_utt) * 2, seq_last = ((p.M - 1) / p.rows_per_utt) * 2 + 1;
+    const int seq_first = seq_of_row(m_first & ~1, p.rows_per_utt, p.single), seq_last = seq_of_row((p.M - 1) | (p.single ? 0 : 1), p.rows_per_utt, p.single);
     {
       const int te = threadIdx.x - 64;                     // 0..255
       for (int idx = te; idx < 3 * GLN3_MAX_SEQ * (GLN3_BN / 4); idx += 256) {
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
       if (te < GLN3_BN / 4) reinterpret_cast<float4*>(bias_s)[te] = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0) + te);
       named_bar_sync(1, 256);
     }
-    const int sl = (mm / p.rows_per_utt) * 2 + (mm & 1) - seq_first;      // this row's sequence inside the table
+    const int sl = seq_of_row(mm, p.rows_per_utt, p.single) - seq_first;      // this row's sequence inside the table
     const uint32_t gate_t = smem_u32(&tab_s[0][sl][half * 128]), bias_t = smem_u32(&bias_s[half * 128]);
     mbar_wait(&acc_full, 0);
     if (tr != nullptr) tr[2] = clock64();
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     }
     // ---- pass 2: u = LN(h') * (1 + scale) + shift -> bf16 tile (128 rows x 64 columns per box) in the rest of the ring
     const int m_first = tile_m * GEMM_BM < p.M ? tile_m * GEMM_BM : p.M - 1;
-    const int sl = (mm / p.rows_per_utt) * 2 + (mm & 1) - (m_first / p.rows_per_utt) * 2;
+    const int sl = seq_of_row(mm, p.rows_per_utt, p.single) - seq_of_row(m_first & ~1, p.rows_per_utt, p.single);
     const uint32_t scale_t = smem_u32(&tab_s[1][sl][half * 128]), shift_t = smem_u32(&tab_s[2][sl][half * 128]);
     const uint32_t t_addr2 = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + half * 128;
     tc_fence_after();

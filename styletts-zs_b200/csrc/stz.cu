@@ -44,6 +44,7 @@ struct Workspace {
   // conditioning
   bf16 *text_bf, *prompt_bf, *ctx_text, *ctx_prompt, *kv_text, *kv_prompt, *cvec;
   float *pool_text, *pool_prompt, *pt, *pp, *ctx_pre, *tfeat, *t1, *temb, *coef;
+  float *gfeat, *g1, *gemb;   // guidance-scale embedding of the guidance-conditioned student
   // denoiser
   float *mod, *x, *xmid, *h, *noise;
   bf16 *xin, *u, *u3, *qkv, *att, *ffh;
@@ -424,7 +425,7 @@ template <int MODE>
 static int launch_gemmln3(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
                           const GemmLnParams& p) {
   if (p.K % (GEMM_BK * GLN3_STAGES)) return fail(H, STZ_E_SHAPE, "gemmln3 needs K %% %d == 0", GEMM_BK * GLN3_STAGES);
-  if (2 * ((GEMM_BM - 1 + p.rows_per_utt - 1) / p.rows_per_utt + 1) > GLN3_MAX_SEQ)
+  if ((p.single ? 1 : 2) * ((GEMM_BM - 1 + p.rows_per_utt - 1) / p.rows_per_utt + 1) > GLN3_MAX_SEQ)
     return fail(H, STZ_E_SHAPE, "gemmln3: a 128-row tile spans too many sequences (rows_per_utt %d)", p.rows_per_utt);
   CUtensorMap ta, tb, tu, th;
   if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
@@ -527,14 +528,14 @@ static int linear_f32(stz_handle* H, cudaStream_t st, int act, const float* X1, 
 }
 
 static int ln_mod(stz_handle* H, cudaStream_t st, const float* h, int rows, int D, const float* mod, int n_mod,
-                  int shift_off, int scale_off, int rows_per_utt, bf16* out, int split3 = 0) {
+                  int shift_off, int scale_off, int rows_per_utt, bf16* out, int split3 = 0, int single = 0) {
   dim3 grid(cdiv(rows, 8));
   ProfScope ps(H, st, PC_LN, (double)rows * D * 6.0);  // fp32 in + bf16 out
   switch (D / 128) {
-    case 1: launch_k(ln_mod_kernel<1>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
-    case 2: launch_k(ln_mod_kernel<2>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
-    case 4: launch_k(ln_mod_kernel<4>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
-    case 8: launch_k(ln_mod_kernel<8>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3); break;
+    case 1: launch_k(ln_mod_kernel<1>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3, single); break;
+    case 2: launch_k(ln_mod_kernel<2>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3, single); break;
+    case 4: launch_k(ln_mod_kernel<4>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3, single); break;
+    case 8: launch_k(ln_mod_kernel<8>, grid, 256, 0, st, h, rows, mod, n_mod, shift_off, scale_off, rows_per_utt, out, split3, single); break;
     default: return fail(H, STZ_E_SHAPE, "d_model %d unsupported by ln_mod", D);
   }
   KCHECK(H);
@@ -590,6 +591,7 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   WANT(ctx_pre, (BT + BP) * d, float);
   WANT(tfeat, (size_t)E * c.d_time, float); WANT(t1, (size_t)E * d, float); WANT(temb, (size_t)E * d, float);
   WANT(coef, (size_t)E * 8, float);
+  WANT(gfeat, c.d_time, float); WANT(g1, d, float); WANT(gemb, d, float);
   const size_t mod_rows = mod_rows_req > w.mod_rows ? (mod_rows_req > NS ? mod_rows_req : NS) : (w.mod_rows > NS ? w.mod_rows : NS);
   WANT(mod, mod_rows * n_mod, float);   // few-step samplers: every evaluation's modulations at once
   WANT(x, BK * Ds, float); WANT(xmid, BK * Ds, float); WANT(h, R * d, float);
@@ -628,6 +630,7 @@ struct EvalPlan {
   std::vector<double> sigma;   // sigma fed to the denoiser at eval e
   std::vector<float> coef;     // [E][8]
   std::vector<float> tfeat;    // [E][d_time]
+  std::vector<float> gfeat;    // [d_time] features of the guidance scale (guidance-conditioned student)
   double sigma0 = 0, cin0 = 0;
 };
 
@@ -656,7 +659,7 @@ static EvalPlan make_plan(const stz_config& c, int steps, int kind, float cfg_sc
     const float row[8] = {(float)cx, (float)cm, (float)cF, (float)cn, (float)cin_next, cfg_scale, (float)dest, 0.f};
     pl.coef.insert(pl.coef.end(), row, row + 8);
   };
-  if (kind == STZ_SAMPLER_STUDENT) {
+  if (kind == STZ_SAMPLER_STUDENT || kind == STZ_SAMPLER_GUIDED) {   // the same Euler steps; guided: F is the single-branch network output
     std::vector<double> s = karras(steps, c.sigma_min, c.sigma_max, c.rho);
     s.push_back(0.0);
     for (int i = 0; i < steps; ++i) {
@@ -687,6 +690,11 @@ static EvalPlan make_plan(const stz_config& c, int steps, int kind, float cfg_sc
   pl.sigma0 = pl.sigma[0];
   { double a, b; precond(pl.sigma0, sd, &a, &b, &pl.cin0); }
   const int half = c.d_time / 2;
+  {  // sinusoidal features of omega / 4 (same frequencies as the time features)
+    const double cg = (double)cfg_scale / 4.0;
+    for (int i = 0; i < half; ++i) pl.gfeat.push_back((float)sin(cg * exp(log(100.0) * i / (half > 1 ? half - 1 : 1))));
+    for (int i = 0; i < half; ++i) pl.gfeat.push_back((float)cos(cg * exp(log(100.0) * i / (half > 1 ? half - 1 : 1))));
+  }
   for (double sg : pl.sigma) {
     const double cn = log(sg) / 4.0;
     for (int i = 0; i < half; ++i) pl.tfeat.push_back((float)sin(cn * exp(log(100.0) * i / (half > 1 ? half - 1 : 1))));
@@ -701,7 +709,7 @@ static EvalPlan make_plan(const stz_config& c, int steps, int kind, float cfg_sc
 //   tfeat_out [E][d_time] fp32, init_out [2] fp64 = (sigma_0, c_in(sigma_0)).
 extern "C" int stz_debug_plan(const stz_config* cfg, int steps, int sampler_kind, float cfg_scale, double* sigma_out,
                               float* coef_out, float* tfeat_out, double* init_out) {
-  if (!cfg || steps < 1 || steps > 1024 || (sampler_kind != STZ_SAMPLER_STUDENT && sampler_kind != STZ_SAMPLER_TEACHER)) return STZ_E_ARG;
+  if (!cfg || steps < 1 || steps > 1024 || sampler_kind < STZ_SAMPLER_STUDENT || sampler_kind > STZ_SAMPLER_GUIDED) return STZ_E_ARG;
   const EvalPlan pl = make_plan(*cfg, steps, sampler_kind, cfg_scale);
   if (sigma_out) std::copy(pl.sigma.begin(), pl.sigma.end(), sigma_out);
   if (coef_out) std::copy(pl.coef.begin(), pl.coef.end(), coef_out);
@@ -930,7 +938,7 @@ extern "C" int stz_graph_count(const stz_handle* h, int64_t* captures_total) {
 extern "C" int stz_reserve(stz_handle* H, int max_B, int max_T, int max_P, int max_steps, int sampler_kind) {
   if (!H) return STZ_E_ARG;
   if (max_B < 1 || max_T < 1 || max_P < 1 || max_steps < 1 || max_steps > 1024) return fail(H, STZ_E_ARG, "bad sizes");
-  if (sampler_kind != STZ_SAMPLER_STUDENT && sampler_kind != STZ_SAMPLER_TEACHER) return fail(H, STZ_E_ARG, "bad sampler kind %d", sampler_kind);
+  if (sampler_kind < STZ_SAMPLER_STUDENT || sampler_kind > STZ_SAMPLER_GUIDED) return fail(H, STZ_E_ARG, "bad sampler kind %d", sampler_kind);
   if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
   const int E = sampler_kind == STZ_SAMPLER_TEACHER ? 2 * max_steps : max_steps;
   const int slices = sampler_kind == STZ_SAMPLER_TEACHER ? max_steps + 1 : 1;
@@ -1077,7 +1085,8 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
   int n_keys = 0;
   for (int i = 0; i < ap.nseg; ++i) n_keys += ap.seg[i].n;
   ProfScope ps(H, st, PC_ATTN, 4.0 * B * H->cfg.n_heads * ap.n_q * (double)n_keys * ATT_DH);
-  const int n_style = ap.n_q / 2, dm = H->cfg.d_model;
+  const int n_style = ap.single ? ap.n_q : ap.n_q / 2, dm = H->cfg.d_model;
+  const int nbr = ap.single ? 1 : 2;     // branches interleaved in the rows of one utterance
   const bool self = ap.nseg == 1 && ap.seg[0].rule == KEY_SAME_BRANCH;
   const bool cross3 = ap.nseg == 3 && ap.seg[0].rule == KEY_ALL && ap.seg[1].rule == KEY_COND && ap.seg[2].rule == KEY_UNCOND && ap.seg[2].n == 1;
   const int T8 = cross3 ? (ap.seg[0].n + 7) / 8 * 8 : 0, P8 = cross3 ? (ap.seg[1].n + 7) / 8 * 8 : 0;
@@ -1087,15 +1096,15 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
     memset(&tp, 0, sizeof tp); memset(&tn, 0, sizeof tn);
     const int qcols = self ? (int)(ap.seg[0].v - ap.q) + dm : dm;
     {  // Q (and, for self-attention, K / V): (column, branch, token) view of the R-layout buffer
-      const cuuint64_t gd[3] = {(cuuint64_t)qcols, 2, (cuuint64_t)B * n_style};
-      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 4};
+      const cuuint64_t gd[3] = {(cuuint64_t)qcols, (cuuint64_t)nbr, (cuuint64_t)B * n_style};
+      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 2 * nbr};
       const cuuint32_t bx[3] = {64, 1, 64};
       if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
     }
     tt = tq;
     AttnTcParams tp_{};
     tp_.out = ap.out; tp_.ldo = ap.ldo; tp_.n_q = ap.n_q; tp_.n_heads = H->cfg.n_heads; tp_.n_units = B * H->cfg.n_heads;
-    tp_.self = self ? 1 : 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2;
+    tp_.self = self ? 1 : 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single;
     if (self) {
       tp_.col_k = (int)(ap.seg[0].k - ap.q); tp_.col_v = (int)(ap.seg[0].v - ap.q);
     } else {
@@ -1118,8 +1127,8 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
     // long text: streaming tcgen05 attention over 128-key blocks (attention_tcs_kernel)
     CUtensorMap tq, tt, tp, tn;
     {
-      const cuuint64_t gd[3] = {(cuuint64_t)dm, 2, (cuuint64_t)B * n_style};
-      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 4};
+      const cuuint64_t gd[3] = {(cuuint64_t)dm, (cuuint64_t)nbr, (cuuint64_t)B * n_style};
+      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 2 * nbr};
       const cuuint32_t bx[3] = {64, 1, 64};
       if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
     }
@@ -1135,12 +1144,13 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
     }
     AttnTcParams tp_{};
     tp_.out = ap.out; tp_.ldo = ap.ldo; tp_.n_q = ap.n_q; tp_.n_heads = H->cfg.n_heads; tp_.n_units = B * H->cfg.n_heads;
-    tp_.self = 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2;
+    tp_.self = 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single;
     tp_.T = sg[0].n; tp_.P = sg[1].n; tp_.T8 = T8; tp_.P8 = P8; tp_.col_k = 0; tp_.col_v = dm;
     tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
     const int units = tp_.n_units;
     launch_k(attention_tcs_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATS_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
   } else {
+    if (ap.single) return fail(H, STZ_E_SHAPE, "the guidance-conditioned student needs the tcgen05 attention kernels (n_style <= 64, prompt <= 127 tokens)");
     launch_k(attention_kernel, grid, 2 * cdiv(ap.n_q / 2, 16) * 32, ATT_SMEM_BYTES, st, ap);   // ceil(K / 16) warps per CFG branch
   }
   KCHECK(H);
@@ -1150,13 +1160,15 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
 // One denoiser evaluation + fused guidance/sampler update (a-4, a-5, a-6) for utterances [b0, b0 + nb) of a batch of
 // Btot.  Utterances never interact, so the evaluation loop of a batch may run as several independent chains
 // (sub-ranges) on parallel graph branches: one chain's launch gaps, prologues and tails are filled by the others.
+// nbr = 2: the CFG pair layout (row = (b*K + k)*2 + branch, conditional / unconditional batched in one launch); nbr = 1: the
+// guidance-conditioned student (row = b*K + k, one branch, the guidance scale enters through the conditioning vector).
 static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int nb, int T, int P, const uint8_t* tmask,
-                    const uint8_t* pmask) {
+                    const uint8_t* pmask, int nbr) {
   const stz_config& c = H->cfg;
   const Workspace& w = H->ws;
   const int d = c.d_model, L = c.n_layers, K = c.n_style, Ds = c.d_style, n_mod = (9 * L + 2) * d;
-  const int R = 2 * nb * K, NS = 2 * nb, impl = H->gemm_impl;
-  const size_t r0 = (size_t)2 * b0 * K, s0 = (size_t)2 * b0;     // first activation row / first sequence of this chain
+  const int R = nbr * nb * K, NS = nbr * nb, impl = H->gemm_impl, single = nbr == 1 ? 1 : 0;
+  const size_t r0 = (size_t)nbr * b0 * K, s0 = (size_t)nbr * b0;     // first activation row / first sequence of this chain
   float* mod = w.mod + s0 * n_mod;
   float* h = w.h + r0 * d;
   bf16 *u = w.u + r0 * d, *u3 = w.u3 + r0 * 3 * d, *qkv = w.qkv + r0 * 3 * d, *att = w.att + r0 * d, *ffh = w.ffh + r0 * c.d_ff;
@@ -1165,17 +1177,17 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   if (pmask) pmask += (size_t)b0 * P;
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)(d / c.n_heads));
   GemmParams base{};
-  base.mod = mod; base.n_mod = n_mod; base.rows_per_utt = 2 * K; base.n_style = K;
+  base.mod = mod; base.n_mod = n_mod; base.rows_per_utt = nbr * K; base.n_style = K; base.single = single;
   // ablation bits: 1 self-attn, 2 cross-attn, 4 ln_mod, 8 qkv, 16 attention out-projections, 32 q2, 64 ff1, 128 ff2, 256 mod,
   // 512 empty dependent nodes, 1024 cross-attention of every layer reads layer 0's K/V (L2-resident)
   const int ab = H->ablate;
 
   if (w.mod_hoisted) {   // all evaluations' modulations were computed by one GEMM before the loop (sample_style_impl)
-    mod = w.mod + ((size_t)e * 2 * Btot + s0) * n_mod;
+    mod = w.mod + ((size_t)e * nbr * Btot + s0) * n_mod;
     base.mod = mod;
   } else if (!(ab & 256)) {  // AdaLN modulations of this eval: mod[NS, n_mod] = c[e] · Wmod^T + b
     GemmParams p = base;
-    p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * 2 * Btot + (int)s0; p.bias = W32(H, "mod.b"); p.out = mod; p.ldo = n_mod;
+    p.M = NS; p.N = n_mod; p.K = d; p.a_row0 = e * nbr * Btot + (int)s0; p.bias = W32(H, "mod.b"); p.out = mod; p.ldo = n_mod;
     RET(gemm<EPI_F32>(H, st, impl, w.cvec, d, w.E * 2 * w.B + 128, WBF(H, "mod.w"), p));
   }
   // GEMM + residual + AdaLN in one kernel.  Product: gemmln3_kernel (fuse_ln = 3) whenever its shape constraints hold
@@ -1183,7 +1195,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   // fuse_ln = 0, the GEMM + ln_mod_kernel pair.
   int fuse_mode = (impl == 0 && d == GLN_N) ? H->fuse_ln : 0;
   if (fuse_mode != 3 && fuse_mode != 4) fuse_mode = 0;
-  if (fuse_mode != 0 && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || 2 * ((GEMM_BM - 1 + 2 * K - 1) / (2 * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
+  if (fuse_mode != 0 && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || nbr * ((GEMM_BM - 1 + nbr * K - 1) / (nbr * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
   // below ~36 row tiles (B < ~46 at K = 50) the separate LayerNorm kernel is cheap and the fused kernel's long serial
   // epilogue loses (measured: -2 .. -4 % at B = 16 / 32); from 36 to ~140 tiles (one to 1.9 waves of CTA pairs) it wins
   // 1 .. 7 % (B = 48 .. 160); from there to ~350 tiles (two to four waves) its one-tile-per-CTA-pair grid quantises worse
@@ -1197,7 +1209,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   const bool fused = fuse_mode != 0;
   H->last_fuse_mode = fuse_mode;
   GemmLnParams lb{};
-  lb.M = R; lb.h = h; lb.mod = mod; lb.n_mod = n_mod; lb.rows_per_utt = 2 * K; lb.pos = W32(H, "pos"); lb.n_style = K;
+  lb.M = R; lb.h = h; lb.mod = mod; lb.n_mod = n_mod; lb.rows_per_utt = nbr * K; lb.pos = W32(H, "pos"); lb.n_style = K; lb.single = single;
   // residual GEMM of a sub-layer followed by the AdaLN of the next one: (gate, shift, scale) offsets into mod
   auto res_ln = [&](const bf16* A, int Kc, const bf16* Wt, const float* bias, int gate_off, int ln_off, bool last) -> int {
     if (fused) {
@@ -1209,7 +1221,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     p.M = R; p.N = d; p.K = Kc; p.bias = bias; p.out = h; p.ldo = d; p.gate_off = gate_off;
     if (!(ab & (Kc == d ? 16 : 128))) RET(gemm<EPI_GATE_RES>(H, st, impl, A, Kc, R, Wt, p));
     if (ab & 4) return 0;
-    return ln_mod(H, st, h, R, d, mod, n_mod, ln_off, ln_off + d, 2 * K, last ? u3 : u, last ? 1 : 0);
+    return ln_mod(H, st, h, R, d, mod, n_mod, ln_off, ln_off + d, nbr * K, last ? u3 : u, last ? 1 : 0, single);
   };
   {  // h = x_in · Win^T + b + pos, u = AdaLN_1 of layer 0
     if (fused) {
@@ -1220,7 +1232,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
       GemmParams p = base;
       p.M = R; p.N = d; p.K = 3 * Ds; p.bias = W32(H, "in.b"); p.out = h; p.ldo = d; p.pos = W32(H, "pos");
       RET(gemm<EPI_F32_POS>(H, st, impl, xin, 3 * Ds, R, H->w_in3, p));
-      RET(ln_mod(H, st, h, R, d, mod, n_mod, 0, d, 2 * K, u));
+      RET(ln_mod(H, st, h, R, d, mod, n_mod, 0, d, nbr * K, u, 0, single));
     }
   }
   for (int l = 0; l < L; ++l) {
@@ -1234,8 +1246,8 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
     }
     if (!(ab & 1)) {
       AttnParams ap{};
-      ap.q = qkv; ap.ldq = 3 * d; ap.out = att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 1; ap.scale_log2 = scale_log2;
-      ap.seg[0] = AttnSeg{qkv + d, qkv + 2 * d, 3 * d, 2 * K, 2 * K, nullptr, KEY_SAME_BRANCH};
+      ap.q = qkv; ap.ldq = 3 * d; ap.out = att; ap.ldo = d; ap.n_q = nbr * K; ap.nseg = 1; ap.scale_log2 = scale_log2; ap.single = single;
+      ap.seg[0] = AttnSeg{qkv + d, qkv + 2 * d, 3 * d, nbr * K, nbr * K, nullptr, KEY_SAME_BRANCH};
       RET(attention(H, st, ap, nb));
     }
     RET(res_ln(att, d, WBF(H, pf + "o.w"), W32(H, pf + "o.b"), mo + 2 * d, mo + 3 * d, false));
@@ -1252,7 +1264,7 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
       const int lk = (ab & 1024) ? 0 : l;   // attribution: every layer reads layer 0's K/V (L2-resident) -> cost of the HBM misses
       const bf16* kt = w.kv_text + ((size_t)b0 * T * L + lk) * 2 * d;
       const bf16* kp = w.kv_prompt + ((size_t)b0 * P * L + lk) * 2 * d;
-      ap.q = qkv; ap.ldq = d; ap.out = att; ap.ldo = d; ap.n_q = 2 * K; ap.nseg = 3; ap.scale_log2 = scale_log2;
+      ap.q = qkv; ap.ldq = d; ap.out = att; ap.ldo = d; ap.n_q = nbr * K; ap.nseg = 3; ap.scale_log2 = scale_log2; ap.single = single;
       ap.seg[0] = AttnSeg{kt, kt + d, ldkv, T, T, tmask, KEY_ALL};
       ap.seg[1] = AttnSeg{kp, kp + d, ldkv, P, P, pmask, KEY_COND};
       ap.seg[2] = AttnSeg{H->kv_null + l * 2 * d, H->kv_null + l * 2 * d + d, ldkv, 1, 0, nullptr, KEY_UNCOND};
@@ -1288,9 +1300,10 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   if (!text || !prompt || !out) return fail(H, STZ_E_ARG, "null tensor argument");
   if (!noise && !H->noise_seeded) return fail(H, STZ_E_ARG, "noise is NULL and no seed was set (stz_set_noise_seed)");
   if (B < 1 || T < 1 || P < 1 || steps < 1 || steps > 1024) return fail(H, STZ_E_ARG, "bad sizes B=%d T=%d P=%d steps=%d", B, T, P, steps);
-  if (kind != STZ_SAMPLER_STUDENT && kind != STZ_SAMPLER_TEACHER) return fail(H, STZ_E_ARG, "bad sampler kind %d", kind);
+  if (kind != STZ_SAMPLER_STUDENT && kind != STZ_SAMPLER_TEACHER && kind != STZ_SAMPLER_GUIDED) return fail(H, STZ_E_ARG, "bad sampler kind %d", kind);
   const int E = kind == STZ_SAMPLER_TEACHER ? 2 * steps : steps;
   const int slices = kind == STZ_SAMPLER_TEACHER ? steps + 1 : 1;
+  const int nbr = kind == STZ_SAMPLER_GUIDED ? 1 : 2;      // the guidance-conditioned student runs ONE branch
   const bool graphed = runs_graphed(H);
   // length bucket: the call runs with T = bucket and a key-padding mask over the extra positions
   const int T_src = T;
@@ -1304,7 +1317,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     tmask = w.st_tmask;
   }
   const int d = c.d_model, L = c.n_layers, K = c.n_style, Ds = c.d_style;
-  const int NS = 2 * B, impl = H->gemm_impl;
+  const int NS = nbr * B, impl = H->gemm_impl;
   const size_t BK = (size_t)B * K;
   H->cur_launches = 0;
 
@@ -1338,7 +1351,14 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
   if (H->wait_prompt) { CK(H, cudaStreamWaitEvent(st, H->cur_ev_prompt, 0)); H->wait_prompt = false; }
   launch_k(cast_pool_kernel, dim3(B, c.d_prompt / 128), 256, 0, st, prompt, pmask, w.prompt_bf, w.pool_prompt, P, c.d_prompt, P); KCHECK(H);
   RET(linear_f32(H, st, ACT_NONE, w.pool_prompt, c.d_prompt, c.d_prompt, nullptr, 0, 0, W32(H, "pprompt.w"), W32(H, "pprompt.b"), w.pp, d, B, d));
-  launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d); KCHECK(H);
+  const float* gemb = nullptr;
+  if (nbr == 1) {   // guidance-scale embedding g = W_g2 SiLU(W_g1 feat(omega) + b_g1) + b_g2, added to the conditioning vector
+    CK(H, cudaMemcpyAsync(w.gfeat, pl.gfeat.data(), pl.gfeat.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    RET(linear_f32(H, st, ACT_SILU, w.gfeat, c.d_time, c.d_time, nullptr, 0, 0, W32(H, "gs.w1"), W32(H, "gs.b1"), w.g1, d, 1, d));
+    RET(linear_f32(H, st, ACT_NONE, w.g1, d, d, nullptr, 0, 0, W32(H, "gs.w2"), W32(H, "gs.b2"), w.gemb, d, 1, d));
+    gemb = w.gemb;
+  }
+  launch_k(cvec_kernel, ew_grid((size_t)E * NS * d), 256, 0, st, w.temb, w.pt, w.pp, W32(H, "null_pp"), w.cvec, E, NS, d, nbr == 1 ? 1 : 0, gemb); KCHECK(H);
   w.mod_hoisted = hoist_mod(c, B, E) && !(H->ablate & 256);
   if (w.mod_hoisted) {   // AdaLN modulations of every evaluation: mod[E * NS, n_mod] = c · Wmod^T + b
     const int n_mod = (9 * L + 2) * d;
@@ -1385,7 +1405,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     // loop read the call's constants (context K/V, modulations) before their griddepcontrol.wait (attention_tc2_kernel's
     // early K/V boxes); this launch guarantees the conditioning prep has completed before any of them can start, also
     // for tiny grids where a whole chain of waiting kernels is co-resident.
-    launch_k_nopdl(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0);
+    launch_k_nopdl(init_state_kernel, ew_grid(BK * Ds / 4), 256, 0, st, noise, w.x, w.xin, BK, Ds, (float)pl.sigma0, (float)pl.cin0, nbr);
     KCHECK(H);
   }
   H->launches += H->cur_launches;
@@ -1393,7 +1413,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
 
   // ---- the evaluation loop: one CUDA graph per (B, T, P, E, kind) ----------------------------
   if (graphed) {
-    auto key = std::make_tuple(B, T, P, E, kind * 2 + (tmask ? 1 : 0) + (pmask ? 4 : 0));
+    auto key = std::make_tuple(B, T, P, E, kind * 4 + (tmask ? 1 : 0) + (pmask ? 2 : 0));
     auto it = H->graphs.find(key);
     // the graph bakes in the mask pointers: masks are copied into library-owned staging first
     const uint8_t* tm = nullptr; const uint8_t* pm = nullptr;
@@ -1417,7 +1437,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
       for (int e = 0; e < E && rc == 0; ++e)
         for (int ch = 0; ch < nch && rc == 0; ++ch) {
           const int b0 = (int)((long long)B * ch / nch), b1 = (int)((long long)B * (ch + 1) / nch);
-          rc = run_eval(H, ch == 0 ? H->stream : H->chain_stream[ch], e, B, b0, b1 - b0, T, P, tm, pm);
+          rc = run_eval(H, ch == 0 ? H->stream : H->chain_stream[ch], e, B, b0, b1 - b0, T, P, tm, pm, nbr);
         }
       for (int ch = 1; ch < nch && rc == 0; ++ch) {
         if (cudaEventRecord(H->join_ev[ch], H->chain_stream[ch]) != cudaSuccess || cudaStreamWaitEvent(H->stream, H->join_ev[ch], 0) != cudaSuccess)
@@ -1446,7 +1466,7 @@ static int sample_style_impl(stz_handle* H, const float* text, const uint8_t* tm
     CK(H, cudaGraphLaunch(it->second.exec, st));
     H->launches += it->second.launches;
   } else {
-    for (int e = 0; e < E; ++e) RET(run_eval(H, st, e, B, 0, B, T, P, tmask, pmask));
+    for (int e = 0; e < E; ++e) RET(run_eval(H, st, e, B, 0, B, T, P, tmask, pmask, nbr));
     H->launches += H->cur_launches;
     H->cur_launches = 0;
   }

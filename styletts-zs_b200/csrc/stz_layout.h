@@ -72,6 +72,9 @@ inline std::vector<WeightEntry> build_layout(const stz_config& c, size_t* total)
   add("pros.h1.w", 2 * dp * (dh + ds)); add("pros.h1.b", 2 * dp);
   add("pros.f0.w", dp); add("pros.f0.b", 1);
   add("pros.en.w", dp); add("pros.en.b", 1);
+  // guidance-scale embedding of the guidance-conditioned student
+  add("gs.w1", d * c.d_time); add("gs.b1", d);
+  add("gs.w2", d * d); add("gs.b2", d);
   if (total) *total = off;
   return E;
 }

@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from .spec import (ABI_VERSION, DEFAULT, SAMPLER_STUDENT, SAMPLER_TEACHER, StzConfig, n_noise_slices,
+from .spec import (ABI_VERSION, DEFAULT, SAMPLER_GUIDED, SAMPLER_STUDENT, SAMPLER_TEACHER, StzConfig, n_noise_slices,
                    weight_offsets)
 
 # STZ_LIBRARY: an alternative build of the same sources (the timeline build libstz_trace.so of tools/*_trace.py)
@@ -139,6 +139,8 @@ def _kind(sampler) -> int:
         return SAMPLER_STUDENT
     if sampler in ("teacher", SAMPLER_TEACHER):
         return SAMPLER_TEACHER
+    if sampler in ("guided", SAMPLER_GUIDED):
+        return SAMPLER_GUIDED
     raise ValueError(f"unknown sampler {sampler!r}")
 
 

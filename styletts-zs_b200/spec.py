@@ -23,6 +23,7 @@ ABI_VERSION = 1
 # sampler kinds (C-ABI enum stz_sampler_kind)
 SAMPLER_STUDENT = 0   # distilled few-step student: deterministic Euler on a Karras grid + terminal 0
 SAMPLER_TEACHER = 1   # undistilled teacher: ADPM2 (2 denoiser evals / step, ancestral noise)
+SAMPLER_GUIDED = 2    # guidance-conditioned student: cfg_scale as an input embedding, ONE branch per step
 
 
 @dataclass(frozen=True)
@@ -137,6 +138,9 @@ def weight_entries(cfg: StzConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
     a(("pros.h1.w", (2 * cfg.d_pros, dh + ds), "w")); a(("pros.h1.b", (2 * cfg.d_pros,), "b"))
     a(("pros.f0.w", (cfg.d_pros,), "w")); a(("pros.f0.b", (1,), "b"))
     a(("pros.en.w", (cfg.d_pros,), "w")); a(("pros.en.b", (1,), "b"))
+    # --- guidance-scale embedding of the guidance-conditioned student, appended ---------------
+    a(("gs.w1", (d, cfg.d_time), "w")); a(("gs.b1", (d,), "b"))
+    a(("gs.w2", (d, d), "w")); a(("gs.b2", (d,), "b"))
     return E
 
 

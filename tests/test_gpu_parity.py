@@ -675,3 +675,47 @@ def test_prosody_heads_cfg2_size_properties(path):
         assert int(flb[0]) == int(fl[b])
         k = int(fl[b])
         assert float((f0b[0, :k] - f0[b, :k]).abs().max()) < 1e-3 and float((enb[0, :k] - en[b, :k]).abs().max()) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# guidance-conditioned student: one branch per step, the guidance scale as an input embedding
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,P,steps,tlen", [(1, 16, 50, 1, None), (3, 40, 33, 4, (10, 40)), (2, 200, 50, 2, (90, 200)),
+                                                (64, 64, 50, 4, None), (5, 512, 50, 2, (16, 512))])
+def test_guided_student_vs_oracle(path, oracle, B, T, P, steps, tlen):
+    """sampler='guided' against the oracle: resident and streaming attention in the single-branch row layout, masks, odd
+    batch sizes, and the cfg2 size (B = 64: 25 row tiles)."""
+    inp = stz.synthetic_inputs(CFG, B, T, P=P, steps=steps, seed=300 + T, var_len=tlen)
+    tm = inp["text_mask"] if tlen else None
+    pm = inp["prompt_mask"].clone()
+    if B > 1:
+        pm[1, P // 2:] = False
+    z = path.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 1.8, text_mask=tm, prompt_mask=pm, noise=inp["noise"],
+                          sampler="guided")
+    z_ref = oracle.sample_style(inp["text_emb"], inp["prompt_feats"], steps, 1.8, text_mask=tm, prompt_mask=pm,
+                                noise=inp["noise"], sampler="guided")
+    assert bool(torch.isfinite(z).all())
+    assert rel(z, z_ref) < TOL_STYLE
+
+
+def test_guided_student_properties(path):
+    """The guidance scale matters (it is an input), the result is deterministic, batch-invariant, and graph == eager; the
+    CFG student on the same inputs is a different function (the two share no code path in the sampler epilogue)."""
+    B, T = 8, 64                             # an exact length bucket: the graphed and the eager call run the same shapes
+    inp = stz.synthetic_inputs(CFG, B, T, steps=4, seed=12)
+    run = lambda w, **kw: path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, w, noise=inp["noise"], sampler="guided", **kw)
+    z = run(2.0)
+    assert torch.equal(z, run(2.0))
+    assert rel(run(3.0), z) > 1e-3
+    path.set_option("use_graph", 0)
+    z_eager = run(2.0)
+    path.set_option("use_graph", 1)
+    assert torch.equal(z, z_eager)
+    zi = path.sample_style(inp["text_emb"][3:4], inp["prompt_feats"][3:4], 4, 2.0, noise=inp["noise"][:, 3:4], sampler="guided")
+    assert rel(zi[0], z[3]) < 5e-3
+    path.set_option("fuse_ln", 4)           # the fused GEMM + AdaLN kernel in the single-branch layout
+    z4 = run(2.0)
+    path.set_option("fuse_ln", 3)
+    assert rel(z4, z) < 5e-3
+    z_cfg = path.sample_style(inp["text_emb"], inp["prompt_feats"], 4, 2.0, noise=inp["noise"])
+    assert rel(z_cfg, z) > 1e-2
