@@ -65,7 +65,7 @@ def workload_config(n_gpus: int):
 # ----------------------------------------------------------------------------------------------
 # algorithmic work
 # ----------------------------------------------------------------------------------------------
-def sampler_flops(cfg, B: int, T, P: int, evals: int) -> float:
+def sampler_flops(cfg, B: int, T, P: int, evals: int, branches: int = 2) -> float:
     """Algorithmic flops of one sample_style call.  T: an int or a list of per-utterance valid lengths (padding is not
     credited).  Per sequence-evaluation: L [2K(6d^2 + 2 d d_ff) + 4Kd(K + S) + 18 d^2] + 4 K Ds d + 4 d^2, S = T + P for
     the conditional branch, T + 1 for the unconditional one; once per utterance: 2 S d^2 + L 4 S d^2 (context tokens)."""
@@ -73,7 +73,7 @@ def sampler_flops(cfg, B: int, T, P: int, evals: int) -> float:
     lens = [T] * B if isinstance(T, int) else list(T)
     total = 0.0
     for t in lens:
-        for S in (t + P, t + 1):
+        for S in (t + P, t + 1)[:branches]:      # branches = 1: the guidance-conditioned student (conditional branch only)
             total += evals * (L * (2 * K * (6 * d * d + 2 * d * dff) + 4 * K * d * (K + S) + 18 * d * d) + 4 * K * Ds * d + 4 * d * d)
         S = t + P
         total += 2 * S * d * d + L * 4 * S * d * d
@@ -329,9 +329,13 @@ def config_legs(torch, stz, path, cfg, flush):
                      desc="undistilled teacher: 32 ADPM2 steps (64 CFG evaluations), batch 32"),
         "cfg4": dict(B=256, T=512, steps=4, sampler="student", var_len=(16, 512), iters=4, oracle_B=16, pred=True,
                      desc="variable-length text (16..512 tokens, padding masks), batch 256, distilled 4-step sampler + predictor"),
+        # the cfg2 workload with the guidance-conditioned student (one branch per step)
+        "cfg2_guided_student": dict(B=64, T=64, steps=4, sampler="guided", var_len=None, iters=8, oracle_B=16, pred=True,
+                                    desc="cfg2's batch with the guidance-conditioned student: guidance scale as an input "
+                                         "embedding, ONE branch per step (4 denoiser sequence-evals per utterance) + predictor"),
     }
     for name, sp in specs.items():
-        kind = stz.SAMPLER_TEACHER if sp["sampler"] == "teacher" else stz.SAMPLER_STUDENT
+        kind = {"teacher": stz.SAMPLER_TEACHER, "guided": stz.SAMPLER_GUIDED}.get(sp["sampler"], stz.SAMPLER_STUDENT)
         inp = stz.synthetic_inputs(cfg, sp["B"], sp["T"], steps=sp["steps"], sampler=kind, seed=1234, var_len=sp["var_len"])
         dev = {k: inp[k].cuda() for k in ("text_emb", "prompt_feats", "noise")}
         tm = inp["text_mask"].cuda() if sp["var_len"] else None
@@ -351,7 +355,8 @@ def config_legs(torch, stz, path, cfg, flush):
         s_ms = timed_steps(torch, samp, sp["iters"], flush)
         ms, s_ms = sum(ms) / len(ms), sum(s_ms) / len(s_ms)
         E = 2 * sp["steps"] if sp["sampler"] == "teacher" else sp["steps"]
-        fl = sampler_flops(cfg, sp["B"], inp["lens"].tolist() if sp["var_len"] else sp["T"], cfg.n_style, E)
+        fl = sampler_flops(cfg, sp["B"], inp["lens"].tolist() if sp["var_len"] else sp["T"], cfg.n_style, E,
+                           branches=1 if sp["sampler"] == "guided" else 2)
         frames = int(last["d"].sum()) if sp["pred"] else None
         # the oracle on the first oracle_B utterances of the same batch (utterances are independent)
         nb = sp["oracle_B"]
@@ -372,6 +377,29 @@ def config_legs(torch, stz, path, cfg, flush):
                      "cpu_oracle": {"utt_per_s": nb / o_s, "seconds": o_s, "threads": threads,
                                     "sample": f"the first {nb} of the batch's {sp['B']} utterances, one pass, fp32 PyTorch oracle"},
                      "speedup_vs_cpu_oracle": (sp["B"] / ms * 1e3) / (nb / o_s)}
+    # the prosody heads (F0 / energy over the length-regulated frames) on cfg2's batch
+    inp = stz.synthetic_inputs(cfg, WORK["B"], WORK["T"], steps=1, seed=1234)
+    text = inp["text_emb"].cuda()
+    style = (0.7 * torch.randn(WORK["B"], cfg.n_style, cfg.d_style, generator=torch.Generator().manual_seed(5))).cuda()
+    F_max = 1536
+    pros = lambda: last.__setitem__("p", path.predict_prosody(text, style, max_frames=F_max))
+    last = {}
+    for _ in range(2):
+        pros()
+    ms = timed_steps(torch, pros, 5, flush)
+    ms = sum(ms) / len(ms)
+    frames = int(last["p"][2].sum())
+    nb = 4
+    t0 = time.perf_counter()
+    oracle.predict_prosody(inp["text_emb"][:nb], style[:nb].cpu(), max_frames=F_max)
+    o_s = time.perf_counter() - t0
+    out["prosody_heads"] = {"workload": f"predict_prosody on cfg2's batch: duration predictor + length regulator + BiLSTM over the frames + F0 / "
+                                        f"energy heads, {WORK['B']} utterances, {frames} frames in total (F_max {F_max})",
+                            "ms": ms, "utt_per_s": WORK["B"] / ms * 1e3, "frames_per_s": frames / ms * 1e3,
+                            "path_rtf": (ms * 1e-3) / (frames / FRAMES_PER_S) if frames else None,
+                            "cpu_oracle": {"utt_per_s": nb / o_s, "seconds": o_s, "threads": threads,
+                                           "sample": f"the first {nb} utterances, one pass, fp32 PyTorch oracle"},
+                            "bound": "the frame BiLSTM's serial chain: longest utterance's frame count x ~1.9 us per recurrent step"}
     return out
 
 

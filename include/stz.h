@@ -210,6 +210,12 @@ int stz_get_option(const stz_handle* h, const char* key, int* value);
  * 4 LSTM recurrence, 5 predictor elementwise, 6 other. */
 int stz_profile_read(stz_handle* h, int kernel_class, double* ms, double* work, int64_t* launches);
 
+/* Own bounds checking (compute-sanitizer is not available on every pool): set_option("guard_bytes", n > 0) re-plans the
+ * library's workspace arenas with an n-byte poisoned gap after every internal buffer; stz_debug_check_guards synchronises and
+ * counts the gap bytes that no longer hold the pattern — *bad_bytes == 0 means no kernel wrote outside its buffers.  Returns
+ * the number of gaps checked (0 when guards are off or nothing is allocated yet) or a negative status. */
+int stz_debug_check_guards(stz_handle* h, long long* bad_bytes);
+
 /* Copies the fp32 residual stream h [B*K*2, d_model] (row = (b*K+k)*2 + branch) into
  * tap_dev after (eval, layer, stage) during eager (use_graph=0) runs; stage 0/1/2 = after the
  * self-attention / cross-attention / FFN sub-layer, layer == n_layers -> the guided F.

@@ -66,6 +66,7 @@ struct Workspace {
 };
 
 constexpr int STZ_MAX_CHAINS = 8;
+constexpr int STZ_GUARD_BYTE = 0xA5;
 // The sigma schedule is known before the loop, so the AdaLN modulations c[e] · Wmod^T of every evaluation can be one GEMM
 // (M = E * 2B) instead of E small ones at the head of each evaluation's dependency chain.  E * 2B * n_mod floats: 78 MB at
 // cfg2 (E = 4), 620 MB at cfg3 (64 teacher evaluations, B = 32); beyond 1 GB the per-evaluation GEMM is kept.
@@ -139,6 +140,10 @@ struct stz_handle {
   int64_t graph_captures = 0;   // captures since creation (stz_graph_count)
   int max_graphs = 32;
   int t_buckets = 1;            // round the text length up to a bucket (with masks) so that free-form T reuses graphs
+  // own bounds checking (compute-sanitizer is closed on this pool): "guard_bytes" > 0 lays a poisoned gap after every buffer
+  // of the workspace arenas; stz_debug_check_guards counts the gap bytes a kernel has overwritten
+  int guard_bytes = 0;
+  std::vector<std::pair<size_t, size_t>> guards, guards_pros;    // (offset, length) of the gaps
   int last_fuse_mode = 0, last_T = 0;   // what the last sample_style call dispatched (stz_get_option: tests assert the benched kernel ran)
   int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 3;
   int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
@@ -578,7 +583,13 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
   const size_t ds = c.d_sty_tok, dh = c.d_hid, h8 = 4 * dh;  // 8h = 4 * d_hid
   size_t off = 0;
   std::vector<std::pair<void**, size_t>> plan;
-  auto want = [&](void** p, size_t bytes) { plan.push_back({p, off}); off = align_up(off + bytes, 1024); };
+  H->guards.clear();
+  auto want = [&](void** p, size_t bytes) {
+    plan.push_back({p, off});
+    const size_t end = off + bytes;
+    off = align_up(end + (size_t)H->guard_bytes, 1024);
+    if (H->guard_bytes > 0) H->guards.push_back({end, off - end});
+  };
 #define WANT(field, count, type) want((void**)&w.field, (size_t)(count) * sizeof(type))
   WANT(text_bf, BT * c.d_text, bf16); WANT(prompt_bf, BP * c.d_prompt, bf16);
   // context tokens [text rows ; prompt rows] and their per-layer K/V are contiguous (one LN, one K/V GEMM per call);
@@ -617,6 +628,7 @@ static int ensure_workspace(stz_handle* H, int B, int T, int P, int E, int noise
     return fail(H, STZ_E_NOMEM, "workspace of %zu bytes: %s", off, cudaGetErrorString(e));
   }
   for (auto& pr : plan) *pr.first = w.base + pr.second;
+  if (H->guard_bytes > 0) CK(H, cudaMemsetAsync(w.base, STZ_GUARD_BYTE, off, H->stream));
   w.bytes = off; w.B = B; w.T = T; w.P = P; w.E = E; w.noise_slices = noise_slices; w.mod_rows = mod_rows;
   CK(H, cudaMemsetAsync(w.cvec, 0, ((size_t)E * NS * d + 128 * d) * sizeof(bf16), H->stream));
   CK(H, cudaStreamSynchronize(H->stream));
@@ -965,6 +977,16 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     else if (!strcmp(key, "gemm_cluster")) H->gemm_cluster = value;
     else H->fuse_ln = value;
   } else if (!strcmp(key, "t_buckets")) H->t_buckets = value;
+  else if (!strcmp(key, "guard_bytes")) {    // re-plan both arenas with (or without) poisoned gaps
+    if (value < 0) return fail(H, STZ_E_ARG, "guard_bytes must be >= 0");
+    for (auto& sl : H->slot) if (sl.busy) return fail(H, STZ_E_ARG, "guard_bytes with a host call in flight");
+    if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+    CK(H, cudaDeviceSynchronize());
+    drop_graphs(H);
+    if (H->ws.base) { CK(H, cudaFree(H->ws.base)); H->ws = Workspace(); }
+    if (H->pws.base) { CK(H, cudaFree(H->pws.base)); H->pws = stz_handle::ProsodyWs(); }
+    H->guard_bytes = value;
+  }
   else if (!strcmp(key, "max_graphs")) {
     if (value < 1) return fail(H, STZ_E_ARG, "max_graphs must be >= 1");
     H->max_graphs = value;
@@ -990,10 +1012,46 @@ extern "C" int stz_get_option(const stz_handle* H, const char* key, int* value) 
   else if (!strcmp(key, "lstm_impl")) *value = H->lstm_impl;
   else if (!strcmp(key, "pred_gemm_impl")) *value = H->pred_gemm_impl;
   else if (!strcmp(key, "profile")) *value = H->profile;
+  else if (!strcmp(key, "guard_bytes")) *value = H->guard_bytes;
   else if (!strcmp(key, "last_fuse_mode")) *value = H->last_fuse_mode;
   else if (!strcmp(key, "last_T")) *value = H->last_T;
   else return STZ_E_ARG;
   return 0;
+}
+
+__global__ void guard_check_kernel(const uint8_t* __restrict__ p, size_t n, unsigned long long* __restrict__ bad) {
+  unsigned long long local = 0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    local += p[i] != STZ_GUARD_BYTE ? 1 : 0;
+  if (local) atomicAdd(bad, local);
+}
+
+// Counts the guard-gap bytes of both workspace arenas that no longer hold the poison pattern (synchronises the device).
+// Returns the number of gaps checked or a negative status; *bad_bytes = 0 means no kernel wrote outside its buffers.
+extern "C" int stz_debug_check_guards(stz_handle* H, long long* bad_bytes) {
+  if (!H || !bad_bytes) return STZ_E_ARG;
+  if (cudaSetDevice(H->device) != cudaSuccess) return fail(H, STZ_E_DEVICE, "cudaSetDevice failed");
+  CK(H, cudaDeviceSynchronize());
+  unsigned long long* bad = nullptr;
+  CK(H, cudaMalloc(&bad, sizeof *bad));
+  CK(H, cudaMemset(bad, 0, sizeof *bad));
+  int n = 0;
+  auto scan = [&](const char* base, const std::vector<std::pair<size_t, size_t>>& gaps) {
+    if (!base) return;
+    for (auto& g : gaps) {
+      if (g.second == 0) continue;
+      guard_check_kernel<<<(unsigned)((g.second + 255) / 256 < 64 ? (g.second + 255) / 256 : 64), 256>>>((const uint8_t*)base + g.first, g.second, bad);
+      ++n;
+    }
+  };
+  scan(H->ws.base, H->guards);
+  scan(H->pws.base, H->guards_pros);
+  unsigned long long hb = 0;
+  cudaError_t e = cudaMemcpy(&hb, bad, sizeof hb, cudaMemcpyDeviceToHost);
+  cudaFree(bad);
+  if (e != cudaSuccess) return fail(H, STZ_E_CUDA, "guard check -> %s", cudaGetErrorString(e));
+  *bad_bytes = (long long)hb;
+  return n;
 }
 
 // Max co-resident 8-CTA clusters of the BiLSTM recurrence kernel on the current device (diagnostic).
@@ -1656,7 +1714,13 @@ static int ensure_prosody_ws(stz_handle* H, int B, int F, int T) {
   const size_t BF = (size_t)B * F, kin = c.d_hid + c.d_sty_tok, h8 = 4 * (size_t)c.d_hid;
   size_t off = 0;
   std::vector<std::pair<void**, size_t>> plan;
-  auto want = [&](void** p, size_t bytes) { plan.push_back({p, off}); off = align_up(off + bytes, 1024); };
+  H->guards_pros.clear();
+  auto want = [&](void** p, size_t bytes) {
+    plan.push_back({p, off});
+    const size_t end = off + bytes;
+    off = align_up(end + (size_t)H->guard_bytes, 1024);
+    if (H->guard_bytes > 0) H->guards_pros.push_back({end, off - end});
+  };
   want((void**)&w.frames, BF * kin * sizeof(float));
   want((void**)&w.pa, (BF + 128) * 3 * kin * sizeof(bf16));
   want((void**)&w.G, BF * h8 * sizeof(float));
@@ -1670,6 +1734,7 @@ static int ensure_prosody_ws(stz_handle* H, int B, int F, int T) {
     return fail(H, STZ_E_NOMEM, "prosody workspace of %zu bytes: %s", off, cudaGetErrorString(e));
   }
   for (auto& pr : plan) *pr.first = w.base + pr.second;
+  if (H->guard_bytes > 0) { CK(H, cudaMemset(w.base, STZ_GUARD_BYTE, off)); }
   w.bytes = off; w.B = B; w.F = F; w.T = T;
   return 0;
 }

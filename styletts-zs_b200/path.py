@@ -91,6 +91,8 @@ def load_library(path: Optional[str] = None):
     lib.stz_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.stz_get_option.restype = i32
     lib.stz_get_option.argtypes = [vp, C.c_char_p, C.POINTER(i32)]
+    lib.stz_debug_check_guards.restype = i32
+    lib.stz_debug_check_guards.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.stz_profile_read.restype = i32
     lib.stz_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     lib.stz_bench_gemm.restype = i32
@@ -131,7 +133,7 @@ EXPORTED_SYMBOLS = ("stz_abi_version", "stz_weights_nfloats", "stz_weight_offset
                     "stz_synthesize_host", "stz_synthesize_host_submit", "stz_synthesize_host_wait", "stz_regulate_length", "stz_set_noise_seed", "stz_set_noise_utterances", "stz_philox_normal", "stz_debug_plan", "stz_launch_count", "stz_set_option", "stz_profile_read",
                     "stz_debug_set_tap", "stz_debug_set_att_trace", "stz_debug_set_gemm_trace", "stz_debug_set_lstm_trace", "stz_debug_max_lstm_clusters", "stz_bench_gemm",
                     "stz_op_gemm_bf16", "stz_op_attention", "stz_op_gemm_epi", "stz_op_gemm_sampler", "stz_op_gemm_ln",
-                    "stz_graph_count", "stz_reserve", "stz_get_option", "stz_predict_prosody")
+                    "stz_graph_count", "stz_reserve", "stz_get_option", "stz_predict_prosody", "stz_debug_check_guards")
 
 
 def _kind(sampler) -> int:
@@ -198,6 +200,14 @@ class StyleTTSZSPath:
         v = C.c_int()
         self._check(self.lib.stz_get_option(self._h, key.encode(), C.byref(v)), f"get_option({key})")
         return int(v.value)
+
+    def check_guards(self) -> Tuple[int, int]:
+        """(gaps checked, overwritten guard bytes) — see include/stz.h: stz_debug_check_guards; needs set_option('guard_bytes', n)."""
+        bad = C.c_longlong()
+        n = self.lib.stz_debug_check_guards(self._h, C.byref(bad))
+        if n < 0:
+            raise StzError(f"stz_debug_check_guards failed ({n}): {self.lib.stz_last_error(self._h).decode()}")
+        return int(n), int(bad.value)
 
     def launch_count(self) -> int:
         return int(self.lib.stz_launch_count(self._h))
@@ -298,7 +308,7 @@ class StyleTTSZSPath:
     # ---------------------------------------------------------------------------------
     def sample_style(self, text_emb, prompt_feats, steps: int, cfg_scale: float, *, text_mask=None,
                      prompt_mask=None, noise=None, sampler="student", seed: Optional[int] = None,
-                     first_utterance=0) -> torch.Tensor:
+                     first_utterance=0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """-> style codes [B,K,Ds] fp32 on this path's device.  ``noise`` [n_slices,B,K,Ds] is an
         input ("identical seeds" == identical noise tensors); or pass ``seed``
         (and the global index of the batch's first utterance) to draw it on the device — the same
@@ -317,7 +327,10 @@ class StyleTTSZSPath:
             te, pf = self._dev(text_emb, torch.float32), self._dev(prompt_feats, torch.float32)
             nz = None if noise is None else self._dev(noise, torch.float32)
             tm, pm = self._mask(text_mask), self._mask(prompt_mask)
-            out = torch.empty(B, cfg.n_style, cfg.d_style, dtype=torch.float32, device=self.device)
+            if out is None:
+                out = torch.empty(B, cfg.n_style, cfg.d_style, dtype=torch.float32, device=self.device)
+            elif tuple(out.shape) != (B, cfg.n_style, cfg.d_style) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous fp32 CUDA tensor [B, K, Ds]")
             st = torch.cuda.current_stream().cuda_stream
             rc = self.lib.stz_sample_style(self._h, _ptr(te), _ptr(tm), _ptr(pf), _ptr(pm), _ptr(nz), B, T, P,
                                            int(steps), float(cfg_scale), kind, _ptr(out), C.c_void_p(st))
