@@ -487,12 +487,15 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     __syncthreads();              // visb[buf] visible
     ATC2_TR();
     const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
-    if (tid == 0) {
+    if (warp == 0) {     // warp-uniform operands, one elected lane issues (no per-instruction waterfall: see gemm2_kernel)
       tc_fence_after();
       const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(ks);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(&bar_s);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&bar_s);
+      }
+      __syncwarp();
     }
     if (warp < 4) {  // per-branch visibility of each 32-key chunk
       const uint8_t v = visb[buf][warp * 32 + lane];
@@ -570,15 +573,18 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     ATC2_TR();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
-        const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
-        umma_bf16(tmem_o, da, db, idesc_o, j != 0 ? 1u : 0u);
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
+          const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
+          umma_bf16(tmem_o, da, db, idesc_o, j != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_o);
       }
-      umma_commit(&bar_o);
+      __syncwarp();
     }
     const float ltot = psum[0][row] + psum[1][row];
     const float inv = ltot > 0.f ? 1.f / ltot : 0.f;

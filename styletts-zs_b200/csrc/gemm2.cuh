@@ -300,6 +300,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   if (tr != nullptr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
+    // TMA producer: one lane.  (The warp-uniform + elect form that pays for the MMA warp below was measured SLOWER here:
+    // 688 vs 568 cycles per k-block, tools/mainloop_probe.py — two TMA issues per k-block do not pace the loop.)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -311,6 +313,21 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
           if constexpr (CM == 1) {
             const bool pre = tile == unit0 && kb < n_pre;   // this stage's W tile (and its expect_tx) went out before the wait
+            if ((dbg & 24) && !pre) {   // timing experiments (trace build): 8 = no W loads, 16 = no A loads (results are wrong)
+              const uint32_t bytes = ((dbg & 8) ? 0u : B_BYTES) + ((dbg & 16) ? 0u : A_BYTES);
+              if (bytes == 0) { mbar_arrive(&full_bar[stage]); }
+              else {
+                mbar_expect_tx(&full_bar[stage], bytes);
+                if (!(dbg & 16))
+                  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                               ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK), "r"(p.a_row0 + tile_m * GEMM_BM) : "memory");
+                if (!(dbg & 8))
+                  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                               ::"r"(sa + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])), "r"(kb * GEMM_BK), "r"(tile_n * BN) : "memory");
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              continue;
+            }
             if (!pre) mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -336,7 +353,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       if (tr != nullptr) tr[4] = clock64();
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    // MMA issue: the WHOLE warp runs the loop — barrier waits, stage / descriptor arithmetic are warp-uniform, so the
+    // compiler keeps them in uniform registers — and one elected lane issues the tcgen05 instructions.  With the loop under
+    // `if (lane == 0)` every tcgen05.mma / commit sat in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (operands in vector
+    // registers of a divergent region): ~65 cycles per MMA, ~670 per 64-wide k-block against 512 of tensor-pipe time for a
+    // 128 x 256 tile (tools/mainloop_probe.py, tools/micro/umma_issue.cu).
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CM, BN);
       int stage = 0, tcount = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
@@ -346,23 +368,36 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          const bool trk = tr != nullptr && tcount == 0 && kb >= 8 && kb < 12;     // issue-loop timeline, k-blocks 8..11 of the first tile
+          if (trk && lane == 0) tr[40 + 5 * (kb - 8)] = clock64();
           mbar_wait(&full_bar[stage], phase);
-          if (tr != nullptr && kb == 0 && tcount < 4) tr[8 + 4 * tcount] = clock64();
+          if (tr != nullptr && lane == 0 && kb == 0 && tcount < 4) tr[8 + 4 * tcount] = clock64();
+          if (trk && lane == 0) tr[41 + 5 * (kb - 8)] = clock64();
           tc_fence_after();
+          if (trk && lane == 0) tr[42 + 5 * (kb - 8)] = clock64();
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            if constexpr (CM == 1) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              if ((dbg & 32) && k > 0) break;   // timing experiment (trace build): one MMA per k-block
+              if constexpr (CM == 1) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (trk) tr[43 + 5 * (kb - 8)] = clock64();
+            if constexpr (CM == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_2cta(&empty_bar[stage]);
+            if (trk) tr[44 + 5 * (kb - 8)] = clock64();
           }
-          if constexpr (CM == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_2cta(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if constexpr (CM == 1) umma_commit(&tmem_full[acc]);
-        else umma_commit_2cta(&tmem_full[acc]);
-        if (tr != nullptr && tcount < 4) tr[9 + 4 * tcount] = clock64();
+        if (elect_one()) {
+          if constexpr (CM == 1) umma_commit(&tmem_full[acc]);
+          else umma_commit_2cta(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (tr != nullptr && lane == 0 && tcount < 4) tr[9 + 4 * tcount] = clock64();
         ++tcount;
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;

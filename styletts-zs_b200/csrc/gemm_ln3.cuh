@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
   if (tr != nullptr) tr[1] = clock64();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0) {     // TMA producer: one lane (see gemm2_kernel)
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -146,22 +146,25 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GLN3_BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = ring + stage * GLN3_STAGE_BYTES;
-        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
+    // warp-uniform loop, one elected lane issues (see gemm2_kernel)
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GLN3_BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = ring + stage * GLN3_STAGE_BYTES;
+      const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + A_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == GLN3_STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(&acc_full);
+      __syncwarp();
+      if (++stage == GLN3_STAGES) { stage = 0; phase ^= 1u; }
     }
+    if (elect_one()) umma_commit(&acc_full);
+    __syncwarp();
   } else {
     const int q4 = warp & 3, half = (warp - 2) >> 2;
     const int r_in = q4 * 32 + lane;                // row inside the tile == TMEM lane

@@ -155,9 +155,11 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
   for (int s = 0; s < maxlen; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
     if (tid == 0) mbar_expect_tx(&hbar[nxt], kStepBytes);   // arm the buffer this step's h will land in
-    if ((warp == 4 || warp == 5) && lane == 0) {
-      // two issuing threads (tcgen05.mma issue is ~50 cycles per instruction and per thread at these tiny N):
-      // warp 4: W_hi x [h_hi ; h_lo] (N = 32) -> columns 0..31;  warp 5: W_lo x h_hi (N = 16) -> columns 32..47
+    if (warp == 4 || warp == 5) {
+      // two issuing warps: warp 4: W_hi x [h_hi ; h_lo] (N = 32) -> columns 0..31;  warp 5: W_lo x h_hi (N = 16) -> columns 32..47.
+      // The whole warp runs the (warp-uniform) wait and descriptor arithmetic and ONE elected lane issues: under
+      // `lane == 0` every tcgen05.mma sat in an ELECT / R2UR.BROADCAST waterfall, ~65 cycles each instead of ~28
+      // (tools/micro/umma_issue.cu) — 16 of them head every time step's dependency chain.
       const int seg = warp - 4;
       if (tr != nullptr && seg == 0 && s < 64) tr[s * 8 + 0] = clock64();
       if (s > 0) {
@@ -171,13 +173,16 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
       fence_proxy_async();
       tc_fence_after();
       const uint32_t hb = h_base + cur * H_BUF, wa = w_base + seg * 4 * LT_W_TILE, dcol = tmem_d + seg * 2 * LT_NB;
+      if (elect_one()) {
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
-        const uint64_t da = umma_desc_sw128(wa + kb * LT_W_TILE), db = umma_desc_sw128(hb + kb * LT_H_TILE);
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t da = umma_desc_sw128(wa + kb * LT_W_TILE), db = umma_desc_sw128(hb + kb * LT_H_TILE);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(dcol, da + 2 * k, db + 2 * k, seg == 0 ? idesc32 : idesc16, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16(dcol, da + 2 * k, db + 2 * k, seg == 0 ? idesc32 : idesc16, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&mma_bar);
       }
-      umma_commit(&mma_bar);
+      __syncwarp();
       if (tr != nullptr && seg == 0 && s < 64) tr[s * 8 + 2] = clock64();
     }
     if (warp < 4) {     // thread = gate row: accumulator -> pre_s[seq][gate row]
