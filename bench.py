@@ -407,6 +407,7 @@ def sharded_leg(torch, stz, path, cfg, rank, world, local_rank, barrier, reps=3)
     """Strong scaling through the sharder: one global variable-length batch, length-sorted round-robin over the ranks, the
     per-rank host-buffer call, results gathered in a shared host mapping, re-ordered on rank 0 — all timed."""
     Bg, Tg, steps = SHARDED["B"], SHARDED["T"], SHARDED["steps"]
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))     # torchrun pins OMP_NUM_THREADS=1: rank 0's re-ordering copy is host work
     g = torch.Generator().manual_seed(4321)
     lens = torch.randint(SHARDED["lens"][0], SHARDED["lens"][1] + 1, (Bg,), generator=g)
     shards = stz.shard_utterances(lens.tolist(), world)
@@ -477,8 +478,20 @@ def main_native(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line (NCCL prints its version banner there)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout to the one JSON line by pointing
+        # fd 1 at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if dist is not None:
