@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   __shared__ uint32_t colmask[2][4];        // [branch][32-column chunk] of the current unit
   __shared__ float pmax[2][128], psum[2][128];
   const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index provably uniform
   const int q4 = warp & 3, half = warp >> 2;
   const int row = q4 * 32 + lane;                      // query row = TMEM lane
   const int br = row >> 6;                             // rows 0..63 conditional, 64..127 unconditional
@@ -427,6 +427,8 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
     const uint32_t bar = smem_u32(&bar_full[buf]);
     const int t0 = b * n_tok, hc = head * ATT_DH;
+    // (every lane computes the warp-uniform addresses above — they stay in uniform registers; lane 0 issues)
+    if (lane != 0) return;
     if (parts & 2) {
       if (warp == 0) mbar_expect_tx(&bar_full[buf], tx_bytes);   // the whole unit's bytes, armed with its first part
       if (p.self) {
@@ -450,13 +452,13 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     }
   };
   const bool kv_early = !p.self && static_cast<int>(blockIdx.x) < p.n_units;
-  if (kv_early && lane == 0) produce_tma(blockIdx.x, 0, 2);
+  if (kv_early) produce_tma(blockIdx.x, 0, 2);
   pdl_sync();
   ATC2_TR();
 
   auto produce = [&](int unit, int buf, int parts) {
     const int b = unit / p.n_heads;
-    if (lane == 0) produce_tma(unit, buf, parts);
+    produce_tma(unit, buf, parts);
     if (tid < 128) {   // visibility of key row `tid`: bit 0 = conditional queries, bit 1 = unconditional queries
       uint8_t vis = 0;
       if (p.self) {
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
   __shared__ float pmax[2][128], psum[2][128];
   const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
   const uint32_t qs = smem_base, kv0 = smem_base + ATC_TILE, p1s = smem_base + 5 * ATC_TILE;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index provably uniform
   const int q4 = warp & 3, half = warp >> 2;
   const int row = q4 * 32 + lane;
   const int br = row >> 6, tok = row & 63;

@@ -237,7 +237,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * (A_BYTES + B_BYTES);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: provably warp-uniform for the compiler, so everything derived from it (staging-tile
+  // addresses, store coordinates) lives in uniform registers and the epilogue's TMA stores need no ELECT / R2UR waterfall
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 #ifdef STZ_TRACE
   long long* tr = g_gemm_trace != nullptr ? g_gemm_trace + blockIdx.x * 64 : nullptr;
   const int dbg = g_gemm_dbg;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
 
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t u_base = ring + GLN3_H_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp index provably uniform
 #ifdef STZ_TRACE
   long long* tr = (g_gemm_trace != nullptr && warp == 2 && lane == 0) ? g_gemm_trace + (148 + blockIdx.x) * 64 : nullptr;   // second half of the buffer (gemm2_kernel uses the first)
 #else

@@ -69,7 +69,7 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
   float* pre_s = reinterpret_cast<float*>(lt_smem_raw + (smem_base - smem_u32(lt_smem_raw)) + LT_W_BYTES + LT_H_BYTES);   // [seq][gate row]
   const int rank = static_cast<int>(cluster_ctarank());
   const int group = blockIdx.x / LC_CS, dir = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index provably uniform
 #ifdef STZ_TRACE
   long long* tr = (g_lstm_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? g_lstm_trace : nullptr;
 #else
