@@ -37,6 +37,9 @@ struct GemmLnParams {
   int n_style;
   int split3;             // u is the split-bf16 operand [hi | lo | hi] with row stride 3 * 512
   int single;             // row layout (see GemmParams::single)
+  int tile_rows;          // rows of the residual stream one CTA pair owns: 128, or fewer (a multiple of 8) so that a problem
+                          // with 38 .. 74 full tiles spreads over (nearly) all 148 SMs — the MMAs still run at M = 128 (the tile's
+                          // unused accumulator rows are never read), the shared-memory-bound epilogue passes shrink with the rows
 };
 
 constexpr int GLN_N = 512, GLN_THREADS = 320;
@@ -88,6 +91,9 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
 #endif
   if (tr != nullptr) tr[0] = clock64();
   const int num_kb = p.K / GEMM_BK;                 // multiple of GLN3_STAGES (host-checked)
+  const int TR = p.tile_rows;                       // valid rows of this tile (host: 8 | TR, 8 <= TR <= 128)
+  const uint32_t a_bytes = static_cast<uint32_t>(TR) * 128u;                       // one A box: TR rows x 64 bf16
+  const uint32_t stage_tx = a_bytes + GLN3_BN * GEMM_BK * 2, h_tx = 8u * a_bytes;   // (an h box is TR rows x 32 fp32: the same bytes)
   const int crank = static_cast<int>(g2_cluster_rank());
   const int tile_m = blockIdx.x >> 1;
   const int ncol0 = crank * GLN3_BN;                // first global column of this CTA
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     n_pre = num_kb < GLN3_STAGES ? num_kb : GLN3_STAGES;
     for (int s = 0; s < n_pre; ++s) {
-      mbar_expect_tx(&full_bar[s], GLN3_STAGE_BYTES);
+      mbar_expect_tx(&full_bar[s], stage_tx);
       tma_load_2d_u32(ring + s * GLN3_STAGE_BYTES + A_BYTES, &tmB, smem_u32(&full_bar[s]), s * GEMM_BK, ncol0);
     }
   }
@@ -128,19 +134,19 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const uint32_t sa = ring + stage * GLN3_STAGE_BYTES;
         if (kb >= n_pre) {
-          mbar_expect_tx(&full_bar[stage], GLN3_STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_2d_u32(sa + A_BYTES, &tmB, smem_u32(&full_bar[stage]), kb * GEMM_BK, ncol0);
         }
-        tma_load_2d_u32(sa, &tmA, smem_u32(&full_bar[stage]), kb * GEMM_BK, tile_m * GEMM_BM);
+        tma_load_2d_u32(sa, &tmA, smem_u32(&full_bar[stage]), kb * GEMM_BK, tile_m * TR);
         if (++stage == GLN3_STAGES) { stage = 0; phase ^= 1u; }
       }
       if constexpr (MODE == GLN_RES) {
         // residual tile into the ring as the MMAs release it: boxes 0..2 live in stage 0, 3..5 in stage 1, 6..7 in stage 2
-        mbar_expect_tx(&h_full, GLN3_H_BYTES);
+        mbar_expect_tx(&h_full, h_tx);
         for (int s = 0; s < 3; ++s) {            // stage == s here: num_kb is a multiple of the ring depth
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           for (int cc = 3 * s; cc < 3 * s + 3 && cc < 8; ++cc)
-            tma_load_2d_u32(ring + cc * GLN3_H_BOX, &tmH, smem_u32(&h_full), ncol0 + cc * 32, tile_m * GEMM_BM);
+            tma_load_2d_u32(ring + cc * GLN3_H_BOX, &tmH, smem_u32(&h_full), ncol0 + cc * 32, tile_m * TR);
           if (++stage == GLN3_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -168,14 +174,15 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
   } else {
     const int q4 = warp & 3, half = (warp - 2) >> 2;
     const int r_in = q4 * 32 + lane;                // row inside the tile == TMEM lane
-    const int m = tile_m * GEMM_BM + r_in;
-    const int mm = m < p.M ? m : p.M - 1;           // clamp for loads; rows >= M are never stored (TMA clips)
+    const int m = tile_m * TR + r_in;
+    const int mm = m < p.M ? m : p.M - 1;           // clamp for loads; rows >= M (or >= TR inside the tile) are never stored (TMA clips)
+    const bool warp_active = q4 * 32 < TR;          // warps whose 32 rows lie past the tile's rows skip both passes
     const float* src = p.pos + static_cast<size_t>(tok_of_row(mm, p.n_style, p.single)) * GLN_N;   // GLN_POS only
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + half * 128;
     const int col0 = ncol0 + half * 128;            // first global column of this warp
     const uint32_t sw = r_in & 7;
     // modulation table: every epilogue thread copies its share while the mainloop runs
-    const int m_first = tile_m * GEMM_BM < p.M ? tile_m * GEMM_BM : p.M - 1;
+    const int m_first = tile_m * TR < p.M ? tile_m * TR : p.M - 1;
     const int seq_first = seq_of_row(m_first & ~1, p.rows_per_utt, p.single), seq_last = seq_of_row((p.M - 1) | (p.single ? 0 : 1), p.rows_per_utt, p.single);
     {
       const int te = threadIdx.x - 64;                     // 0..255
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     // ---- pass 1: h' = h + gate * (acc + bias)  (or acc + bias + pos), in place in the ring tile; statistics
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < (warp_active ? 4 : 0); ++c) {
       const int col = col0 + c * 32;
       const uint32_t sb = ring + (half * 4 + c) * GLN3_H_BOX + r_in * 128;
       uint32_t r[32];
@@ -260,8 +267,9 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
   if (warp >= 2) {
     const int q4 = warp & 3, half = (warp - 2) >> 2;
     const int r_in = q4 * 32 + lane;
-    const int m = tile_m * GEMM_BM + r_in;
+    const int m = tile_m * TR + r_in;
     const int mm = m < p.M ? m : p.M - 1;
+    const bool warp_active = q4 * 32 < TR;
     const int col0 = ncol0 + half * 128;
     const uint32_t sw = r_in & 7;
     const float2 a0 = stats_s[0][r_in], a1 = stats_s[1][r_in], a2 = stats_s[2][r_in], a3 = stats_s[3][r_in];
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     // it, the barrier's release waited ~5 k cycles for the 128 KB of stores to drain)
     if (q4 == 0 && lane == 0) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tma_store_2d(&tmH, ring + (half * 4 + c) * GLN3_H_BOX, col0 + c * 32, tile_m * GEMM_BM);
+      for (int c = 0; c < 4; ++c) tma_store_2d(&tmH, ring + (half * 4 + c) * GLN3_H_BOX, col0 + c * 32, tile_m * TR);
       bulk_commit();
     }
     if (p.split3) {     // the lo tiles reuse the residual boxes: their TMA stores must have read them out first
@@ -280,13 +288,13 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
       named_bar_sync(2 + half, 128);
     }
     // ---- pass 2: u = LN(h') * (1 + scale) + shift -> bf16 tile (128 rows x 64 columns per box) in the rest of the ring
-    const int m_first = tile_m * GEMM_BM < p.M ? tile_m * GEMM_BM : p.M - 1;
+    const int m_first = tile_m * TR < p.M ? tile_m * TR : p.M - 1;
     const int sl = seq_of_row(mm, p.rows_per_utt, p.single) - seq_of_row(m_first & ~1, p.rows_per_utt, p.single);
     const uint32_t scale_t = smem_u32(&tab_s[1][sl][half * 128]), shift_t = smem_u32(&tab_s[2][sl][half * 128]);
     const uint32_t t_addr2 = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + half * 128;
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < (warp_active ? 4 : 0); ++c) {
       const int sub = c & 1, ub = half * 2 + (c >> 1);
       uint32_t hr[32];
       tmem_ld32(t_addr2 + c * 32, hr);
@@ -328,10 +336,10 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int ub = half * 2 + k, n0 = ncol0 + ub * 64;
-        tma_store_2d(&tmU, u_base + ub * GLN3_H_BOX, n0, tile_m * GEMM_BM);
+        tma_store_2d(&tmU, u_base + ub * GLN3_H_BOX, n0, tile_m * TR);
         if (p.split3) {
-          tma_store_2d(&tmU, ring + (2 * ub) * GLN3_H_BOX, GLN_N + n0, tile_m * GEMM_BM);
-          tma_store_2d(&tmU, u_base + ub * GLN3_H_BOX, 2 * GLN_N + n0, tile_m * GEMM_BM);
+          tma_store_2d(&tmU, ring + (2 * ub) * GLN3_H_BOX, GLN_N + n0, tile_m * TR);
+          tma_store_2d(&tmU, u_base + ub * GLN3_H_BOX, 2 * GLN_N + n0, tile_m * TR);
         }
       }
       bulk_commit();

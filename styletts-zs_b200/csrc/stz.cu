@@ -150,6 +150,7 @@ struct stz_handle {
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
   int attn_impl = 0;   // 0 = tcgen05 + TMA kernels (resident keys, streaming for long text; mma.sync streaming beyond their shapes), 2 = always the mma.sync streaming kernel
+  int gln_tile_rows = 0;   // knob "gln_tile_rows": 0 = heuristic (gemmln3_tile_rows), else forced rows per CTA pair of the fused kernel
   int use_pdl = 1, gemm_bn = 0, gemm_cluster = 0;   // launch knobs (copied into the thread-local launch context by every entry point)
   int ablate = 0;   // tools/ablate.py: bit mask of kernel families skipped inside run_eval (timing attribution only; results are wrong)
   int64_t launches = 0;
@@ -426,20 +427,34 @@ static int launch_gemm2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, 
 
 // ---- fused GEMM + residual/pos + AdaLN (gemm_ln3.cuh): N = d_model = 512 ------------------------------
 // residual tile staged in the operand ring (gemm_ln3.cuh)
+// Rows per CTA pair: 128, or — when the problem has 38 .. 74 full tiles — the multiple of 8 that spreads the rows over (at
+// most) num_sms / 2 pairs: cfg2's 6400 rows -> 88-row tiles on 146 SMs instead of 128-row tiles on 100 (the MMAs keep M = 128;
+// the shared-memory-bound epilogue passes shrink with the rows).
+static int gemmln3_tile_rows(int M) {
+  const int pairs = g_num_sms / 2, tiles128 = cdiv(M, GEMM_BM);
+  if (tiles128 > pairs || 2 * tiles128 <= pairs) return GEMM_BM;
+  const int tr = (cdiv(M, pairs) + 7) / 8 * 8;
+  return tr < 64 ? 64 : (tr > GEMM_BM ? GEMM_BM : tr);
+}
+
 template <int MODE>
 static int launch_gemmln3(stz_handle* H, cudaStream_t st, const bf16* A, int lda, int a_rows, const bf16* W, bf16* u,
-                          const GemmLnParams& p) {
+                          const GemmLnParams& p_in) {
+  GemmLnParams p = p_in;
+  if (p.tile_rows == 0) p.tile_rows = H->gln_tile_rows > 0 ? H->gln_tile_rows : gemmln3_tile_rows(p.M);
+  if (p.tile_rows < 8 || p.tile_rows > GEMM_BM || p.tile_rows % 8) return fail(H, STZ_E_ARG, "gemmln3 tile_rows %d", p.tile_rows);
   if (p.K % (GEMM_BK * GLN3_STAGES)) return fail(H, STZ_E_SHAPE, "gemmln3 needs K %% %d == 0", GEMM_BK * GLN3_STAGES);
   if ((p.single ? 1 : 2) * ((GEMM_BM - 1 + p.rows_per_utt - 1) / p.rows_per_utt + 1) > GLN3_MAX_SEQ)
     return fail(H, STZ_E_SHAPE, "gemmln3: a 128-row tile spans too many sequences (rows_per_utt %d)", p.rows_per_utt);
   CUtensorMap ta, tb, tu, th;
-  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, GEMM_BM) ||
+  const int TR = p.tile_rows;
+  if (make_tmap(&ta, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda, TR) ||
       make_tmap(&tb, W, (uint64_t)GLN_N, (uint64_t)p.K, (uint64_t)p.K, GLN3_BN) ||
-      make_tmap_out(&th, p.h, false, (uint64_t)p.M, (uint64_t)GLN_N, (uint64_t)GLN_N, 128, 128) ||
-      make_tmap_out(&tu, u, true, (uint64_t)p.M, (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), 128, 128))
+      make_tmap_out(&th, p.h, false, (uint64_t)p.M, (uint64_t)GLN_N, (uint64_t)GLN_N, 128, TR) ||
+      make_tmap_out(&tu, u, true, (uint64_t)p.M, (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), (uint64_t)(p.split3 ? 3 * GLN_N : GLN_N), 128, TR))
     return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled failed (gemmln3 M=%d K=%d)", p.M, p.K);
   ProfScope ps(H, st, PC_GEMM_TC, 2.0 * p.M * GLN_N * p.K);
-  launch_kc(2, gemmln3_kernel<MODE>, 2 * cdiv(p.M, GEMM_BM), GLN_THREADS, GLN3_SMEM_BYTES, st, ta, tb, tu, th, p);
+  launch_kc(2, gemmln3_kernel<MODE>, 2 * cdiv(p.M, TR), GLN_THREADS, GLN3_SMEM_BYTES, st, ta, tb, tu, th, p);
   KCHECK(H);
   return 0;
 }
@@ -966,7 +981,7 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
-  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
+  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "gln_tile_rows") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
            !strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // baked into captured graphs
     drop_graphs(H);
     if (!strcmp(key, "chains")) H->chains = value;
@@ -975,6 +990,7 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     else if (!strcmp(key, "gemm_bn")) H->gemm_bn = value;
     else if (!strcmp(key, "use_pdl")) H->use_pdl = value;
     else if (!strcmp(key, "gemm_cluster")) H->gemm_cluster = value;
+    else if (!strcmp(key, "gln_tile_rows")) H->gln_tile_rows = value;
     else H->fuse_ln = value;
   } else if (!strcmp(key, "t_buckets")) H->t_buckets = value;
   else if (!strcmp(key, "guard_bytes")) {    // re-plan both arenas with (or without) poisoned gaps
@@ -1007,6 +1023,7 @@ extern "C" int stz_get_option(const stz_handle* H, const char* key, int* value) 
   else if (!strcmp(key, "gemm_impl")) *value = H->gemm_impl;
   else if (!strcmp(key, "gemm_bn")) *value = H->gemm_bn;
   else if (!strcmp(key, "fuse_ln")) *value = H->fuse_ln;
+  else if (!strcmp(key, "gln_tile_rows")) *value = H->gln_tile_rows;
   else if (!strcmp(key, "attn_impl")) *value = H->attn_impl;
   else if (!strcmp(key, "chains")) *value = H->chains;
   else if (!strcmp(key, "lstm_impl")) *value = H->lstm_impl;

@@ -155,3 +155,28 @@ def test_fused_gemm_positional_adaln(path, M):
     h = torch.full((M, N), float("nan"), device="cuda")                # GLN_POS never reads h
     u = path.op_gemm_ln(A, W, b, h, mod, mode=1, shift_off=0, scale_off=N, pos=pos)
     assert rel(h, hp) < 2e-5 and rel(u, u_ref) < 5e-3
+
+
+@pytest.mark.parametrize("rows", [64, 72, 88, 96, 120])
+@pytest.mark.parametrize("M,K,split3", [(6400, 512, False), (1000, 2048, True)])
+def test_fused_gemm_residual_adaln_tile_rows(path, rows, M, K, split3):
+    """gemmln3_kernel with fewer than 128 rows per CTA pair (the heuristic picks 88 at cfg2's 6400 rows: 146 SMs busy
+    instead of 100): every forced row count gives the same h' / u as the PyTorch restatement."""
+    N = 512
+    A, W, b, g = _operands(M, N, K, 8)
+    mod = 0.5 * torch.randn(_n_seq(M), 4 * N, device="cuda", generator=g)
+    h0 = torch.randn(M, N, device="cuda", generator=g)
+    seq = _seq_of_rows(M)
+    hp = h0 + mod[seq, 0:N] * (A.float() @ W.float().t() + b)
+    u_ref = _ln_mod(hp, mod, seq, N, 2 * N)
+    h = h0.clone()
+    path.set_option("gln_tile_rows", rows)
+    try:
+        u = path.op_gemm_ln(A, W, b, h, mod, mode=0, gate_off=0, shift_off=N, scale_off=2 * N, split3=split3)
+    finally:
+        path.set_option("gln_tile_rows", 0)
+    assert rel(h, hp) < 2e-5
+    if not split3:
+        assert rel(u, u_ref) < 5e-3
+    else:
+        assert torch.equal(u[:, :N], u[:, 2 * N:]) and rel(u[:, :N].float() + u[:, N:2 * N].float(), u_ref) < 5e-5
