@@ -188,8 +188,9 @@ int stz_reserve(stz_handle* h, int max_B, int max_T, int max_P, int max_steps, i
  *   "use_pdl"        1 | 0        programmatic dependent launch
  *   "gemm_impl"      0 | 1        persistent tcgen05 GEMM | SIMT cross-check kernel
  *   "gemm_bn"        0 | 128/192/256   tile width heuristic | forced
- *   "fuse_ln"        3 | 0 | 4    residual GEMM + AdaLN in one cluster-of-two kernel where it measured faster (36 .. 140 and
- *                                 >= 350 row tiles), GEMM + ln_mod kernels otherwise | never fused | fused at any size
+ *   "fuse_ln"        3 | 0 | 4    residual GEMM + AdaLN in one cluster-of-two kernel where it measured faster (37 .. 74 row
+ *                                 tiles: one wave of CTA pairs), GEMM + ln_mod kernels otherwise | never fused | fused at any size
+ *   "gln_tile_rows"  0 | 8..128   rows per CTA pair of that kernel: heuristic (96 where one wave still fits, else 128) | forced
  *   "attn_impl"      0 | 2        tcgen05 + TMA attention (resident keys; streaming over 128-key blocks for long text; the
  *                                 mma.sync streaming kernel beyond their shapes: P > 127, K > 64) | always the mma.sync kernel
  *   "chains"         1 | 2..8     utterance chains on parallel graph branches

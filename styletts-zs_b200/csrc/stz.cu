@@ -427,14 +427,13 @@ static int launch_gemm2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, 
 
 // ---- fused GEMM + residual/pos + AdaLN (gemm_ln3.cuh): N = d_model = 512 ------------------------------
 // residual tile staged in the operand ring (gemm_ln3.cuh)
-// Rows per CTA pair: 128, or — when the problem has 38 .. 74 full tiles — the multiple of 8 that spreads the rows over (at
-// most) num_sms / 2 pairs: cfg2's 6400 rows -> 88-row tiles on 146 SMs instead of 128-row tiles on 100 (the MMAs keep M = 128;
-// the shared-memory-bound epilogue passes shrink with the rows).
+// Rows per CTA pair: 128, or 96 when 96-row tiles still fit one wave of num_sms / 2 pairs: cfg2's 6400 rows -> 67 tiles on 134
+// SMs instead of 50 tiles on 100 (the MMAs keep M = 128; the shared-memory-bound epilogue passes shrink with the rows).
+// Whole epilogue warps (32 rows) are what is saved, so only multiples of 32 pay: 72- or 88-row tiles cost what 96-row tiles
+// cost, 64-row tiles need two waves from 37 tiles on (tools/ab_tile_rows.py, profiles/r02_ab_tile_rows.txt).
 static int gemmln3_tile_rows(int M) {
-  const int pairs = g_num_sms / 2, tiles128 = cdiv(M, GEMM_BM);
-  if (tiles128 > pairs || 2 * tiles128 <= pairs) return GEMM_BM;
-  const int tr = (cdiv(M, pairs) + 7) / 8 * 8;
-  return tr < 64 ? 64 : (tr > GEMM_BM ? GEMM_BM : tr);
+  const int pairs = g_num_sms / 2;
+  return (cdiv(M, 96) <= pairs && 2 * cdiv(M, GEMM_BM) > pairs) ? 96 : GEMM_BM;
 }
 
 template <int MODE>
@@ -1271,14 +1270,13 @@ static int run_eval(stz_handle* H, cudaStream_t st, int e, int Btot, int b0, int
   int fuse_mode = (impl == 0 && d == GLN_N) ? H->fuse_ln : 0;
   if (fuse_mode != 3 && fuse_mode != 4) fuse_mode = 0;
   if (fuse_mode != 0 && (d % 256 || c.d_ff % 256 || (3 * Ds) % 256 || nbr * ((GEMM_BM - 1 + nbr * K - 1) / (nbr * K) + 1) > GLN3_MAX_SEQ)) fuse_mode = 0;
-  // below ~36 row tiles (B < ~46 at K = 50) the separate LayerNorm kernel is cheap and the fused kernel's long serial
-  // epilogue loses (measured: -2 .. -4 % at B = 16 / 32); from 36 to ~140 tiles (one to 1.9 waves of CTA pairs) it wins
-  // 1 .. 7 % (B = 48 .. 160); from there to ~350 tiles (two to four waves) its one-tile-per-CTA-pair grid quantises worse
-  // than the persistent GEMM + LayerNorm pair (measured 1 .. 4 % slower at B = 192 .. 384); with more waves it wins again
-  // (1.5 .. 2 % at B = 512 .. 1024).  fuse_ln = 4 forces the fused kernel at any size.
+  // The fused kernel wins where its CTA pairs fill ONE wave: 37 .. 74 row tiles (B = 47 .. 94 at K = 50: +7 .. 12 %, with
+  // 96-row tiles where they fit).  Below, the separate LayerNorm kernel is cheap and the fused kernel's long serial epilogue
+  // loses 2 .. 9 %; above (two and more waves of pairs) the persistent GEMM + LayerNorm pair wins 1 .. 5 % since its MMA issue
+  // loop went warp-uniform (tools/ab_tile_rows.py, profiles/r02_ab_tile_rows.txt).  fuse_ln = 4 forces the fused kernel.
   {
     const int row_tiles = cdiv(R, GEMM_BM);
-    if (fuse_mode == 3 && (row_tiles < 36 || (row_tiles > 140 && row_tiles < 350))) fuse_mode = 0;
+    if (fuse_mode == 3 && (row_tiles < 37 || row_tiles > g_num_sms / 2)) fuse_mode = 0;
   }
   if (fuse_mode == 4) fuse_mode = 3;
   const bool fused = fuse_mode != 0;
