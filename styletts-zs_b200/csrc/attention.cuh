@@ -350,6 +350,9 @@ struct AttnTcParams {
   float scale_log2;
   int single;              // single-branch row layout (guidance-conditioned student): query row = b * n_style + token, only tile
                            // rows 0..63 (the "conditional" half) are loaded and written; the unit is still (utterance, head)
+  int box2;                // the Q (self: Q / K / V) tensor map is (column, token, branch) with a box of 64 x 64 x branches: ONE
+                           // TMA instruction per operand lands both branches de-interleaved (TMA issues serialise at ~200
+                           // cycles each per SM: tools/att_trace.py); 0: (column, branch, token) map, one box per branch
 };
 
 __device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
@@ -427,15 +430,21 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
     const uint32_t bar = smem_u32(&bar_full[buf]);
     const int t0 = b * n_tok, hc = head * ATT_DH;
-    // (every lane computes the warp-uniform addresses above — they stay in uniform registers; lane 0 issues)
-    if (lane != 0) return;
+    // (every lane computes the warp-uniform addresses above; ONE elected lane issues — inside an elect.sync region the compiler
+    // may keep operands in uniform registers, under `lane == 0` every TMA instruction sat in an ELECT / R2UR waterfall)
+    if (!elect_one()) return;
     if (parts & 2) {
       if (warp == 0) mbar_expect_tx(&bar_full[buf], tx_bytes);   // the whole unit's bytes, armed with its first part
       if (p.self) {
-        if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
-        else if (warp == 1 && !p.single) tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
-        else if (warp == 2) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
-        else if (warp == 3 && !p.single) tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
+        if (p.box2) {
+          if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, t0, 0);
+          else if (warp == 2) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, t0, 0);
+        } else {
+          if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
+          else if (warp == 1 && !p.single) tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
+          else if (warp == 2) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
+          else if (warp == 3 && !p.single) tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
+        }
       } else {
         const uint32_t o1 = p.T8 * 128, o2 = (p.T8 + p.P8) * 128;
         if (warp == 0) tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
@@ -447,8 +456,12 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
       }
     }
     if (parts & 1) {
-      if (warp == 6) tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
-      else if (warp == 7 && !p.single) tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+      if (p.box2) {
+        if (warp == 6) tma_load_3d_u32(qs, &tmQ, bar, hc, t0, 0);
+      } else {
+        if (warp == 6) tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
+        else if (warp == 7 && !p.single) tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+      }
     }
   };
   const bool kv_early = !p.self && static_cast<int>(blockIdx.x) < p.n_units;
@@ -732,10 +745,14 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
       for (int j = 1; j < nbt; ++j) nbv += p.tmask[static_cast<size_t>(b) * p.T + j * 128] != 0 ? 1 : 0;
     }
     const int nblk = nbv + 1;                  // valid text blocks, then the prompt + null block (id nbt)
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {     // one elected lane of warp 0 issues (elect.sync region: no per-instruction waterfall)
       mbar_expect_tx(&bar_q, p.single ? 8192u : 2u * 8192u);
-      tma_load_3d_u32(qs, &tmQ, smem_u32(&bar_q), head * ATT_DH, 0, b * n_tok);
-      if (!p.single) tma_load_3d_u32(qs + 8192, &tmQ, smem_u32(&bar_q), head * ATT_DH, 1, b * n_tok);
+      if (p.box2) {
+        tma_load_3d_u32(qs, &tmQ, smem_u32(&bar_q), head * ATT_DH, b * n_tok, 0);
+      } else {
+        tma_load_3d_u32(qs, &tmQ, smem_u32(&bar_q), head * ATT_DH, 0, b * n_tok);
+        if (!p.single) tma_load_3d_u32(qs + 8192, &tmQ, smem_u32(&bar_q), head * ATT_DH, 1, b * n_tok);
+      }
       load_block(b, head, 0, 0);
       load_block(b, head, 1, nblk > 2 ? 1 : nbt);       // nblk >= 2 always
       issue_s(0);
@@ -766,7 +783,7 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
       // may be refilled with block j + 1
       if (jj > 0) {
         mbar_wait(&bar_o, ph_o); ph_o ^= 1u;
-        if (tid == 0 && jj + 1 < nblk) load_block(b, head, jj + 1, jj + 1 < nbv ? jj + 1 : nbt);
+        if (warp == 0 && jj + 1 < nblk && elect_one()) load_block(b, head, jj + 1, jj + 1 < nbv ? jj + 1 : nbt);
       }
       tc_fence_after();
 
@@ -844,7 +861,7 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
       tc_fence_before();
       __syncthreads();
       l_run = l_run * alpha + (psum[0][row] + psum[1][row]);
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

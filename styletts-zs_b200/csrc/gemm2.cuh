@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
 #pragma unroll
             for (int pc = 0; pc < PIECES; ++pc) {
               if (trc && pc == 0) te[2] = clock64();
-              if (lane == 0) bulk_wait_read<1>();
+              if (elect_one()) bulk_wait_read<1>();
               __syncwarp();
               if (trc && pc == 0) te[3] = clock64();
               const uint32_t tile = stage_buf + tsel * 2048;
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
               fence_proxy_async();
               __syncwarp();
               if (trc && pc == 0) te[5] = clock64();
-              if (lane == 0) {
+              if (elect_one()) {     // (elect.sync region: uniform-register operands, no waterfall around the TMA instruction)
                 const int n0 = tile_n * BN + col + pc * 16;
                 if (m0 < p.M && !(dbg & 1)) {
                   if constexpr (EPI == EPI_GATE_RES) tma_reduce_add_2d(&tmC, tile, n0, m0);
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (lane == 0) bulk_wait_read<0>();
+    if (elect_one()) bulk_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();

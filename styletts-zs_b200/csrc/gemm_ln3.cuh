@@ -278,13 +278,13 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     const float rstd = rsqrtf(var + 1e-5f);
     // h' goes out now (the cluster barrier above also ordered the four row groups of each column half; issued before
     // it, the barrier's release waited ~5 k cycles for the 128 KB of stores to drain)
-    if (q4 == 0 && lane == 0) {
+    if (q4 == 0 && elect_one()) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) tma_store_2d(&tmH, ring + (half * 4 + c) * GLN3_H_BOX, col0 + c * 32, tile_m * TR);
       bulk_commit();
     }
     if (p.split3) {     // the lo tiles reuse the residual boxes: their TMA stores must have read them out first
-      if (q4 == 0 && lane == 0) bulk_wait_read<0>();
+      if (q4 == 0 && elect_one()) bulk_wait_read<0>();
       named_bar_sync(2 + half, 128);
     }
     // ---- pass 2: u = LN(h') * (1 + scale) + shift -> bf16 tile (128 rows x 64 columns per box) in the rest of the ring
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
     fence_proxy_async();
     named_bar_sync(2 + half, 128);
     if (tr != nullptr) tr[8] = clock64();
-    if (q4 == 0 && lane == 0) {
+    if (q4 == 0 && elect_one()) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int ub = half * 2 + k, n0 = ncol0 + ub * 64;

@@ -150,6 +150,7 @@ struct stz_handle {
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
   int attn_impl = 0;   // 0 = tcgen05 + TMA kernels (resident keys, streaming for long text; mma.sync streaming beyond their shapes), 2 = always the mma.sync streaming kernel
+  int attn_box2 = 1;       // knob "attn_box2": one TMA box per attention operand (both branches) | one box per branch
   int gln_tile_rows = 0;   // knob "gln_tile_rows": 0 = heuristic (gemmln3_tile_rows), else forced rows per CTA pair of the fused kernel
   int use_pdl = 1, gemm_bn = 0, gemm_cluster = 0;   // launch knobs (copied into the thread-local launch context by every entry point)
   int ablate = 0;   // tools/ablate.py: bit mask of kernel families skipped inside run_eval (timing attribution only; results are wrong)
@@ -980,7 +981,7 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
-  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "gln_tile_rows") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
+  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "gln_tile_rows") || !strcmp(key, "attn_box2") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
            !strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // baked into captured graphs
     drop_graphs(H);
     if (!strcmp(key, "chains")) H->chains = value;
@@ -990,6 +991,7 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     else if (!strcmp(key, "use_pdl")) H->use_pdl = value;
     else if (!strcmp(key, "gemm_cluster")) H->gemm_cluster = value;
     else if (!strcmp(key, "gln_tile_rows")) H->gln_tile_rows = value;
+    else if (!strcmp(key, "attn_box2")) H->attn_box2 = value;
     else H->fuse_ln = value;
   } else if (!strcmp(key, "t_buckets")) H->t_buckets = value;
   else if (!strcmp(key, "guard_bytes")) {    // re-plan both arenas with (or without) poisoned gaps
@@ -1167,18 +1169,26 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
   if (H->attn_impl == 0 && ap.n_q <= 128 && n_style <= 64 && (self || (cross3 && T8 + P8 + 1 <= 128))) {
     // tcgen05 attention, TMA-staged operands (attention_tc2_kernel)
     CUtensorMap tq, tt, tp, tn;
+    bool box2 = false;
     memset(&tp, 0, sizeof tp); memset(&tn, 0, sizeof tn);
     const int qcols = self ? (int)(ap.seg[0].v - ap.q) + dm : dm;
     {  // Q (and, for self-attention, K / V): (column, branch, token) view of the R-layout buffer
-      const cuuint64_t gd[3] = {(cuuint64_t)qcols, (cuuint64_t)nbr, (cuuint64_t)B * n_style};
-      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 2 * nbr};
-      const cuuint32_t bx[3] = {64, 1, 64};
-      if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
+      // (column, token, branch) view, box 64 x 64 x branches: one TMA instruction lands both branches de-interleaved
+      const cuuint64_t gd2[3] = {(cuuint64_t)qcols, (cuuint64_t)B * n_style, (cuuint64_t)nbr};
+      const cuuint64_t gs2[2] = {(cuuint64_t)ap.ldq * 2 * nbr, (cuuint64_t)ap.ldq * 2};
+      const cuuint32_t bx2[3] = {64, 64, (cuuint32_t)nbr};
+      box2 = H->attn_box2 && make_tmap_nd(&tq, ap.q, 3, gd2, gs2, bx2) == 0;
+      if (!box2) {   // (column, branch, token) view, one box per branch
+        const cuuint64_t gd[3] = {(cuuint64_t)qcols, (cuuint64_t)nbr, (cuuint64_t)B * n_style};
+        const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 2 * nbr};
+        const cuuint32_t bx[3] = {64, 1, 64};
+        if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
+      }
     }
     tt = tq;
     AttnTcParams tp_{};
     tp_.out = ap.out; tp_.ldo = ap.ldo; tp_.n_q = ap.n_q; tp_.n_heads = H->cfg.n_heads; tp_.n_units = B * H->cfg.n_heads;
-    tp_.self = self ? 1 : 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single;
+    tp_.self = self ? 1 : 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single; tp_.box2 = box2 ? 1 : 0;
     if (self) {
       tp_.col_k = (int)(ap.seg[0].k - ap.q); tp_.col_v = (int)(ap.seg[0].v - ap.q);
     } else {
@@ -1200,11 +1210,18 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
   } else if (H->attn_impl == 0 && cross3 && ap.n_q <= 128 && n_style <= 64 && P8 + 1 <= 128) {
     // long text: streaming tcgen05 attention over 128-key blocks (attention_tcs_kernel)
     CUtensorMap tq, tt, tp, tn;
+    bool box2 = false;
     {
-      const cuuint64_t gd[3] = {(cuuint64_t)dm, (cuuint64_t)nbr, (cuuint64_t)B * n_style};
-      const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 2 * nbr};
-      const cuuint32_t bx[3] = {64, 1, 64};
-      if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
+      const cuuint64_t gd2[3] = {(cuuint64_t)dm, (cuuint64_t)B * n_style, (cuuint64_t)nbr};
+      const cuuint64_t gs2[2] = {(cuuint64_t)ap.ldq * 2 * nbr, (cuuint64_t)ap.ldq * 2};
+      const cuuint32_t bx2[3] = {64, 64, (cuuint32_t)nbr};
+      box2 = H->attn_box2 && make_tmap_nd(&tq, ap.q, 3, gd2, gs2, bx2) == 0;
+      if (!box2) {
+        const cuuint64_t gd[3] = {(cuuint64_t)dm, (cuuint64_t)nbr, (cuuint64_t)B * n_style};
+        const cuuint64_t gs[2] = {(cuuint64_t)ap.ldq * 2, (cuuint64_t)ap.ldq * 2 * nbr};
+        const cuuint32_t bx[3] = {64, 1, 64};
+        if (make_tmap_nd(&tq, ap.q, 3, gd, gs, bx)) return fail(H, STZ_E_CUDA, "cuTensorMapEncodeTiled (attention Q) failed");
+      }
     }
     const AttnSeg* sg = ap.seg;
     CUtensorMap* maps[3] = {&tt, &tp, &tn};
@@ -1218,7 +1235,7 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
     }
     AttnTcParams tp_{};
     tp_.out = ap.out; tp_.ldo = ap.ldo; tp_.n_q = ap.n_q; tp_.n_heads = H->cfg.n_heads; tp_.n_units = B * H->cfg.n_heads;
-    tp_.self = 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single;
+    tp_.self = 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single; tp_.box2 = box2 ? 1 : 0;
     tp_.T = sg[0].n; tp_.P = sg[1].n; tp_.T8 = T8; tp_.P8 = P8; tp_.col_k = 0; tp_.col_v = dm;
     tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
     const int units = tp_.n_units;

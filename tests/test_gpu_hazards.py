@@ -106,5 +106,11 @@ def test_results_do_not_depend_on_launch_mode_or_repetition(weights):
         p.set_option("use_pdl", 1)
         z = p.sample_style(dev["text_emb"], dev["prompt_feats"], 4, 2.0, noise=dev["noise"])
         assert torch.equal(z, z0)
+        # one TMA box per attention operand (permuted tensor map) vs one box per CFG branch: the same bytes land in the same places
+        p.set_option("use_graph", 1)
+        p.set_option("attn_box2", 0)
+        for a, b in zip(ref, _battery(p)):
+            assert torch.equal(a, b)
+        p.set_option("attn_box2", 1)
     finally:
         p.close()

@@ -13,6 +13,9 @@ dev = {k: inp[k].cuda() for k in ("text_emb", "prompt_feats", "noise")}
 tr = torch.zeros(296 * 32, dtype=torch.int64, device="cuda")
 names = ["start", "alloc", "pdl", "produce", "landed+sync", "S done", "pass1+sync", "pass2", "fence+sync", "PV issued", "O done", "epi+sync",
          "produce2", "landed2", "S2", "pass1", "pass2", "sync", "PVi", "O2", "epi2"]
+for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
+    path.set_option(k, int(v))
+    print("option", k, v)
 for which, bits in (("cross-attention", 0), ("self-attention", 2)):
     path.set_option("ablate", bits)
     for _ in range(3):
