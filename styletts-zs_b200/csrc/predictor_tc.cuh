@@ -29,6 +29,22 @@ constexpr int LT_H_TILE = 2 * LT_NB * 128;               // one 32-row (hi rows,
 constexpr int LT_H_BYTES = 2 * 4 * LT_H_TILE;            // 2 buffers x 4 k-blocks = 32 KB
 constexpr int LT_PRE_BYTES = LT_NB * LC_COLS * 4;        // pre-activations [seq][gate row] fp32 = 8 KB
 constexpr int LT_SMEM_BYTES = LT_W_BYTES + LT_H_BYTES + LT_PRE_BYTES + 1024;
+// W_TMEM form: the W_hh slice lives in TENSOR MEMORY as the A operand (tcgen05.mma with A from TMEM): lane = gate row, one
+// 32-bit column = two consecutive k (bf16 pair) -> 128 columns for W_hi + 128 for W_lo behind the 64 accumulator columns.
+// Every recurrent MMA then reads its A slab from TMEM instead of streaming 4 KB from shared memory (~84 cycles per MMA
+// whatever N: the 32 MMAs of a step were 1.34 k of its 3.28 k cycles, profiles/r02_lstm_trace.txt).
+constexpr int LT_SMEM_BYTES_WT = LT_H_BYTES + LT_PRE_BYTES + 1024;
+constexpr int LT_TMEM_W_HI = 64, LT_TMEM_W_LO = 64 + 128;
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: A operand from tensor memory (K-major: lane = row, 32-bit column = a k pair)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ void st_async_b32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
@@ -56,6 +72,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // [5] after st.async (warp 0)
 __device__ long long* g_lstm_trace = nullptr;
 
+template <bool W_TMEM>
 __global__ void __cluster_dims__(LC_CS, 1, 1) __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const int* __restrict__ lens,
                const int* __restrict__ perm, float* __restrict__ out, int B, int T) {
@@ -64,9 +81,11 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
   __shared__ uint32_t tmem_slot;
   __shared__ int len_s[LT_NB], seq_s[LT_NB];
   const uint32_t smem_base = (smem_u32(lt_smem_raw) + 1023u) & ~1023u;
-  const uint32_t w_base = smem_base;                       // [hi | lo][k-block][128 rows x 128 B]
-  const uint32_t h_base = smem_base + LT_W_BYTES;          // [buffer][k-block][32 rows x 128 B]: rows 0..15 h_hi, 16..31 h_lo
-  float* pre_s = reinterpret_cast<float*>(lt_smem_raw + (smem_base - smem_u32(lt_smem_raw)) + LT_W_BYTES + LT_H_BYTES);   // [seq][gate row]
+  constexpr uint32_t W_SMEM = W_TMEM ? 0u : static_cast<uint32_t>(LT_W_BYTES);
+  const uint32_t w_base = smem_base;                       // [hi | lo][k-block][128 rows x 128 B]   (shared-memory form only)
+  const uint32_t h_base = smem_base + W_SMEM;              // [buffer][k-block][32 rows x 128 B]: rows 0..15 h_hi, 16..31 h_lo
+  float* pre_s = reinterpret_cast<float*>(lt_smem_raw + (smem_base - smem_u32(lt_smem_raw)) + W_SMEM + LT_H_BYTES);   // [seq][gate row]
+  constexpr int TMEM_COLS = W_TMEM ? 512 : 64;
   const int rank = static_cast<int>(cluster_ctarank());
   const int group = blockIdx.x / LC_CS, dir = blockIdx.y;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index provably uniform
@@ -78,7 +97,7 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
 
   // ---- W_hh slice -> split-bf16 operand tiles (constant: under the previous kernel's tail) ---------------------------
   // gate row r = gate * 32 + unit  <->  W_hh row dir*4h + gate*h + rank*32 + unit; thread -> 8 consecutive k of a row
-  for (int i = tid; i < LC_COLS * (LC_H / 8); i += LT_THREADS) {
+  for (int i = tid; i < (W_TMEM ? 0 : LC_COLS * (LC_H / 8)); i += LT_THREADS) {
     const int r = i >> 5, c8 = i & 31;                     // row, 8-wide k chunk (32 per row)
     const int g = r >> 5, u = r & 31;
     const float4* src = reinterpret_cast<const float4*>(
@@ -99,7 +118,33 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
     mbar_init(&mma_bar, 2);      // one commit per issuing thread
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<64>(&tmem_slot);
+  if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_slot);
+  if constexpr (W_TMEM) {
+    // thread = gate row (warps 0..3 = TMEM lane quadrants): the row's 256 weights -> 128 hi words + 128 lo words in TMEM
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp < 4) {
+      const int r = tid, g = r >> 5, u = r & 31;
+      const float4* src = reinterpret_cast<const float4*>(Whh + (static_cast<size_t>(dir) * 4 * LC_H + g * LC_H + rank * LC_UPC + u) * LC_H);
+      const uint32_t lane_base = tmem_slot + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {            // 64 k = 32 packed columns per sweep
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 a = __ldg(src + c * 16 + j);
+          uint2 h2;
+          h2.x = pack_bf16(a.x, a.y); h2.y = pack_bf16(a.z, a.w);
+          const uint2 l2 = split_lo4(a, h2);
+          hi[2 * j] = h2.x; hi[2 * j + 1] = h2.y; lo[2 * j] = l2.x; lo[2 * j + 1] = l2.y;
+        }
+        tmem_st32(lane_base + LT_TMEM_W_HI + c * 32, hi);
+        tmem_st32(lane_base + LT_TMEM_W_LO + c * 32, lo);
+      }
+      tmem_st_wait();
+    }
+  }
   pdl_sync();
   if (tid < LT_NB) {
     const int idx = group * LT_NB + tid;
@@ -173,12 +218,19 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
       fence_proxy_async();
       tc_fence_after();
       const uint32_t hb = h_base + cur * H_BUF, wa = w_base + seg * 4 * LT_W_TILE, dcol = tmem_d + seg * 2 * LT_NB;
+      const uint32_t wt = tmem_d + (seg == 0 ? LT_TMEM_W_HI : LT_TMEM_W_LO);     // W_TMEM: 8 columns per K = 16 slab
       if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = umma_desc_sw128(wa + kb * LT_W_TILE), db = umma_desc_sw128(hb + kb * LT_H_TILE);
+          const uint64_t db = umma_desc_sw128(hb + kb * LT_H_TILE);
+          if constexpr (W_TMEM) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(dcol, da + 2 * k, db + 2 * k, seg == 0 ? idesc32 : idesc16, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(dcol, wt + (kb * 4 + k) * 8, db + 2 * k, seg == 0 ? idesc32 : idesc16, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = umma_desc_sw128(wa + kb * LT_W_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(dcol, da + 2 * k, db + 2 * k, seg == 0 ? idesc32 : idesc16, (kb | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&mma_bar);
       }
@@ -240,7 +292,7 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 0) tmem_dealloc<64>(tmem_d);
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
 }  // namespace stz

@@ -493,7 +493,8 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES_WT)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(style_pool_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (2 * 256 + 1) + 4) * 4)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(1))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(2))) != cudaSuccess) return e;
@@ -1082,7 +1083,7 @@ extern "C" int stz_debug_max_lstm_clusters(void) {
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = -1;
   if (init_kernel_attrs() != cudaSuccess) return -2;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel, &cfg) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<false>, &cfg) != cudaSuccess) return -1;
   return n;
 }
 
@@ -1658,9 +1659,10 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
     float* xo = bufs[l & 1];
     {
       ProfScope ps(H, st, PC_LSTM, 2.0 * BT * 2.0 * h * 4.0 * h);
-      if (h == LC_H && H->lstm_impl == 0) {  // product path: recurrent product on tcgen05 (split-bf16), cluster of 8 CTAs, DSMEM exchange
+      if (h == LC_H && (H->lstm_impl == 0 || H->lstm_impl == 3)) {  // product path (3: W_hh in shared memory instead of tensor memory, A/B): recurrent product on tcgen05 (split-bf16), cluster of 8 CTAs, DSMEM exchange
         const float* whh = H->whh + (size_t)l * 2 * 4 * h * h;
-        launch_k(lstm_tc_kernel, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, w.G, whh, w.lens, w.perm, xo, B, T);
+        if (H->lstm_impl == 0) launch_k(lstm_tc_kernel<true>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES_WT, st, w.G, whh, w.lens, w.perm, xo, B, T);
+        else launch_k(lstm_tc_kernel<false>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, w.G, whh, w.lens, w.perm, xo, B, T);
       } else {
         lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
       }
@@ -1814,8 +1816,12 @@ extern "C" int stz_predict_prosody(stz_handle* H, const float* text_emb_dev, con
   RET(gemm3(H->wih3_pros, H->lstm_b_pros, w.G, 8 * h));
   {
     ProfScope ps(H, st, PC_LSTM, 2.0 * BF * 2.0 * h * 4.0 * h);
-    launch_k(lstm_tc_kernel, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, (const float*)w.G, (const float*)H->whh_pros,
-             (const int*)w.flens, (const int*)w.perm, w.y, B, F_max);
+    if (H->lstm_impl == 3)
+      launch_k(lstm_tc_kernel<false>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, (const float*)w.G, (const float*)H->whh_pros,
+               (const int*)w.flens, (const int*)w.perm, w.y, B, F_max);
+    else
+      launch_k(lstm_tc_kernel<true>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES_WT, st, (const float*)w.G, (const float*)H->whh_pros,
+               (const int*)w.flens, (const int*)w.perm, w.y, B, F_max);
     KCHECK(H);
   }
   // z = [y | s_frame] W_h1^T + b_h1 (the s_frame columns of the operand are still in place), then the two heads
