@@ -22,18 +22,20 @@
 
 namespace stz {
 
-constexpr int LT_NB = 16, LT_THREADS = 512;
+// NB = sequences per cluster (16, or 8 for B <= 16: every CTA sends its 32 new units of NB sequences to all 8 CTAs each
+// step = NB KB out of the SM at the ~17 B/clk DSMEM rate — with W_hh in tensor memory that exchange is the largest part
+// of the step: 2.26 k cycles per step at NB = 16, 1.51 k at NB = 8, but only while few clusters run, see launch_lstm_tc).
 constexpr int LT_W_TILE = 128 * 128;                     // one 128-row x 64-k bf16 tile
 constexpr int LT_W_BYTES = 2 * 4 * LT_W_TILE;            // hi, lo x 4 k-blocks = 128 KB
-constexpr int LT_H_TILE = 2 * LT_NB * 128;               // one 32-row (hi rows, lo rows) x 64-k bf16 tile
-constexpr int LT_H_BYTES = 2 * 4 * LT_H_TILE;            // 2 buffers x 4 k-blocks = 32 KB
-constexpr int LT_PRE_BYTES = LT_NB * LC_COLS * 4;        // pre-activations [seq][gate row] fp32 = 8 KB
-constexpr int LT_SMEM_BYTES = LT_W_BYTES + LT_H_BYTES + LT_PRE_BYTES + 1024;
+constexpr int lt_threads(int nb) { return nb * 32 < 256 ? 256 : nb * 32; }      // warp = sequence; warps 0..5 also drain / issue
+constexpr int lt_h_tile(int nb) { return 2 * nb * 128; }                         // one 2 NB-row (hi rows, lo rows) x 64-k bf16 tile
+constexpr int lt_h_bytes(int nb) { return 2 * 4 * lt_h_tile(nb); }               // 2 buffers x 4 k-blocks (32 KB at NB = 16)
+constexpr int lt_pre_bytes(int nb) { return nb * LC_COLS * 4; }                  // pre-activations [seq][gate row] fp32
+constexpr int lt_smem_bytes(bool w_tmem, int nb) { return (w_tmem ? 0 : LT_W_BYTES) + lt_h_bytes(nb) + lt_pre_bytes(nb) + 1024; }
 // W_TMEM form: the W_hh slice lives in TENSOR MEMORY as the A operand (tcgen05.mma with A from TMEM): lane = gate row, one
 // 32-bit column = two consecutive k (bf16 pair) -> 128 columns for W_hi + 128 for W_lo behind the 64 accumulator columns.
 // Every recurrent MMA then reads its A slab from TMEM instead of streaming 4 KB from shared memory (~84 cycles per MMA
 // whatever N: the 32 MMAs of a step were 1.34 k of its 3.28 k cycles, profiles/r02_lstm_trace.txt).
-constexpr int LT_SMEM_BYTES_WT = LT_H_BYTES + LT_PRE_BYTES + 1024;
 constexpr int LT_TMEM_W_HI = 64, LT_TMEM_W_LO = 64 + 128;
 
 // D[tmem] (+)= A[tmem] * B[smem]^T: A operand from tensor memory (K-major: lane = row, 32-bit column = a k pair)
@@ -72,10 +74,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // [5] after st.async (warp 0)
 __device__ long long* g_lstm_trace = nullptr;
 
-template <bool W_TMEM>
-__global__ void __cluster_dims__(LC_CS, 1, 1) __launch_bounds__(LT_THREADS, 1)
+template <bool W_TMEM, int NB>
+__global__ void __cluster_dims__(LC_CS, 1, 1) __launch_bounds__(lt_threads(NB), 1)
 lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const int* __restrict__ lens,
                const int* __restrict__ perm, float* __restrict__ out, int B, int T) {
+  constexpr int LT_NB = NB, LT_THREADS = lt_threads(NB), LT_H_TILE = lt_h_tile(NB), LT_H_BYTES = lt_h_bytes(NB);
+  static_assert(NB == 8 || NB == 16, "operand rows [h_hi ; h_lo] = 2 NB must be a multiple of the 8-row swizzle atom and an MMA N");
   extern __shared__ uint8_t lt_smem_raw[];
   __shared__ __align__(8) uint64_t hbar[2], mma_bar;
   __shared__ uint32_t tmem_slot;
@@ -186,7 +190,8 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
   const uint32_t dst_off = (k0 >> 6) * LT_H_TILE + ((lane & 1) * LT_NB + warp) * 128 +
                            ((((k0 & 63) >> 3) ^ (warp & 7)) << 4) + (k0 & 7) * 2;
   constexpr uint32_t kStepBytes = LT_NB * LC_H * 4;      // hi + lo of 16 x 256 values
-  constexpr uint32_t idesc32 = umma_idesc_bf16(128, 2 * LT_NB), idesc16 = umma_idesc_bf16(128, LT_NB);
+  // (M = 128 needs N % 16 == 0: at NB = 8 the W_lo pass also runs over all 16 rows; its h_lo columns are never read)
+  constexpr uint32_t idesc32 = umma_idesc_bf16(128, 2 * LT_NB), idesc16 = umma_idesc_bf16(128, LT_NB < 16 ? 16 : LT_NB);
   constexpr int H_BUF = 4 * LT_H_TILE;                   // bytes per buffer
   // remote addresses of this lane's operand word and of the step barriers in all 8 CTAs (hoisted out of the step loop)
   uint32_t rdst[LC_CS], rbar[LC_CS];
@@ -242,9 +247,17 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
       if (tr != nullptr && warp == 0 && s < 64) tr[s * 8 + 3] = clock64();
       tc_fence_after();
       uint32_t r[32], r2[16];
-      tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), r);
-      tmem_ld16(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + 2 * LT_NB, r2);
+      if constexpr (NB == 16) {
+        tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), r);
+        tmem_ld16(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + 2 * LT_NB, r2);
+      } else {                     // columns 0..15 = W_hi [h_hi ; h_lo], 16..23 = W_lo h_hi
+        tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), r);
+      }
       tmem_ld_wait();
+      if constexpr (NB != 16) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n) r2[n] = r[2 * NB + n];
+      }
 #pragma unroll
       for (int n = 0; n < LT_NB; ++n)
         pre_s[n * LC_COLS + tid] = (__uint_as_float(r[n]) + __uint_as_float(r[LT_NB + n])) + __uint_as_float(r2[n]);

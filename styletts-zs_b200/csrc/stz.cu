@@ -145,7 +145,7 @@ struct stz_handle {
   int guard_bytes = 0;
   std::vector<std::pair<size_t, size_t>> guards, guards_pros;    // (offset, length) of the gaps
   int last_fuse_mode = 0, last_T = 0;   // what the last sample_style call dispatched (stz_get_option: tests assert the benched kernel ran)
-  int use_graph = 1, gemm_impl = 0, lstm_impl = 0, pred_gemm_impl = 0, fuse_ln = 3;
+  int use_graph = 1, gemm_impl = 0, lstm_impl = 0, lstm_nb = 0, pred_gemm_impl = 0, fuse_ln = 3;
   int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
@@ -493,8 +493,9 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES_WT)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(false, 16))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(true, 16))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(true, 8))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(style_pool_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (2 * 256 + 1) + 4) * 4)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(1))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(2))) != cudaSuccess) return e;
@@ -980,7 +981,11 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
   else if (!strcmp(key, "gemm_impl")) {
     if (H->gemm_impl != value) drop_graphs(H);
     H->gemm_impl = value;
-  } else if (!strcmp(key, "lstm_impl")) H->lstm_impl = value;
+  } else if (!strcmp(key, "lstm_impl") || !strcmp(key, "lstm_nb")) {
+    if (!strcmp(key, "lstm_nb") && value != 0 && value != 8 && value != 16) return fail(H, STZ_E_ARG, "lstm_nb must be 0, 8 or 16");
+    drop_graphs(H);
+    (key[5] == 'i' ? H->lstm_impl : H->lstm_nb) = value;
+  }
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
   else if (!strcmp(key, "fuse_ln") || !strcmp(key, "gln_tile_rows") || !strcmp(key, "attn_box2") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
            !strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // baked into captured graphs
@@ -1029,6 +1034,7 @@ extern "C" int stz_get_option(const stz_handle* H, const char* key, int* value) 
   else if (!strcmp(key, "attn_impl")) *value = H->attn_impl;
   else if (!strcmp(key, "chains")) *value = H->chains;
   else if (!strcmp(key, "lstm_impl")) *value = H->lstm_impl;
+  else if (!strcmp(key, "lstm_nb")) *value = H->lstm_nb;
   else if (!strcmp(key, "pred_gemm_impl")) *value = H->pred_gemm_impl;
   else if (!strcmp(key, "profile")) *value = H->profile;
   else if (!strcmp(key, "guard_bytes")) *value = H->guard_bytes;
@@ -1073,17 +1079,32 @@ extern "C" int stz_debug_check_guards(stz_handle* H, long long* bad_bytes) {
   return n;
 }
 
+// BiLSTM recurrence on tcgen05 (predictor_tc.cuh).  Sequences per cluster: 8 for B <= 16 (half the per-step DSMEM exchange:
+// -10 % on the whole predictor), else 16 — beyond 4 clusters the 8-sequence form measured SLOWER (clusters sharing a GPC
+// share its DSMEM bandwidth, and only 15 clusters of 8 are co-resident: profiles/r02_ab_lstm_forms.txt).
+// lstm_impl 3 = W_hh operand in shared memory (A/B baseline).
+static void launch_lstm_tc(stz_handle* H, cudaStream_t st, const float* G, const float* whh, const int* lens, const int* perm,
+                           float* out, int B, int T) {
+  if (H->lstm_impl == 3) {
+    launch_k(lstm_tc_kernel<false, 16>, dim3(cdiv(B, 16) * LC_CS, 2), lt_threads(16), lt_smem_bytes(false, 16), st, G, whh, lens, perm, out, B, T);
+    return;
+  }
+  const int nb = H->lstm_nb != 0 ? H->lstm_nb : (B <= 16 ? 8 : 16);
+  if (nb == 8) launch_k(lstm_tc_kernel<true, 8>, dim3(cdiv(B, 8) * LC_CS, 2), lt_threads(8), lt_smem_bytes(true, 8), st, G, whh, lens, perm, out, B, T);
+  else launch_k(lstm_tc_kernel<true, 16>, dim3(cdiv(B, 16) * LC_CS, 2), lt_threads(16), lt_smem_bytes(true, 16), st, G, whh, lens, perm, out, B, T);
+}
+
 // Max co-resident 8-CTA clusters of the BiLSTM recurrence kernel on the current device (diagnostic).
 extern "C" int stz_debug_max_lstm_clusters(void) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(LC_CS * 64, 2); cfg.blockDim = dim3(LT_THREADS); cfg.dynamicSmemBytes = LT_SMEM_BYTES;
+  cfg.gridDim = dim3(LC_CS * 64, 2); cfg.blockDim = dim3(lt_threads(16)); cfg.dynamicSmemBytes = lt_smem_bytes(true, 16);
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = LC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = -1;
   if (init_kernel_attrs() != cudaSuccess) return -2;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<false>, &cfg) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<true, 16>, &cfg) != cudaSuccess) return -1;
   return n;
 }
 
@@ -1661,8 +1682,7 @@ static int predict_duration_impl(stz_handle* H, const float* text, const uint8_t
       ProfScope ps(H, st, PC_LSTM, 2.0 * BT * 2.0 * h * 4.0 * h);
       if (h == LC_H && (H->lstm_impl == 0 || H->lstm_impl == 3)) {  // product path (3: W_hh in shared memory instead of tensor memory, A/B): recurrent product on tcgen05 (split-bf16), cluster of 8 CTAs, DSMEM exchange
         const float* whh = H->whh + (size_t)l * 2 * 4 * h * h;
-        if (H->lstm_impl == 0) launch_k(lstm_tc_kernel<true>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES_WT, st, w.G, whh, w.lens, w.perm, xo, B, T);
-        else launch_k(lstm_tc_kernel<false>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, w.G, whh, w.lens, w.perm, xo, B, T);
+        launch_lstm_tc(H, st, w.G, whh, w.lens, w.perm, xo, B, T);
       } else {
         lstm_rec_kernel<NB><<<dim3(cdiv(B, NB), 2), 4 * h, lstm_smem, st>>>(w.G, H->whhT + (size_t)l * 2 * h * 4 * h, w.lens, xo, B, T, h);
       }
@@ -1816,12 +1836,7 @@ extern "C" int stz_predict_prosody(stz_handle* H, const float* text_emb_dev, con
   RET(gemm3(H->wih3_pros, H->lstm_b_pros, w.G, 8 * h));
   {
     ProfScope ps(H, st, PC_LSTM, 2.0 * BF * 2.0 * h * 4.0 * h);
-    if (H->lstm_impl == 3)
-      launch_k(lstm_tc_kernel<false>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES, st, (const float*)w.G, (const float*)H->whh_pros,
-               (const int*)w.flens, (const int*)w.perm, w.y, B, F_max);
-    else
-      launch_k(lstm_tc_kernel<true>, dim3(cdiv(B, LT_NB) * LC_CS, 2), LT_THREADS, LT_SMEM_BYTES_WT, st, (const float*)w.G, (const float*)H->whh_pros,
-               (const int*)w.flens, (const int*)w.perm, w.y, B, F_max);
+    launch_lstm_tc(H, st, w.G, H->whh_pros, w.flens, w.perm, w.y, B, F_max);
     KCHECK(H);
   }
   // z = [y | s_frame] W_h1^T + b_h1 (the s_frame columns of the operand are still in place), then the two heads

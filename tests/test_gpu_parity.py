@@ -112,6 +112,31 @@ def test_predict_duration_vs_golden(path, name):
     assert bool((d[~m] == 0).all()) and bool((d[m] >= 1).all()) and int(d.max()) <= CFG.max_dur
 
 
+@pytest.mark.parametrize("knobs", [{"lstm_nb": 8}, {"lstm_nb": 16}, {"lstm_impl": 3}], ids=["nb8", "nb16", "w_smem"])
+@pytest.mark.parametrize("B", [5, 21])
+def test_lstm_forms_vs_oracle(path, oracle, knobs, B):
+    """Every form of the tcgen05 BiLSTM recurrence (8 / 16 sequences per cluster, W_hh in tensor / shared memory) against
+    the oracle on a ragged batch (packed-sequence semantics, a partial last cluster), and bit-identical to each other."""
+    T = 40
+    inp = stz.synthetic_inputs(CFG, B, T, steps=1, seed=4321)
+    lens = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(B))
+    lens[0] = T
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    style = 0.7 * torch.randn(B, CFG.n_style, CFG.d_style, generator=torch.Generator().manual_seed(9))
+    d_ref, s_ref = oracle.predict_duration(inp["text_emb"], style, text_mask=mask, return_presum=True)
+    d0, s0 = path.predict_duration(inp["text_emb"], style, text_mask=mask, return_presum=True)
+    try:
+        for k, v in knobs.items():
+            path.set_option(k, v)
+        d, s = path.predict_duration(inp["text_emb"], style, text_mask=mask, return_presum=True)
+    finally:
+        path.set_option("lstm_nb", 0)
+        path.set_option("lstm_impl", 0)
+    assert float((s.cpu()[mask] - s_ref[mask]).abs().max()) < 2e-3
+    assert float((d.cpu()[mask] == d_ref[mask]).float().mean()) >= TOL_DUR_AGREE
+    assert torch.equal(d.cpu(), d0.cpu()) and torch.equal(s.cpu()[mask], s0.cpu()[mask])
+
+
 def test_cfg1_single_utterance_vs_oracle(path, oracle):
     """BASELINE configs[0]: 1 utterance, distilled 1-step sampling + duration predictor."""
     inp = stz.synthetic_inputs(CFG, 1, 64, steps=1, seed=1234)
