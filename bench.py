@@ -311,10 +311,11 @@ def predictor_leg(torch, path, cfg, dev, z, B, T, flush, n_timed):
                    "achieved_gbs = algorithmic bytes of the fp32 elementwise kernels (each input + output tensor once) / "
                    "their summed event time; measured dram__bytes per kernel: ncu_dram (profiles/r02_ncu_predictor.json)",
             "classes": cls, "ncu_dram": ncu,
-            "binds": "neither HBM nor FMA throughput: the BiLSTM's serial chain (T steps x n_lstm layers x ~1.7 us per "
-                     "recurrent step: tcgen05 issue floor + gate math + DSMEM exchange of h_t across the 8-CTA cluster); "
+            "binds": "neither HBM nor FMA throughput: the BiLSTM's serial chain (T steps x n_lstm layers x ~1.15 us per "
+                     "recurrent step: DSMEM exchange of h_t across the 8-CTA cluster ~1.1 k cycles + 32 tcgen05.mma with W_hh "
+                     "in tensor memory ~0.5 k + gate math; profiles/r02_ab_lstm_forms.txt); "
                      "the working set (< 40 MB at cfg2) is L2-resident, so the elementwise kernels' GB/s is L2 traffic",
-            "chain_us": T * nl * 1.7}
+            "chain_us": T * nl * 1.15}
 
 
 def config_legs(torch, stz, path, cfg, flush):
@@ -399,7 +400,7 @@ def config_legs(torch, stz, path, cfg, flush):
                             "path_rtf": (ms * 1e-3) / (frames / FRAMES_PER_S) if frames else None,
                             "cpu_oracle": {"utt_per_s": nb / o_s, "seconds": o_s, "threads": threads,
                                            "sample": f"the first {nb} utterances, one pass, fp32 PyTorch oracle"},
-                            "bound": "the frame BiLSTM's serial chain: longest utterance's frame count x ~1.9 us per recurrent step"}
+                            "bound": "the frame BiLSTM's serial chain: longest utterance's frame count x ~1.2 us per recurrent step"}
     return out
 
 
