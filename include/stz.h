@@ -193,6 +193,8 @@ int stz_reserve(stz_handle* h, int max_B, int max_T, int max_P, int max_steps, i
  *   "gln_tile_rows"  0 | 8..128   rows per CTA pair of that kernel: heuristic (96 where one wave still fits, else 128) | forced
  *   "attn_impl"      0 | 2        tcgen05 + TMA attention (resident keys; streaming over 128-key blocks for long text; the
  *                                 mma.sync streaming kernel beyond their shapes: P > 127, K > 64) | always the mma.sync kernel
+ *   "attn_ctas"      0 | 2 | 4    resident-key attention kernel: by unit count (4 CTAs/SM with one unit in flight each where all
+ *                                 units then fit one wave, else 2 persistent CTAs/SM with prefetch) | forced
  *   "attn_box2"      1 | 0        one TMA box per attention operand (both CFG branches, permuted tensor map) | one box per branch
  *   "chains"         1 | 2..8     utterance chains on parallel graph branches
  *   "lstm_impl"      0 | 1 | 3    tcgen05 cluster recurrence, W_hh in tensor memory | generic kernel | tcgen05, W_hh in shared memory

@@ -648,6 +648,286 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------
+// attention_tc4_kernel — the same contractions with ONE unit in flight per CTA and FOUR CTAs per SM.
+//
+// attention_tc2_kernel's timeline (tools/att_trace.py) is a serial chain per unit — operands land, S = Q K^T, row max,
+// exp + P, P V, normalise + store: ~4.7 k cycles — and at cfg2 (512 units) its 296 persistent CTAs run that chain twice
+// behind a ~2 k-cycle issue prologue.  Here a CTA is 4 warps (thread = query row = TMEM lane: no cross-warp row
+// statistics, two block barriers fewer), one operand buffer (48 KB) and 128 TMEM columns (the O accumulator
+// overwrites S, which is dead once P is in shared memory), so four CTAs share an SM and all 512 units of cfg2 run in
+// one wave: the chain is paid once and the four CTAs fill each other's bubbles.
+// ------------------------------------------------------------------------------------------------------
+constexpr int ATC4_SMEM_BYTES = ATC_BUF_BYTES + 1024;
+
+__global__ void __launch_bounds__(128, 4) attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                               const __grid_constant__ CUtensorMap tmT,
+                                                               const __grid_constant__ CUtensorMap tmP,
+                                                               const __grid_constant__ CUtensorMap tmN,
+                                                               const AttnTcParams p) {
+  extern __shared__ uint8_t atc_smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full, bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t colmask[2][4];        // [branch][32-key chunk]
+  const uint32_t smem_base = (smem_u32(atc_smem_raw) + 1023u) & ~1023u;
+  const uint32_t qs = smem_base, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index provably uniform
+  const int row = tid;                                 // query row = TMEM lane
+  const int br = row >> 6;                             // rows 0..63 conditional, 64..127 unconditional (warp-uniform)
+  const int n_tok = p.n_style;
+#ifdef STZ_TRACE
+  long long* tr = (g_att_trace != nullptr && tid == 0 && blockIdx.x < 296) ? g_att_trace + blockIdx.x * 32 : nullptr;
+#else
+  constexpr long long* tr = nullptr;
+#endif
+  int tri = 0;
+#define ATC4_TR() do { if (tr != nullptr && tri < 32) tr[tri++] = clock64(); } while (0)
+  ATC4_TR();
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmT);
+    if (!p.self) { prefetch_tmap(&tmP); prefetch_tmap(&tmN); }
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  // V rows that no TMA box covers must be finite (p = 0 times NaN would poison O): see attention_tc2_kernel
+  if (!p.self || p.single) {
+    for (uint32_t o = tid * 16; o < ATC_TILE; o += 128 * 16) st_shared_v4(vs + o, 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot;        // O (64 columns) overwrites S (128 columns)
+  ATC4_TR();
+  const uint32_t nbox = p.single ? 1u : 2u;
+  const uint32_t tx_bytes = p.self ? 3u * nbox * 8192u : nbox * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
+  const bool pow2 = (p.n_heads & (p.n_heads - 1)) == 0;
+  const int hshift = 31 - __clz(p.n_heads);
+  // parts: 1 = Q (written by the previous kernel), 2 = K / V.  One elected lane per warp issues that warp's boxes; warp 0
+  // arms the barrier with the unit's total bytes (boxes of other warps may land first: the transaction count is signed).
+  auto produce_tma = [&](int b, int head, int parts) {
+    const uint32_t bar = smem_u32(&bar_full);
+    const int t0 = b * n_tok, hc = head * ATT_DH;
+    if (!elect_one()) return;
+    if (parts & 2) {
+      if (warp == 0) mbar_expect_tx(&bar_full, tx_bytes);
+      if (p.self) {
+        if (p.box2) {
+          if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, t0, 0);
+          else if (warp == 1) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, t0, 0);
+        } else {
+          if (warp == 0) {
+            tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, 0, t0);
+            if (!p.single) tma_load_3d_u32(ks + 8192, &tmQ, bar, p.col_k + hc, 1, t0);
+          } else if (warp == 1) {
+            tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, 0, t0);
+            if (!p.single) tma_load_3d_u32(vs + 8192, &tmQ, bar, p.col_v + hc, 1, t0);
+          }
+        }
+      } else {
+        const uint32_t o1 = p.T8 * 128, o2 = (p.T8 + p.P8) * 128;
+        if (warp == 0) {
+          tma_load_2d_u32(ks, &tmT, bar, p.col_k + hc, b * p.T);
+          tma_load_2d_u32(vs, &tmT, bar, p.col_v + hc, b * p.T);
+        } else if (warp == 1) {
+          tma_load_2d_u32(ks + o1, &tmP, bar, p.col_k + hc, b * p.P);
+          tma_load_2d_u32(vs + o1, &tmP, bar, p.col_v + hc, b * p.P);
+        } else if (warp == 2) {
+          tma_load_2d_u32(ks + o2, &tmN, bar, p.col_k + hc, 0);
+          tma_load_2d_u32(vs + o2, &tmN, bar, p.col_v + hc, 0);
+        }
+      }
+    }
+    if (parts & 1) {
+      if (warp == 3) {
+        if (p.box2) {
+          tma_load_3d_u32(qs, &tmQ, bar, hc, t0, 0);
+        } else {
+          tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
+          if (!p.single) tma_load_3d_u32(qs + 8192, &tmQ, bar, hc, 1, t0);
+        }
+      }
+    }
+  };
+  auto unit_bh = [&](int unit, int& b, int& head) {
+    b = pow2 ? unit >> hshift : unit / p.n_heads;
+    head = unit - b * p.n_heads;
+  };
+  // The cross-attention K / V of a call are constants of the evaluation loop: the first unit's boxes are requested
+  // BEFORE griddepcontrol.wait and land while the previous kernel drains.
+  const bool kv_early = !p.self && static_cast<int>(blockIdx.x) < p.n_units;
+  if (kv_early) {
+    int b, head;
+    unit_bh(blockIdx.x, b, head);
+    produce_tma(b, head, 2);
+  }
+  pdl_sync();
+  ATC4_TR();
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  uint32_t phase = 0;
+  for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+    int b, head;
+    unit_bh(unit, b, head);
+    produce_tma(b, head, (kv_early && unit == static_cast<int>(blockIdx.x)) ? 1 : 3);
+    {   // visibility of key row `tid`: bit 0 = conditional queries, bit 1 = unconditional queries
+      uint8_t vis = 0;
+      if (p.self) {
+        vis = (tid & 63) < n_tok ? static_cast<uint8_t>(1u << (tid >> 6)) : 0;
+      } else if (tid < p.T) {
+        vis = (p.tmask == nullptr || p.tmask[static_cast<size_t>(b) * p.T + tid] != 0) ? 3 : 0;
+      } else if (tid >= p.T8 && tid < p.T8 + p.P) {
+        vis = (p.pmask == nullptr || p.pmask[static_cast<size_t>(b) * p.P + (tid - p.T8)] != 0) ? 1 : 0;
+      } else if (tid == p.T8 + p.P8) {
+        vis = 2;
+      }
+      // warp w holds the visibility of key chunk w
+      const uint32_t m0 = __ballot_sync(0xffffffffu, (vis & 1) != 0), m1 = __ballot_sync(0xffffffffu, (vis & 2) != 0);
+      if (lane == 0) { colmask[0][warp] = m0; colmask[1][warp] = m1; }
+    }
+    ATC4_TR();
+    mbar_wait(&bar_full, phase);
+    __syncthreads();              // colmask visible (and every thread past the barrier wait)
+    ATC4_TR();
+    if (warp == 0) {
+      tc_fence_after();
+      const uint64_t da = umma_desc_sw128(qs), db = umma_desc_sw128(ks);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&bar_s);
+      }
+      __syncwarp();
+    }
+    uint32_t cm[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cm[c] = colmask[br][c];
+    mbar_wait(&bar_s, phase);
+    tc_fence_after();
+    ATC4_TR();
+
+    // ---- pass 1: row max over the visible keys
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (cm[c] == 0) continue;   // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_s + lane_addr + c * 32, r);
+      tmem_ld_wait();
+      if (cm[c] == 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+      } else {   // partially visible chunk: mask, so that the result never depends on a neighbouring utterance's rows
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((cm[c] >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
+      }
+    }
+    const float mb = (mx == -INFINITY ? 0.f : mx) * p.scale_log2;
+    ATC4_TR();
+
+    // ---- pass 2: P = exp2(S * scale - max), masked, bf16, into the dead Q | K tiles (K-major, swizzled)
+    float lsum = 0.f;
+    const uint32_t prow = qs + row * 128, sw = row & 7;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t pb = prow + (c >> 1) * ATC_TILE;
+      if (cm[c] == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), 0u, 0u, 0u, 0u);
+        continue;
+      }
+      uint32_t r[32];
+      tmem_ld32(tmem_s + lane_addr + c * 32, r);
+      tmem_ld_wait();
+      float pv[32];
+      if (cm[c] == 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
+          lsum += pv[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
+          pv[j] = ((cm[c] >> j) & 1u) ? e : 0.f;
+          lsum += pv[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
+                     pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
+    }
+    ATC4_TR();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();              // P complete, every thread done reading S
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t da = umma_desc_sw128(qs + (j >> 2) * ATC_TILE) + 2 * (j & 3);
+          const uint64_t db = umma_desc_sw128_mn(vs + j * 2048);
+          umma_bf16(tmem_o, da, db, idesc_o, j != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_o);
+      }
+      __syncwarp();
+    }
+    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+    ATC4_TR();
+    mbar_wait(&bar_o, phase);
+    tc_fence_after();
+    ATC4_TR();
+    {  // out row = O / rowsum, staged in the (dead) Q tile so that the global stores are full 128-byte rows
+      const uint32_t orow = qs + row * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        tmem_ld32(tmem_o + lane_addr + h * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(orow + (((h * 4 + j) ^ (row & 7)) << 4),
+                       pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv),
+                       pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv),
+                       pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv),
+                       pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();     // O tile complete; TMEM is free again
+    {
+      __nv_bfloat16* obase = p.out + static_cast<size_t>(b) * p.n_q * p.ldo + head * ATT_DH;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int c = it * 128 + tid, orow_i = c >> 3, ch = c & 7;     // 8 x 16 B per 128-byte row
+        const int otok = orow_i & 63, obr = orow_i >> 6;
+        if (otok < n_tok && !(p.single && obr)) {
+          const uint4 v = lds_u4(qs + orow_i * 128 + ((ch ^ (orow_i & 7)) << 4));
+          *reinterpret_cast<uint4*>(obase + static_cast<size_t>(p.single ? otok : 2 * otok + obr) * p.ldo + ch * 8) = v;
+        }
+      }
+    }
+    fence_proxy_async();   // the next TMA boxes (async proxy) overwrite the staged tile
+    __syncthreads();       // the buffer is free again
+    ATC4_TR();
+    phase ^= 1u;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem_slot);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // attention_tcs_kernel — streaming form of attention_tc2_kernel for cross-attention over long text
 // (T8 + P8 + 1 > 128 keys, e.g. BASELINE cfg4: 512 text tokens + 50 prompt tokens + null).
 //

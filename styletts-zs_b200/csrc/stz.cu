@@ -149,6 +149,7 @@ struct stz_handle {
   int chains = 1;      // independent utterance chains (parallel graph branches) of the evaluation loop
   cudaStream_t chain_stream[STZ_MAX_CHAINS] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[STZ_MAX_CHAINS] = {};
+  int attn_ctas = 0;   // resident-key tcgen05 attention: 4 = one unit in flight per CTA, four CTAs per SM (attention_tc4_kernel); 2 = attention_tc2_kernel; 0 = by unit count
   int attn_impl = 0;   // 0 = tcgen05 + TMA kernels (resident keys, streaming for long text; mma.sync streaming beyond their shapes), 2 = always the mma.sync streaming kernel
   int attn_box2 = 1;       // knob "attn_box2": one TMA box per attention operand (both branches) | one box per branch
   int gln_tile_rows = 0;   // knob "gln_tile_rows": 0 = heuristic (gemmln3_tile_rows), else forced rows per CTA pair of the fused kernel
@@ -492,6 +493,7 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(gemmln3_kernel<GLN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GLN3_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC4_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(false, 16))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(true, 16))) != cudaSuccess) return e;
@@ -987,12 +989,13 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     (key[5] == 'i' ? H->lstm_impl : H->lstm_nb) = value;
   }
   else if (!strcmp(key, "pred_gemm_impl")) H->pred_gemm_impl = value;
-  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "gln_tile_rows") || !strcmp(key, "attn_box2") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
+  else if (!strcmp(key, "fuse_ln") || !strcmp(key, "gln_tile_rows") || !strcmp(key, "attn_box2") || !strcmp(key, "attn_ctas") || !strcmp(key, "ablate") || !strcmp(key, "attn_impl") || !strcmp(key, "chains") ||
            !strcmp(key, "gemm_bn") || !strcmp(key, "use_pdl") || !strcmp(key, "gemm_cluster")) {   // baked into captured graphs
     drop_graphs(H);
     if (!strcmp(key, "chains")) H->chains = value;
     else if (!strcmp(key, "ablate")) H->ablate = value;
     else if (!strcmp(key, "attn_impl")) H->attn_impl = value;
+    else if (!strcmp(key, "attn_ctas")) H->attn_ctas = value;
     else if (!strcmp(key, "gemm_bn")) H->gemm_bn = value;
     else if (!strcmp(key, "use_pdl")) H->use_pdl = value;
     else if (!strcmp(key, "gemm_cluster")) H->gemm_cluster = value;
@@ -1032,6 +1035,7 @@ extern "C" int stz_get_option(const stz_handle* H, const char* key, int* value) 
   else if (!strcmp(key, "fuse_ln")) *value = H->fuse_ln;
   else if (!strcmp(key, "gln_tile_rows")) *value = H->gln_tile_rows;
   else if (!strcmp(key, "attn_impl")) *value = H->attn_impl;
+  else if (!strcmp(key, "attn_ctas")) *value = H->attn_ctas;
   else if (!strcmp(key, "chains")) *value = H->chains;
   else if (!strcmp(key, "lstm_impl")) *value = H->lstm_impl;
   else if (!strcmp(key, "lstm_nb")) *value = H->lstm_nb;
@@ -1228,7 +1232,11 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
       tp_.tmask = sg[0].mask; tp_.pmask = sg[1].mask;
     }
     const int units = tp_.n_units;
-    launch_k(attention_tc2_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
+    // one wave of 4 CTAs/SM but not of 2 CTAs/SM (38 <= B <= 74 at 8 heads): attention_tc4_kernel measured -2 % on the cfg2
+    // step and -3.6 % on the guided student; outside that range attention_tc2_kernel (prefetching, 8 warps) is 1-3 % faster
+    const int ctas = H->attn_ctas != 0 ? H->attn_ctas : (units > 2 * g_num_sms && units <= 4 * g_num_sms ? 4 : 2);
+    if (ctas == 4) launch_k(attention_tc4_kernel, units < 4 * g_num_sms ? units : 4 * g_num_sms, 128, ATC4_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
+    else launch_k(attention_tc2_kernel, units < 2 * g_num_sms ? units : 2 * g_num_sms, 256, ATC_SMEM_BYTES, st, tq, tt, tp, tn, tp_);
   } else if (H->attn_impl == 0 && cross3 && ap.n_q <= 128 && n_style <= 64 && P8 + 1 <= 128) {
     // long text: streaming tcgen05 attention over 128-key blocks (attention_tcs_kernel)
     CUtensorMap tq, tt, tp, tn;

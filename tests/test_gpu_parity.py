@@ -234,6 +234,25 @@ def _attention_reference(q, k, v, vis):
 @pytest.mark.parametrize("impl", [0, 2], ids=["tcgen05_tma", "mma_streaming"])
 @pytest.mark.parametrize("B", [1, 5])
 def test_self_attention_vs_torch_fp32(path, impl, B):
+    _check_self_attention(path, impl, B)
+
+
+@pytest.mark.parametrize("ctas", [2, 4], ids=["tc2_two_ctas_per_sm", "tc4_four_ctas_per_sm"])
+def test_resident_attention_kernels_forced(path, ctas):
+    """Both resident-key tcgen05 attention kernels forced at shapes the dispatch would give to the other one: a single
+    unit wave, and more units than CTAs (B = 80: 640 units, attention_tc4_kernel's multi-unit loop without prefetch)."""
+    path.set_option("attn_ctas", ctas)
+    try:
+        for B in (2, 80):
+            _check_self_attention(path, 0, B)
+        for T, P in ((64, 50), (13, 50), (40, 7)):
+            _check_cross_attention(path, 0, T, P)
+        _check_cross_attention(path, 0, 64, 50, B=80)
+    finally:
+        path.set_option("attn_ctas", 0)
+
+
+def _check_self_attention(path, impl, B):
     d, K, H = CFG.d_model, CFG.n_style, CFG.n_heads
     g = torch.Generator().manual_seed(10 + B)
     qkv = torch.randn(2 * B * K, 3 * d, generator=g).bfloat16().cuda()
@@ -250,13 +269,17 @@ def test_self_attention_vs_torch_fp32(path, impl, B):
 @pytest.mark.parametrize("impl", [0, 2], ids=["tcgen05_tma", "mma_streaming"])
 @pytest.mark.parametrize("T,P", [(64, 50), (13, 50), (40, 7), (100, 50), (300, 50), (512, 50), (129, 3)])
 def test_cross_attention_vs_torch_fp32(path, impl, T, P):
-    d, K, H, B = CFG.d_model, CFG.n_style, CFG.n_heads, 3
+    _check_cross_attention(path, impl, T, P)
+
+
+def _check_cross_attention(path, impl, T, P, B=3):
+    d, K, H = CFG.d_model, CFG.n_style, CFG.n_heads
     g = torch.Generator().manual_seed(100 + T)
     q = torch.randn(2 * B * K, d, generator=g).bfloat16().cuda()
     kt = torch.randn(B * T, 2 * d, generator=g).bfloat16().cuda()
     kp = torch.randn(B * P, 2 * d, generator=g).bfloat16().cuda()
     kn = torch.randn(1, 2 * d, generator=g).bfloat16().cuda()
-    tlen = torch.tensor([T, max(1, T // 2), max(1, T - 3)])
+    tlen = torch.tensor([T, max(1, T // 2), max(1, T - 3)] * ((B + 2) // 3))[:B]
     tm = torch.arange(T)[None] < tlen[:, None]
     pm = torch.ones(B, P, dtype=torch.bool)
     pm[1, P // 2:] = False
@@ -410,12 +433,14 @@ def test_cfg2_full_size_properties(path):
                                noise=inp["noise"][:, i:i + 1])
         assert rel(zi[0], z[i]) < 5e-3      # B = 1 runs GEMM + LayerNorm kernels, the batch the fused kernel: bf16-noise level
     path.set_option("fuse_ln", 4)           # same kernels at every size -> invariance to ~fp32 reduction order
+    path.set_option("attn_ctas", 2)         # (the dispatch picks the attention kernel by unit count as well)
     z4 = run()
     for i in (0, 17, 63):
         zi = path.sample_style(inp["text_emb"][i:i + 1], inp["prompt_feats"][i:i + 1], steps, 2.0,
                                noise=inp["noise"][:, i:i + 1])
         assert rel(zi[0], z4[i]) < 1e-3
     path.set_option("fuse_ln", 3)
+    path.set_option("attn_ctas", 0)
     # permutation equivariance
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
     zp = run(text=inp["text_emb"][perm], prompt=inp["prompt_feats"][perm], noise=inp["noise"][:, perm])

@@ -31,6 +31,8 @@ for which, bits in (("cross-attention", 0), ("self-attention", 2)):
         row = t[cta]
         d = [int(row[i] - row[0]) for i in range(21)]
         print(f"  cta {cta:3d}: " + "  ".join(f"{n}={v}" for n, v in zip(names, d) if v > 0))
+    ex = (t[:216, 24:30] - t[:216, 2:3]).float().mean(0)
+    print("  produce detail (cycles after the pdl stamp): unit0 [enter, tma issued, vis stored], next unit [enter, tma issued, vis stored]:", [int(x) for x in ex])
     two = t[:216]
     dd = (two[:, 1:21] - two[:, 0:20]).float().mean(0)
     print("  mean phase cycles (CTAs with 2 units):", {names[i + 1]: int(dd[i]) for i in range(20)})
