@@ -284,10 +284,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   // so only the A tiles (its output) are fetched on the critical path after the dependency resolves.
   constexpr int kPre = STAGES;
   int n_pre = 0;
+  // first tile's coordinates: the integer division runs here, under the previous kernel's tail, not behind the dependency wait
+  const int first_q = unit0 / tiles_n, first_r = unit0 - first_q * tiles_n;
   if constexpr (CM == 1) {
     if (warp == 0 && lane == 0 && unit0 < n_tiles && p.tile_needed == nullptr) {   // (the skip list is produced upstream: not readable yet)
       n_pre = num_kb < kPre ? num_kb : kPre;
-      const int tile_n0 = unit0 % tiles_n;
+      const int tile_n0 = first_r;
       for (int s = 0; s < n_pre; ++s) {
         mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
         asm volatile(
@@ -307,11 +309,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      bool ring_fresh = true;     // no stage has been handed to the MMA warp yet: the first ring needs no empty-barrier wait
       for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
-        const int tile_m = CM * (tile / tiles_n) + crank, tile_n = tile % tiles_n;
+        const int tq = tile == unit0 ? first_q : tile / tiles_n;
+        const int tile_m = CM * tq + crank, tile_n = tile == unit0 ? first_r : tile - tq * tiles_n;
         if (CM == 1 && p.tile_needed != nullptr && p.tile_needed[tile_m] == 0) continue;   // all-padding rows
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          // (a passing mbarrier.try_wait still costs the issuing lane ~200 cycles: skipped while the ring is fresh)
+          if (!(ring_fresh && kb < STAGES)) mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (kb == num_kb - 1) ring_fresh = false;
           const uint32_t sa = smem_base + stage * (A_BYTES + B_BYTES);
           if constexpr (CM == 1) {
             const bool pre = tile == unit0 && kb < n_pre;   // this stage's W tile (and its expect_tx) went out before the wait

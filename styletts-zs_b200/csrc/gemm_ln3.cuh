@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(GLN_THREADS, 1) gemmln3_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (kb >= GLN3_STAGES) mbar_wait(&empty_bar[stage], phase ^ 1u);   // (the first ring is free by construction: a passing
+                                                                           // try_wait still costs the issuing lane ~200 cycles)
         const uint32_t sa = ring + stage * GLN3_STAGE_BYTES;
         if (kb >= n_pre) {
           mbar_expect_tx(&full_bar[stage], stage_tx);
