@@ -355,6 +355,12 @@ struct AttnTcParams {
                            // cycles each per SM: tools/att_trace.py); 0: (column, branch, token) map, one box per branch
 };
 
+// utterance index of an (utterance, head) unit: a shift when the head count is a power of two (an integer division on the
+// uniform datapath is a ~250-cycle dependent chain, and it sits in front of every unit's first TMA issue)
+__device__ __forceinline__ int unit_utt(int unit, int n_heads) {
+  return (n_heads & (n_heads - 1)) == 0 ? unit >> (31 - __clz(n_heads)) : unit / n_heads;
+}
+
 __device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   // other warps may complete before that — the transaction count is signed and the phase cannot complete before warp
   // 0's arrive.
   auto produce_tma = [&](int unit, int buf, int parts) {
-    const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+    const int b = unit_utt(unit, p.n_heads), head = unit - b * p.n_heads;
     const uint32_t qs = smem_base + buf * ATC_BUF_BYTES, ks = qs + ATC_TILE, vs = ks + ATC_TILE;
     const uint32_t bar = smem_u32(&bar_full[buf]);
     const int t0 = b * n_tok, hc = head * ATT_DH;
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
   ATC2_TR();
 
   auto produce = [&](int unit, int buf, int parts) {
-    const int b = unit / p.n_heads;
+    const int b = unit_utt(unit, p.n_heads);
     produce_tma(unit, buf, parts);
     if (tid < 128) {   // visibility of key row `tid`: bit 0 = conditional queries, bit 1 = unconditional queries
       uint8_t vis = 0;
@@ -532,9 +538,13 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
       uint32_t r[32];
       tmem_ld32(tmem_s + lane_addr + (half + 2 * ci) * 32, r);
       tmem_ld_wait();
-      if (cm == 0xffffffffu) {
+      if (cm == 0xffffffffu) {   // four independent chains (a single running max is a 16-deep dependent FMNMX chain per chunk)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+        for (int j = 0; j < 32; j += 8)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m4[i], fmaxf(__uint_as_float(r[j + 2 * i]), __uint_as_float(r[j + 2 * i + 1])));
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       } else {   // partially visible chunk: mask, so that the result never depends on a neighbouring utterance's rows
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((cm >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
@@ -563,20 +573,22 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
       tmem_ld32(tmem_s + lane_addr + c * 32, r);
       tmem_ld_wait();
       float pv[32];
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};     // four independent partial sums (one running sum is a 32-deep FADD chain per chunk)
       if (cm == 0xffffffffu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
-          lsum += pv[j];
+          l4[j & 3] += pv[j];
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
           pv[j] = ((cm >> j) & 1u) ? e : 0.f;
-          lsum += pv[j];
+          l4[j & 3] += pv[j];
         }
       }
+      lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
@@ -603,7 +615,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     }
     const float ltot = psum[0][row] + psum[1][row];
     const float inv = ltot > 0.f ? 1.f / ltot : 0.f;
-    const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+    const int b = unit_utt(unit, p.n_heads), head = unit - b * p.n_heads;
     ATC2_TR();
     mbar_wait(&bar_o, phase);
     tc_fence_after();
@@ -705,8 +717,6 @@ __global__ void __launch_bounds__(128, 4) attention_tc4_kernel(const __grid_cons
   ATC4_TR();
   const uint32_t nbox = p.single ? 1u : 2u;
   const uint32_t tx_bytes = p.self ? 3u * nbox * 8192u : nbox * 8192u + 2u * 128u * static_cast<uint32_t>(p.T + p.P + 1);
-  const bool pow2 = (p.n_heads & (p.n_heads - 1)) == 0;
-  const int hshift = 31 - __clz(p.n_heads);
   // parts: 1 = Q (written by the previous kernel), 2 = K / V.  One elected lane per warp issues that warp's boxes; warp 0
   // arms the barrier with the unit's total bytes (boxes of other warps may land first: the transaction count is signed).
   auto produce_tma = [&](int b, int head, int parts) {
@@ -754,7 +764,7 @@ __global__ void __launch_bounds__(128, 4) attention_tc4_kernel(const __grid_cons
     }
   };
   auto unit_bh = [&](int unit, int& b, int& head) {
-    b = pow2 ? unit >> hshift : unit / p.n_heads;
+    b = unit_utt(unit, p.n_heads);
     head = unit - b * p.n_heads;
   };
   // The cross-attention K / V of a call are constants of the evaluation loop: the first unit's boxes are requested
@@ -820,9 +830,13 @@ __global__ void __launch_bounds__(128, 4) attention_tc4_kernel(const __grid_cons
       uint32_t r[32];
       tmem_ld32(tmem_s + lane_addr + c * 32, r);
       tmem_ld_wait();
-      if (cm[c] == 0xffffffffu) {
+      if (cm[c] == 0xffffffffu) {   // four independent chains (a single running max is a 16-deep dependent FMNMX chain per chunk)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+        for (int j = 0; j < 32; j += 8)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m4[i], fmaxf(__uint_as_float(r[j + 2 * i]), __uint_as_float(r[j + 2 * i + 1])));
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       } else {   // partially visible chunk: mask, so that the result never depends on a neighbouring utterance's rows
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((cm[c] >> j) & 1u) ? __uint_as_float(r[j]) : -INFINITY);
@@ -846,20 +860,22 @@ __global__ void __launch_bounds__(128, 4) attention_tc4_kernel(const __grid_cons
       tmem_ld32(tmem_s + lane_addr + c * 32, r);
       tmem_ld_wait();
       float pv[32];
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};     // four independent partial sums (one running sum is a 32-deep FADD chain per chunk)
       if (cm[c] == 0xffffffffu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
-          lsum += pv[j];
+          l4[j & 3] += pv[j];
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb));
           pv[j] = ((cm[c] >> j) & 1u) ? e : 0.f;
-          lsum += pv[j];
+          l4[j & 3] += pv[j];
         }
       }
+      lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         st_shared_v4(pb + ((((c & 1) * 4 + j) ^ sw) << 4), pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
@@ -1017,7 +1033,7 @@ __global__ void __launch_bounds__(256, 2) attention_tcs_kernel(const __grid_cons
   };
 
   for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
-    const int b = unit / p.n_heads, head = unit - b * p.n_heads;
+    const int b = unit_utt(unit, p.n_heads), head = unit - b * p.n_heads;
     // text masks are prefix masks: a text block whose first key is padding is padding throughout and is skipped
     int nbv = nbt;
     if (p.tmask != nullptr) {

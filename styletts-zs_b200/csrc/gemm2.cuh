@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       for (int tile = unit0; tile < n_tiles; tile += unit_stride) {
         if (CM == 1 && p.tile_needed != nullptr && p.tile_needed[tile / tiles_n] == 0) continue;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        if (tcount >= 2) mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);    // (both accumulators start out free)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
