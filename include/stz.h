@@ -198,7 +198,8 @@ int stz_reserve(stz_handle* h, int max_B, int max_T, int max_P, int max_steps, i
  *   "attn_box2"      1 | 0        one TMA box per attention operand (both CFG branches, permuted tensor map) | one box per branch
  *   "chains"         1 | 2..8     utterance chains on parallel graph branches
  *   "lstm_impl"      0 | 1 | 3    tcgen05 cluster recurrence, W_hh in tensor memory | generic kernel | tcgen05, W_hh in shared memory
- *   "lstm_nb"        0 | 8 | 16   sequences per 8-CTA cluster of that kernel: 8 for batches <= 16, else 16 | forced
+ *   "lstm_nb"        0 | 8|16|24  sequences per 8-CTA cluster of that kernel: 8 for batches <= 16, else the one of 16 / 24 with
+ *                                 fewer waves x step time (15 clusters are co-resident) | forced
  *   "pred_gemm_impl" 0 | 1        split-bf16 tcgen05 predictor GEMMs | fp32 CUDA-core GEMMs
  *   "profile"        0 | 1        see stz_profile_read;   "ablate" (bit mask): tools/ablate.py timing attribution only
  * Knobs are per handle (two handles on two host threads do not interact).  Returns STZ_E_ARG for unknown keys. */

@@ -22,9 +22,10 @@
 
 namespace stz {
 
-// NB = sequences per cluster (16, or 8 for B <= 16: every CTA sends its 32 new units of NB sequences to all 8 CTAs each
-// step = NB KB out of the SM at the ~17 B/clk DSMEM rate — with W_hh in tensor memory that exchange is the largest part
-// of the step: 2.26 k cycles per step at NB = 16, 1.51 k at NB = 8, but only while few clusters run, see launch_lstm_tc).
+// NB = sequences per cluster (8, 16 or 24: every CTA sends its 32 new units of NB sequences to all 8 CTAs each step = NB KB
+// out of the SM at the ~17 B/clk DSMEM rate — with W_hh in tensor memory that exchange is the largest part of the step:
+// 1.51 k cycles per step at NB = 8, 2.26 k at 16, ~3.0 k at 24.  Only 15 clusters of 8 CTAs are co-resident on a B200,
+// so the host picks the NB that minimises waves x step time, see launch_lstm_tc).
 constexpr int LT_W_TILE = 128 * 128;                     // one 128-row x 64-k bf16 tile
 constexpr int LT_W_BYTES = 2 * 4 * LT_W_TILE;            // hi, lo x 4 k-blocks = 128 KB
 constexpr int lt_threads(int nb) { return nb * 32 < 256 ? 256 : nb * 32; }      // warp = sequence; warps 0..5 also drain / issue
@@ -36,7 +37,7 @@ constexpr int lt_smem_bytes(bool w_tmem, int nb) { return (w_tmem ? 0 : LT_W_BYT
 // 32-bit column = two consecutive k (bf16 pair) -> 128 columns for W_hi + 128 for W_lo behind the 64 accumulator columns.
 // Every recurrent MMA then reads its A slab from TMEM instead of streaming 4 KB from shared memory (~84 cycles per MMA
 // whatever N: the 32 MMAs of a step were 1.34 k of its 3.28 k cycles, profiles/r02_lstm_trace.txt).
-constexpr int LT_TMEM_W_HI = 64, LT_TMEM_W_LO = 64 + 128;
+constexpr int LT_TMEM_W_HI = 128, LT_TMEM_W_LO = 128 + 128;   // behind the accumulators (3 NB <= 80 columns)
 
 // D[tmem] (+)= A[tmem] * B[smem]^T: A operand from tensor memory (K-major: lane = row, 32-bit column = a k pair)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -79,7 +80,8 @@ __global__ void __cluster_dims__(LC_CS, 1, 1) __launch_bounds__(lt_threads(NB), 
 lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const int* __restrict__ lens,
                const int* __restrict__ perm, float* __restrict__ out, int B, int T) {
   constexpr int LT_NB = NB, LT_THREADS = lt_threads(NB), LT_H_TILE = lt_h_tile(NB), LT_H_BYTES = lt_h_bytes(NB);
-  static_assert(NB == 8 || NB == 16, "operand rows [h_hi ; h_lo] = 2 NB must be a multiple of the 8-row swizzle atom and an MMA N");
+  static_assert(NB == 8 || NB == 16 || NB == 24, "operand rows [h_hi ; h_lo] = 2 NB must be a multiple of the 8-row swizzle atom and an MMA N");
+  constexpr int N2 = (NB + 15) / 16 * 16;     // N of the W_lo pass (M = 128 needs N % 16 == 0; rows beyond NB are h_lo rows, their columns are never read)
   extern __shared__ uint8_t lt_smem_raw[];
   __shared__ __align__(8) uint64_t hbar[2], mma_bar;
   __shared__ uint32_t tmem_slot;
@@ -190,8 +192,7 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
   const uint32_t dst_off = (k0 >> 6) * LT_H_TILE + ((lane & 1) * LT_NB + warp) * 128 +
                            ((((k0 & 63) >> 3) ^ (warp & 7)) << 4) + (k0 & 7) * 2;
   constexpr uint32_t kStepBytes = LT_NB * LC_H * 4;      // hi + lo of 16 x 256 values
-  // (M = 128 needs N % 16 == 0: at NB = 8 the W_lo pass also runs over all 16 rows; its h_lo columns are never read)
-  constexpr uint32_t idesc32 = umma_idesc_bf16(128, 2 * LT_NB), idesc16 = umma_idesc_bf16(128, LT_NB < 16 ? 16 : LT_NB);
+  constexpr uint32_t idesc32 = umma_idesc_bf16(128, 2 * LT_NB), idesc16 = umma_idesc_bf16(128, N2);
   constexpr int H_BUF = 4 * LT_H_TILE;                   // bytes per buffer
   // remote addresses of this lane's operand word and of the step barriers in all 8 CTAs (hoisted out of the step loop)
   uint32_t rdst[LC_CS], rbar[LC_CS];
@@ -246,21 +247,16 @@ lstm_tc_kernel(const float* __restrict__ G, const float* __restrict__ Whh, const
       mbar_wait(&mma_bar, s & 1);
       if (tr != nullptr && warp == 0 && s < 64) tr[s * 8 + 3] = clock64();
       tc_fence_after();
-      uint32_t r[32], r2[16];
-      if constexpr (NB == 16) {
-        tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), r);
-        tmem_ld16(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + 2 * LT_NB, r2);
-      } else {                     // columns 0..15 = W_hi [h_hi ; h_lo], 16..23 = W_lo h_hi
-        tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), r);
-      }
+      // accumulator columns: [0, NB) W_hi h_hi, [NB, 2 NB) W_hi h_lo, [2 NB, 3 NB) W_lo h_hi
+      const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+      uint32_t a[32], b[NB > 8 ? (NB > 16 ? 32 : 16) : 1], c[NB > 16 ? 16 : 1];
+      tmem_ld32(lane_base, a);
+      if constexpr (NB == 16) tmem_ld16(lane_base + 32, b);
+      if constexpr (NB == 24) { tmem_ld32(lane_base + 32, b); tmem_ld16(lane_base + 64, c); }
       tmem_ld_wait();
-      if constexpr (NB != 16) {
+      auto col = [&](int i) -> float { return __uint_as_float(i < 32 ? a[i & 31] : (i < 64 ? b[(i & 31) % (NB > 16 ? 32 : 16)] : c[(i & 15) % (NB > 16 ? 16 : 1)])); };
 #pragma unroll
-        for (int n = 0; n < NB; ++n) r2[n] = r[2 * NB + n];
-      }
-#pragma unroll
-      for (int n = 0; n < LT_NB; ++n)
-        pre_s[n * LC_COLS + tid] = (__uint_as_float(r[n]) + __uint_as_float(r[LT_NB + n])) + __uint_as_float(r2[n]);
+      for (int n = 0; n < LT_NB; ++n) pre_s[n * LC_COLS + tid] = (col(n) + col(LT_NB + n)) + col(2 * LT_NB + n);
       tc_fence_before();
     }
     __syncthreads();

@@ -365,6 +365,7 @@ constexpr int GEMM_BN = 128;   // N granularity of every GEMM
 
 // ---- persistent, TMEM double-buffered, TMA-store epilogue (gemm2.cuh) ------------------------------
 static int g_num_sms = 148;
+static int g_lstm_max_clusters = 15;   // co-resident 8-CTA clusters of lstm_tc_kernel (queried at init)
 
 static int pick_bn(int M, int N) {
   const int bn_override = tl_launch.gemm_bn;   // tuning knob ("gemm_bn"): 0 = heuristic
@@ -498,6 +499,7 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(lstm_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(false, 16))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(true, 16))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(true, 8))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lstm_tc_kernel<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(true, 24))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(style_pool_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * (2 * 256 + 1) + 4) * 4)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(1))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dur_head2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dur_head2_smem(2))) != cudaSuccess) return e;
@@ -505,6 +507,17 @@ static cudaError_t init_kernel_attrs() {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     g_num_sms = sms;
+  {  // co-resident 8-CTA clusters of the BiLSTM recurrence (its wave model: lstm_pick_nb)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(LC_CS * 64, 2); cfg.blockDim = dim3(lt_threads(16)); cfg.dynamicSmemBytes = lt_smem_bytes(true, 16);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = LC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<true, 16>, &cfg) == cudaSuccess && n > 0) g_lstm_max_clusters = n;
+    else (void)cudaGetLastError();
+  }
   return cudaSuccess;
 }
 
@@ -984,7 +997,7 @@ extern "C" int stz_set_option(stz_handle* H, const char* key, int value) {
     if (H->gemm_impl != value) drop_graphs(H);
     H->gemm_impl = value;
   } else if (!strcmp(key, "lstm_impl") || !strcmp(key, "lstm_nb")) {
-    if (!strcmp(key, "lstm_nb") && value != 0 && value != 8 && value != 16) return fail(H, STZ_E_ARG, "lstm_nb must be 0, 8 or 16");
+    if (!strcmp(key, "lstm_nb") && value != 0 && value != 8 && value != 16 && value != 24) return fail(H, STZ_E_ARG, "lstm_nb must be 0, 8, 16 or 24");
     drop_graphs(H);
     (key[5] == 'i' ? H->lstm_impl : H->lstm_nb) = value;
   }
@@ -1083,33 +1096,40 @@ extern "C" int stz_debug_check_guards(stz_handle* H, long long* bad_bytes) {
   return n;
 }
 
-// BiLSTM recurrence on tcgen05 (predictor_tc.cuh).  Sequences per cluster: 8 for B <= 16 (half the per-step DSMEM exchange:
-// -10 % on the whole predictor), else 16 — beyond 4 clusters the 8-sequence form measured SLOWER (clusters sharing a GPC
-// share its DSMEM bandwidth, and only 15 clusters of 8 are co-resident: profiles/r02_ab_lstm_forms.txt).
+// BiLSTM recurrence on tcgen05 (predictor_tc.cuh).  Sequences per cluster = the NB in {8, 16, 24} that minimises
+// waves x step time.  Only g_lstm_max_clusters (15 on a B200: one GPC holds a single cluster of 8) clusters run at a time, and
+// with the machine full a step at NB = 24 measured 1.66 x a step at NB = 16 (the DSMEM exchange grows with NB and clusters
+// sharing a GPC share its bandwidth): NB = 24 pays where it saves a whole wave — B = 121 .. 168 (16 .. 22 clusters = two
+// waves at NB = 16, one at NB = 24: predictor -10 % at B = 128) — and loses elsewhere (B = 256: +6 %).  NB = 8 only for
+// B <= 16: beyond 4 clusters it measured slower (profiles/r02_ab_lstm_forms.txt).
 // lstm_impl 3 = W_hh operand in shared memory (A/B baseline).
+static int lstm_pick_nb(int B) {
+  if (B <= 16) return 8;
+  int best = 16;
+  long best_cost = -1;
+  for (int nb : {16, 24}) {
+    const long clusters = 2L * cdiv(B, nb), waves = (clusters + g_lstm_max_clusters - 1) / g_lstm_max_clusters;
+    const long cost = waves * (nb == 24 ? 166 : 100);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nb; }
+  }
+  return best;
+}
 static void launch_lstm_tc(stz_handle* H, cudaStream_t st, const float* G, const float* whh, const int* lens, const int* perm,
                            float* out, int B, int T) {
   if (H->lstm_impl == 3) {
     launch_k(lstm_tc_kernel<false, 16>, dim3(cdiv(B, 16) * LC_CS, 2), lt_threads(16), lt_smem_bytes(false, 16), st, G, whh, lens, perm, out, B, T);
     return;
   }
-  const int nb = H->lstm_nb != 0 ? H->lstm_nb : (B <= 16 ? 8 : 16);
+  const int nb = H->lstm_nb != 0 ? H->lstm_nb : lstm_pick_nb(B);
   if (nb == 8) launch_k(lstm_tc_kernel<true, 8>, dim3(cdiv(B, 8) * LC_CS, 2), lt_threads(8), lt_smem_bytes(true, 8), st, G, whh, lens, perm, out, B, T);
+  else if (nb == 24) launch_k(lstm_tc_kernel<true, 24>, dim3(cdiv(B, 24) * LC_CS, 2), lt_threads(24), lt_smem_bytes(true, 24), st, G, whh, lens, perm, out, B, T);
   else launch_k(lstm_tc_kernel<true, 16>, dim3(cdiv(B, 16) * LC_CS, 2), lt_threads(16), lt_smem_bytes(true, 16), st, G, whh, lens, perm, out, B, T);
 }
 
 // Max co-resident 8-CTA clusters of the BiLSTM recurrence kernel on the current device (diagnostic).
 extern "C" int stz_debug_max_lstm_clusters(void) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(LC_CS * 64, 2); cfg.blockDim = dim3(lt_threads(16)); cfg.dynamicSmemBytes = lt_smem_bytes(true, 16);
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = LC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  int n = -1;
   if (init_kernel_attrs() != cudaSuccess) return -2;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<true, 16>, &cfg) != cudaSuccess) return -1;
-  return n;
+  return g_lstm_max_clusters;
 }
 
 extern "C" int stz_profile_read(stz_handle* H, int cls, double* ms, double* work, int64_t* launches) {

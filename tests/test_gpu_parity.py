@@ -112,10 +112,10 @@ def test_predict_duration_vs_golden(path, name):
     assert bool((d[~m] == 0).all()) and bool((d[m] >= 1).all()) and int(d.max()) <= CFG.max_dur
 
 
-@pytest.mark.parametrize("knobs", [{"lstm_nb": 8}, {"lstm_nb": 16}, {"lstm_impl": 3}], ids=["nb8", "nb16", "w_smem"])
-@pytest.mark.parametrize("B", [5, 21])
+@pytest.mark.parametrize("knobs", [{"lstm_nb": 8}, {"lstm_nb": 16}, {"lstm_nb": 24}, {"lstm_impl": 3}], ids=["nb8", "nb16", "nb24", "w_smem"])
+@pytest.mark.parametrize("B", [5, 29])
 def test_lstm_forms_vs_oracle(path, oracle, knobs, B):
-    """Every form of the tcgen05 BiLSTM recurrence (8 / 16 sequences per cluster, W_hh in tensor / shared memory) against
+    """Every form of the tcgen05 BiLSTM recurrence (8 / 16 / 24 sequences per cluster, W_hh in tensor / shared memory) against
     the oracle on a ragged batch (packed-sequence semantics, a partial last cluster), and bit-identical to each other."""
     T = 40
     inp = stz.synthetic_inputs(CFG, B, T, steps=1, seed=4321)

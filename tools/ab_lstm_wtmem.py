@@ -4,12 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import styletts_zs_b200 as stz
 cfg = stz.DEFAULT
 path = stz.StyleTTSZSPath(cfg, stz.init_weights(cfg, 0))
-for B, T in ((64, 64), (72, 64), (512, 128)):
+for B, T in ((64, 64), (128, 64), (256, 128), (512, 128)):
     inp = stz.synthetic_inputs(cfg, B, T, steps=1, seed=7)
     style = (0.7 * torch.randn(B, cfg.n_style, cfg.d_style, generator=torch.Generator().manual_seed(5))).cuda()
     te = inp["text_emb"].cuda()
     outs = {}
-    forms = {"w_tmem nb16": {"lstm_nb": 16}, "w_tmem nb8": {"lstm_nb": 8}, "w_smem nb16": {"lstm_impl": 3}}
+    forms = {"w_tmem nb16": {"lstm_nb": 16}, "w_tmem nb24": {"lstm_nb": 24}, "w_tmem auto": {}, "w_smem nb16": {"lstm_impl": 3}}
     for rnd in range(2):
         for name, kn in forms.items():
             path.set_option("lstm_nb", 0); path.set_option("lstm_impl", 0)
