@@ -350,7 +350,8 @@ struct AttnTcParams {
   float scale_log2;
   int single;              // single-branch row layout (guidance-conditioned student): query row = b * n_style + token, only tile
                            // rows 0..63 (the "conditional" half) are loaded and written; the unit is still (utterance, head)
-  int box2;                // the Q (self: Q / K / V) tensor map is (column, token, branch) with a box of 64 x 64 x branches: ONE
+  int box2;                // 2: self-attention, tmT is a 4-D (column, token, branch, part) view: ONE box lands Q | K | V;
+                           // 1: the Q (self: Q / K / V) tensor map is (column, token, branch) with a box of 64 x 64 x branches: ONE
                            // TMA instruction per operand lands both branches de-interleaved (TMA issues serialise at ~200
                            // cycles each per SM: tools/att_trace.py); 0: (column, branch, token) map, one box per branch
 };
@@ -368,6 +369,11 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const void* tmap, 
 __device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -442,7 +448,9 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
     if (parts & 2) {
       if (warp == 0) mbar_expect_tx(&bar_full[buf], tx_bytes);   // the whole unit's bytes, armed with its first part
       if (p.self) {
-        if (p.box2) {
+        if (p.box2 == 2) {         // Q | K | V tiles in one 4-D box (tmT: column, token, branch, part)
+          if (warp == 0) tma_load_4d_u32(qs, &tmT, bar, hc, t0, 0, 0);
+        } else if (p.box2) {
           if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, t0, 0);
           else if (warp == 2) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, t0, 0);
         } else {
@@ -462,7 +470,8 @@ __global__ void __launch_bounds__(256, 2) attention_tc2_kernel(const __grid_cons
       }
     }
     if (parts & 1) {
-      if (p.box2) {
+      if (p.box2 == 2 && p.self) {
+      } else if (p.box2) {
         if (warp == 6) tma_load_3d_u32(qs, &tmQ, bar, hc, t0, 0);
       } else {
         if (warp == 6) tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);
@@ -726,7 +735,9 @@ __global__ void __launch_bounds__(128, 4) attention_tc4_kernel(const __grid_cons
     if (parts & 2) {
       if (warp == 0) mbar_expect_tx(&bar_full, tx_bytes);
       if (p.self) {
-        if (p.box2) {
+        if (p.box2 == 2) {         // Q | K | V tiles in one 4-D box (tmT: column, token, branch, part)
+          if (warp == 0) tma_load_4d_u32(qs, &tmT, bar, hc, t0, 0, 0);
+        } else if (p.box2) {
           if (warp == 0) tma_load_3d_u32(ks, &tmQ, bar, p.col_k + hc, t0, 0);
           else if (warp == 1) tma_load_3d_u32(vs, &tmQ, bar, p.col_v + hc, t0, 0);
         } else {
@@ -754,7 +765,8 @@ __global__ void __launch_bounds__(128, 4) attention_tc4_kernel(const __grid_cons
     }
     if (parts & 1) {
       if (warp == 3) {
-        if (p.box2) {
+        if (p.box2 == 2 && p.self) {
+        } else if (p.box2) {
           tma_load_3d_u32(qs, &tmQ, bar, hc, t0, 0);
         } else {
           tma_load_3d_u32(qs, &tmQ, bar, hc, 0, t0);

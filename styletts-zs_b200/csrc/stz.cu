@@ -1232,9 +1232,19 @@ static int attention(stz_handle* H, cudaStream_t st, const AttnParams& ap, int B
       }
     }
     tt = tq;
+    // self-attention with Q | K | V side by side in one buffer: a 4-D view (column, token, branch, part) whose box
+    // 64 x 64 x 2 x 3 lands all three operand tiles with ONE TMA instruction (48 KB; TMA issues serialise per SM)
+    bool box3 = false;
+    if (self && box2 && nbr == 2 && (int)(ap.seg[0].k - ap.q) == dm && (int)(ap.seg[0].v - ap.q) == 2 * dm) {
+      const cuuint64_t gd4[4] = {(cuuint64_t)dm, (cuuint64_t)B * n_style, 2, 3};
+      const cuuint64_t gs4[3] = {(cuuint64_t)ap.ldq * 2 * 2, (cuuint64_t)ap.ldq * 2, (cuuint64_t)dm * 2};
+      const cuuint32_t bx4[4] = {64, 64, 2, 3};
+      box3 = make_tmap_nd(&tt, ap.q, 4, gd4, gs4, bx4) == 0;
+      if (!box3) tt = tq;
+    }
     AttnTcParams tp_{};
     tp_.out = ap.out; tp_.ldo = ap.ldo; tp_.n_q = ap.n_q; tp_.n_heads = H->cfg.n_heads; tp_.n_units = B * H->cfg.n_heads;
-    tp_.self = self ? 1 : 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single; tp_.box2 = box2 ? 1 : 0;
+    tp_.self = self ? 1 : 0; tp_.n_style = n_style; tp_.scale_log2 = ap.scale_log2; tp_.single = ap.single; tp_.box2 = box3 ? 2 : (box2 ? 1 : 0);
     if (self) {
       tp_.col_k = (int)(ap.seg[0].k - ap.q); tp_.col_v = (int)(ap.seg[0].v - ap.q);
     } else {
