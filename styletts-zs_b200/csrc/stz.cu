@@ -428,15 +428,18 @@ static int launch_gemm2(stz_handle* H, cudaStream_t st, const bf16* A, int lda, 
   return fail(H, STZ_E_SHAPE, "gemm N=%d is not a multiple of 128", p.N);
 }
 
-// ---- fused GEMM + residual/pos + AdaLN (gemm_ln3.cuh): N = d_model = 512 ------------------------------
-// residual tile staged in the operand ring (gemm_ln3.cuh)
-// Rows per CTA pair: 128, or 96 when 96-row tiles still fit one wave of num_sms / 2 pairs: cfg2's 6400 rows -> 67 tiles on 134
-// SMs instead of 50 tiles on 100 (the MMAs keep M = 128; the shared-memory-bound epilogue passes shrink with the rows).
-// Whole epilogue warps (32 rows) are what is saved, so only multiples of 32 pay: 72- or 88-row tiles cost what 96-row tiles
-// cost, 64-row tiles need two waves from 37 tiles on (tools/ab_tile_rows.py, profiles/r02_ab_tile_rows.txt).
+// ---- fused GEMM + residual/pos + AdaLN (gemm_ln3.cuh): N = d_model = 512, residual tile staged in the operand ring ----------
+// Rows per CTA pair of gemmln3_kernel: the smallest multiple of 8 (the swizzle atom) with which the row blocks still fill
+// ONE wave of pairs — cfg2's 6400 rows: 88-row blocks on 73 pairs = 146 SMs instead of 128-row blocks on 50 pairs = 100 SMs.
+// The MMAs keep M = 128; what shrinks with the rows is the shared-memory-bound epilogue (whole 32-row warps drop out below
+// 97 / 65 / 33 rows) and the TMA traffic of the residual / operand tiles.  Measured (tools/ab_tile_rows2.py,
+// profiles/r02_ab_tile_rows.txt): B = 64: 88 = 96 rows, -2 % vs 128; B = 72: 104 rows -1.7 % vs 128; B = 48: 72 rows -0.6 % vs 96,
+// -4.7 % vs 128.  More row blocks than pairs (two waves and more): 128 rows.
 static int gemmln3_tile_rows(int M) {
   const int pairs = g_num_sms / 2;
-  return (cdiv(M, 96) <= pairs && 2 * cdiv(M, GEMM_BM) > pairs) ? 96 : GEMM_BM;
+  if (cdiv(M, GEMM_BM) > pairs) return GEMM_BM;
+  const int tr = (cdiv(M, pairs) + 7) / 8 * 8;
+  return tr < 8 ? 8 : (tr > GEMM_BM ? GEMM_BM : tr);
 }
 
 template <int MODE>

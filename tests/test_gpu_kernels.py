@@ -157,7 +157,7 @@ def test_fused_gemm_positional_adaln(path, M):
     assert rel(h, hp) < 2e-5 and rel(u, u_ref) < 5e-3
 
 
-@pytest.mark.parametrize("rows", [64, 72, 88, 96, 120])
+@pytest.mark.parametrize("rows", [8, 24, 64, 72, 88, 96, 104, 120])
 @pytest.mark.parametrize("M,K,split3", [(6400, 512, False), (1000, 2048, True)])
 def test_fused_gemm_residual_adaln_tile_rows(path, rows, M, K, split3):
     """gemmln3_kernel with fewer than 128 rows per CTA pair (the heuristic picks 88 at cfg2's 6400 rows: 146 SMs busy
