@@ -406,9 +406,9 @@ def config_legs(torch, stz, path, cfg, flush):
 
 def sharded_leg(torch, stz, path, cfg, rank, world, local_rank, barrier, reps=3):
     """Strong scaling through the sharder: one global variable-length batch, length-sorted round-robin over the ranks, the
-    per-rank host-buffer call, results gathered in a shared host mapping, re-ordered on rank 0 — all timed."""
+    per-rank host-buffer call, results gathered in a shared host mapping, every rank re-ordering its own rows — all timed."""
     Bg, Tg, steps = SHARDED["B"], SHARDED["T"], SHARDED["steps"]
-    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))     # torchrun pins OMP_NUM_THREADS=1: rank 0's re-ordering copy is host work
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))     # torchrun pins OMP_NUM_THREADS=1: the re-ordering copy is host work
     g = torch.Generator().manual_seed(4321)
     lens = torch.randint(SHARDED["lens"][0], SHARDED["lens"][1] + 1, (Bg,), generator=g)
     shards = stz.shard_utterances(lens.tolist(), world)
@@ -437,12 +437,13 @@ def sharded_leg(torch, stz, path, cfg, rank, world, local_rank, barrier, reps=3)
         o_style, o_dur = out.slab(n, t)
         compute(text, mask, prompt, None, None, out_style=o_style, out_dur=o_dur)
         t1 = time.perf_counter()
-        barrier()
+        out.scatter_own(shards, shard_T)
         t2 = time.perf_counter()
+        barrier()
         if rank == 0:
-            res = out.assemble(shards, shard_T)
+            res = out.ordered()
         t3 = time.perf_counter()
-        times.append(t3 - t0); t_compute.append(t1 - t0); t_asm.append(t3 - t2)
+        times.append(t3 - t0); t_compute.append(t1 - t0); t_asm.append(t2 - t1)
     ok = None
     if rank == 0:
         style, dur = res
@@ -457,13 +458,15 @@ def sharded_leg(torch, stz, path, cfg, rank, world, local_rank, barrier, reps=3)
     return {"workload": f"ONE global batch of {Bg} utterances, text lengths uniform in [{SHARDED['lens'][0]}, {SHARDED['lens'][1]}] (padding "
                         f"masks), {steps}-step CFG student + duration predictor, length-sorted round-robin over {world} rank(s)",
             "scaling": "strong", "global_batch": Bg, "per_rank_batch": n, "value": Bg / total, "unit": UNIT, "seconds": total,
-            "per_rank_call_seconds_max": comp, "rank0_reorder_seconds": asm,
+            "per_rank_call_seconds_max": comp, "per_rank_reorder_seconds_max": asm,
             "host_gather": "every rank's D2H lands in its slab of one /dev/shm mapping registered as pinned memory "
-                           f"(pinned={out.pinned}); barrier; rank 0 re-orders into the caller's utterance order "
-                           f"({Bg * cfg.n_style * cfg.d_style * 4 / 1e6:.0f} MB of style codes + durations): no collective, no pickling",
+                           f"(pinned={out.pinned}); every rank copies ITS rows to their places in the caller's utterance order "
+                           f"inside the same mapping ({Bg * cfg.n_style * cfg.d_style * 4 / 1e6:.0f} MB of style codes + durations "
+                           "in total, 1 / world of it per rank, in parallel); barrier; rank 0 returns views: no collective, no "
+                           "pickling, no serial re-ordering pass",
             "h2d_bytes_per_rank": int(text.numel() * 4 + prompt.numel() * 4 + mask.numel()),
             "d2h_bytes_per_rank": int(n * cfg.n_style * cfg.d_style * 4 + n * t * 4), "results_ok": ok,
-            "timing": "wall clock around [per-rank blocking stz_synthesize_host into the shared slab; barrier; rank-0 re-order], "
+            "timing": "wall clock around [per-rank blocking stz_synthesize_host into the shared slab; per-rank re-order; barrier], "
                       f"best of {reps}, max over ranks; inputs are each rank's own pinned host tensors (a server hands every "
                       "rank its utterances), noise drawn on the device from global utterance indices"}
 

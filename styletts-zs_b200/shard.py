@@ -86,9 +86,11 @@ def synthesize_sharded(compute: Callable[..., Tuple[torch.Tensor, torch.Tensor]]
 
 class SharedHostOutputs:
     """The host-side gather without a gather: one /dev/shm-backed mapping per job, shared by the ranks of one box.  Rank r's
-    device->host copies land directly in slab r (the mapping is registered as pinned memory when CUDA is present), so
-    after a barrier rank 0 holds every rank's results in host memory — no collective, no pickling, no extra copy but the
-    final re-ordering into the caller's utterance order (``assemble``).
+    device->host copies land directly in slab r (the mapping is registered as pinned memory when CUDA is present); every
+    rank then places ITS OWN rows at their positions in the caller's utterance order inside the same mapping
+    (``scatter_own``: the re-ordering is host work of B / world_size rows per rank, in parallel), and after a barrier rank 0
+    holds the complete, ordered result (``ordered``) — no collective, no pickling, no serial re-ordering pass.
+    (``assemble`` is the older form: rank 0 re-orders every slab by itself.)
 
     ``tag`` names the job and must be the same on every rank (bench.py uses MASTER_PORT); ``barrier`` is a callable that
     synchronises the ranks (``dist.barrier`` of a gloo / nccl group; a no-op for world_size 1)."""
@@ -98,18 +100,23 @@ class SharedHostOutputs:
         self.rank, self.world, self.B, self.T, self.K, self.Ds = rank, world_size, B, T, K, Ds
         self.n_max = math.ceil(B / world_size)
         self._paths = [f"/dev/shm/stz_{tag}_style", f"/dev/shm/stz_{tag}_dur"]
-        n_style, n_dur = world_size * self.n_max * K * Ds, world_size * self.n_max * T
+        n_slab_style, n_slab_dur = world_size * self.n_max * K * Ds, world_size * self.n_max * T
+        n_style, n_dur = n_slab_style + B * K * Ds, n_slab_dur + B * T          # slabs, then the ordered result
         if rank == 0:
             for path, nbytes in zip(self._paths, (4 * n_style, 4 * n_dur)):
                 with open(path, "wb") as f:
                     f.truncate(nbytes)
         barrier()
-        self.style = torch.from_file(self._paths[0], shared=True, size=n_style, dtype=torch.float32).view(world_size, self.n_max, K, Ds)
-        self.dur = torch.from_file(self._paths[1], shared=True, size=n_dur, dtype=torch.int32).view(world_size, self.n_max * T)
+        self._map_style = torch.from_file(self._paths[0], shared=True, size=n_style, dtype=torch.float32)
+        self._map_dur = torch.from_file(self._paths[1], shared=True, size=n_dur, dtype=torch.int32)
+        self.style = self._map_style[:n_slab_style].view(world_size, self.n_max, K, Ds)
+        self.dur = self._map_dur[:n_slab_dur].view(world_size, self.n_max * T)
+        self.style_all = self._map_style[n_slab_style:].view(B, K, Ds)          # caller's utterance order
+        self.dur_all = self._map_dur[n_slab_dur:].view(B, T)
         self._registered = []
         if pin and torch.cuda.is_available():
             rt = torch.cuda.cudart()
-            for t in (self.style, self.dur):
+            for t in (self.style, self.dur):     # only the slabs are DMA targets
                 if int(rt.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)) == 0:
                     self._registered.append(t.data_ptr())
         self.pinned = len(self._registered) == 2
@@ -118,6 +125,23 @@ class SharedHostOutputs:
     def slab(self, n: int, t: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """This rank's output buffers: style [n,K,Ds] fp32 and durations [n,t] int32 (contiguous)."""
         return self.style[self.rank, :n], self.dur[self.rank, :n * t].view(n, t)
+
+    def scatter_own(self, shards: List[List[int]], shard_T: List[int]) -> None:
+        """This rank's rows -> their positions in the caller's utterance order (durations zero-padded to T)."""
+        idx = shards[self.rank]
+        if not idx:
+            return
+        ii = torch.tensor(idx, dtype=torch.long)
+        n, t = len(idx), shard_T[self.rank]
+        self.style_all.index_copy_(0, ii, self.style[self.rank, :n])
+        rows = torch.zeros(n, self.T, dtype=torch.int32)
+        rows[:, :t] = self.dur[self.rank, :n * t].view(n, t)
+        self.dur_all.index_copy_(0, ii, rows)
+
+    def ordered(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """After every rank's ``scatter_own`` and a barrier: (style [B,K,Ds], dur [B,T]) in the caller's order — views of the
+        shared mapping (valid until ``close`` or the next batch; ``.clone()`` to keep them)."""
+        return self.style_all, self.dur_all
 
     def assemble(self, shards: List[List[int]], shard_T: List[int]) -> Tuple[torch.Tensor, torch.Tensor]:
         """Rank 0, after the barrier: results in the caller's utterance order (durations zero-padded to T)."""
@@ -138,7 +162,7 @@ class SharedHostOutputs:
             for ptr in self._registered:
                 rt.cudaHostUnregister(ptr)
             self._registered = []
-        self.style = self.dur = None
+        self.style = self.dur = self.style_all = self.dur_all = self._map_style = self._map_dur = None
         if barrier is not None:
             barrier()
         if self.rank == 0:
@@ -155,7 +179,8 @@ def synthesize_sharded_shm(compute: Callable[..., Tuple[torch.Tensor, torch.Tens
     """The product form of ``synthesize_sharded``: this rank's shard (``shard_inputs`` = ``take_shard(inputs, shards[rank])``,
     prepared by the caller: in a server every rank receives its own utterances) runs through
     ``compute(text_emb, text_mask, prompt_feats, prompt_mask, noise, out_style=..., out_dur=...)`` with the output buffers
-    inside the shared host mapping; a barrier; rank 0 re-orders.  Returns (style [B,K,Ds], dur [B,T]) on rank 0, None elsewhere."""
+    inside the shared host mapping; every rank scatters its own rows into the ordered result; a barrier.  Returns
+    (style [B,K,Ds], dur [B,T]) on rank 0 — views of the shared mapping, see ``SharedHostOutputs.ordered`` — and None elsewhere."""
     idx = shards[out.rank]
     if idx:
         o_style, o_dur = out.slab(len(idx), shard_T[out.rank])
@@ -165,7 +190,8 @@ def synthesize_sharded_shm(compute: Callable[..., Tuple[torch.Tensor, torch.Tens
         if res is not None and res[0] is not None and res[0].data_ptr() != o_style.data_ptr():   # a compute without out= support
             o_style.copy_(res[0])
             o_dur.copy_(res[1])
+    out.scatter_own(shards, shard_T)
     barrier()
     if out.rank != 0:
         return None
-    return out.assemble(shards, shard_T)
+    return out.ordered()

@@ -51,7 +51,7 @@ def _worker(rank, world, port, q):
     compute = _oracle_compute(cfg, w)
     res = stz.synthesize_sharded(compute, inp, rank, world)
     res_seeded = stz.synthesize_sharded(compute, _seeded(inp), rank, world)   # on-"device" noise from global indices
-    # the product form: outputs land in a shared host mapping (no collective on the data path), rank 0 re-orders
+    # the product form: outputs land in a shared host mapping (no collective on the data path), every rank re-orders its own rows
     shards = stz.shard_utterances(inp["lens"].tolist(), world)
     shard_T = [max(int(inp["lens"][i]) for i in sh) if sh else 1 for sh in shards]
     out = stz.SharedHostOutputs(f"test{port}", 5, 14, cfg.n_style, cfg.d_style, rank, world, dist.barrier)
@@ -61,6 +61,9 @@ def _worker(rank, world, port, q):
     res_shm = stz.synthesize_sharded_shm(compute_out, stz.take_shard(inp, shards[rank]) if shards[rank] else None, shards,
                                          shard_T, out, dist.barrier)
     if rank == 0:
+        # the ordered result every rank scattered into == rank 0 re-ordering the slabs by itself (the older form)
+        a_style, a_dur = out.assemble(shards, shard_T)
+        assert torch.equal(a_style, res_shm[0]) and torch.equal(a_dur, res_shm[1])
         q.put((res[0], res[1], res_seeded[0], res_seeded[1], res_shm[0].clone(), res_shm[1].clone()))
     else:
         assert res is None and res_seeded is None and res_shm is None
