@@ -34,6 +34,9 @@ def _battery(p):
     out.append(p.sample_style(inp["text_emb"], inp["prompt_feats"], 2, 2.0, text_mask=inp["text_mask"], seed=5, sampler="guided"))
     style = 0.7 * torch.randn(3, CFG.n_style, CFG.d_style, generator=torch.Generator().manual_seed(1))
     out += list(p.predict_prosody(inp["text_emb"], style, text_mask=inp["text_mask"], max_frames=500))[:3]
+    inp = stz.synthetic_inputs(CFG, 130, 24, steps=1, seed=6, var_len=(5, 24))                       # 24 sequences per BiLSTM cluster
+    style = 0.7 * torch.randn(130, CFG.n_style, CFG.d_style, generator=torch.Generator().manual_seed(2))
+    out.append(p.predict_duration(inp["text_emb"], style, text_mask=inp["text_mask"]))
     a = stz.synthetic_inputs(CFG, 4, 32, steps=2, seed=5)                                            # pipelined host slots
     o0 = p.synthesize_host(a["text_emb"], a["prompt_feats"], 2, 2.0, noise=a["noise"], slot=0)
     o1 = p.synthesize_host(a["text_emb"], a["prompt_feats"], 2, 2.0, seed=7, slot=1)
